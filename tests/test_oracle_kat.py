@@ -1,0 +1,259 @@
+"""Pin the CPU oracle on every known-answer vector the reference's own tests hold for the hot
+path.  Each test names the reference test it reproduces."""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+
+# stft.rs:173-196 stft_works -- exact
+def test_stft_works(orc):
+    x = np.zeros(4, np.float32)
+    x[2] = 1.0
+    got = orc.perform_stft(x, 4, 2, 4)
+    want = np.array([[0, 0, 0], [0.25, -0.25, 0.25], [0.25, -0.25, 0.25]], np.complex64)
+    assert got.shape == (3, 3)
+    assert np.array_equal(got, want)
+
+
+# stft.rs:198-203 stft_short_wav -- shape only in the reference
+def test_stft_short_wav(orc):
+    x = np.zeros(2, np.float32)
+    x[1] = 1.0
+    got = orc.perform_stft(x, 8, 6, 8)
+    # padded length 2 + 2*4 = 10 -> (10-8)/6+1 = 1 frame, 5 bins
+    assert got.shape == (1, 5)
+    assert np.all(np.isfinite(got.view(np.float32)))
+
+
+# windows.rs:88-91 hann_window_works -- exact
+def test_hann_window_works(orc):
+    assert np.array_equal(orc.hann(4, False), np.array([0, 0.5, 1.0, 0.5], np.float32))
+
+
+# utils.rs:166-176 pad_works (reflect leg; multi-wrap)
+def test_pad_works(orc):
+    got = orc.pad_reflect([1, 2, 3], 3, 4)
+    assert np.array_equal(got, np.array([2, 3, 2, 1, 2, 3, 2, 1, 2, 3], np.float32))
+
+
+def test_pad_reflect_matches_numpy(orc):
+    rng = np.random.default_rng(1)
+    for n in (2, 3, 5, 17):
+        x = rng.standard_normal(n).astype(np.float32)
+        for pl, pr in ((0, 0), (1, 0), (0, 1), (n - 1, n - 1), (3 * n, 2 * n + 1)):
+            assert np.array_equal(orc.pad_reflect(x, pl, pr), np.pad(x, (pl, pr), mode="reflect"))
+
+
+# src-common/src/lib.rs:168-174 mel_hz_convert -- 1e-14 in f64
+def test_mel_hz_convert(orc):
+    assert abs(orc.mel_from_hz(100.0, f64=True) - 1.5) < 1e-14
+    assert abs(orc.mel_from_hz(1100.0, f64=True) - 16.38629404765444) < 1e-14
+    assert abs(orc.mel_to_hz(1.0, f64=True) - 66.66666666666667) < 1e-14
+    assert abs(orc.mel_to_hz(16.0, f64=True) - 1071.1702874944676) < 1e-14
+
+
+# src-common/src/lib.rs:176-202 mel_works -- first filter of (24000, 2048, 80), eps 1e-8 in f64
+def test_mel_works(orc):
+    sr, n_fft, n_mel = 24000, 2048, 80
+    ans = [0.0, 0.07852016499598029, 0.15704032999196058, 0.23556049498794085, 0.25,
+           0.17147983500401973, 0.09295967000803942, 0.014439505012059144, 0.0]
+    fb = orc.mel_fb(sr, n_fft, n_mel, f64=True)
+    assert fb.shape == (n_fft // 2 + 1, n_mel)
+    col0 = fb[:, 0]
+    want = np.zeros(n_fft // 2 + 1)
+    want[: len(ans)] = ans
+    assert np.max(np.abs(col0 - want)) < 1e-8
+    # f32 bank agrees with the f64 one to f32 precision
+    fb32 = orc.mel_fb(sr, n_fft, n_mel)
+    assert np.max(np.abs(fb32 - fb)) < 5e-6  # f32 mel-edge rounding moves weights by ~1e-6
+
+
+# src-common/src/lib.rs:204-232 mel_default_works
+@pytest.mark.parametrize("sr", [400, 800, 1000, 2000, 4000, 8000, 16000, 24000, 44100, 48000, 88200, 96000])
+def test_mel_default_works(orc, sr):
+    for e in range(5, 15):
+        n_fft = 2 ** e
+        fb = orc.mel_fb_default(sr, n_fft)
+        assert np.all(fb.sum(axis=0) > 0), (sr, n_fft)
+        if fb.shape[1] == fb.shape[0]:
+            continue
+        fail = orc.mel_fb(sr, n_fft, fb.shape[1] + 1)
+        assert np.any(fail.sum(axis=0) == 0), (sr, n_fft, fb.shape[1])
+
+
+def test_mel_fb_rows_sum_to_one_and_sparse(orc):
+    fb = orc.mel_fb_default(48000, 2048)
+    assert fb.shape == (1025, 347)
+    assert np.allclose(fb.sum(axis=0), 1.0, atol=1e-5)
+    assert np.count_nonzero(fb) < 3 * 1025  # <= ~2 filters per FFT bin
+
+
+# decibel.rs:257-270 scalar_dB_conversions_round_trip
+def test_scalar_dB_round_trip(orc):
+    assert abs(orc.dB_scalar(0.25) - (-12.0412)) < 1e-4
+    assert abs(orc.dB_scalar(0.25, factor=10.0) - (-6.0206)) < 1e-4
+
+
+# decibel.rs:272-282 scalar_dB_conversion_handles_floor_and_invalid_input
+def test_scalar_dB_floor_and_invalid(orc):
+    assert orc.dB_scalar(0.0) == -math.inf
+    assert orc.dB_scalar(0.0, factor=10.0) == -math.inf
+    assert math.isnan(orc.dB_scalar(-1.0))
+    assert math.isnan(orc.dB_scalar(math.nan, factor=10.0))
+    assert abs(orc.dB_scalar(1.0, ref=2.0) - (-6.0206)) < 1e-4
+
+
+# decibel.rs:284-301 array_dB_inplace_conversion_matches_scalar_rules (amp leg, Value ref)
+def test_array_dB_inplace(orc):
+    a = np.array([1.0, 0.5, 0.0, -1.0, np.nan], np.float32)
+    orc.dB_from_amp_inplace(a, 1.0, 1e-3)
+    assert a[0] == 0.0
+    assert abs(a[1] - (-6.0206)) < 1e-4
+    assert abs(a[2] - (-60.0)) < 1e-5
+    assert math.isnan(a[3]) and math.isnan(a[4])
+
+
+# drawing.rs:43-56 spectrogram_to_img_transposes_and_clamps_dB_values -- exact
+def test_spectrogram_to_img(orc):
+    spec = np.array([[-100.0, -50.0, 0.0], [100.0, -200.0, -25.0]], np.float32)
+    img = orc.spec_to_img(spec, (0, 4), (-100.0, 0.0), 4)
+    assert img.shape == (4, 2)
+    assert img.tolist() == [[16384, 65535], [40960, 0], [65535, 53247], [0, 0]]
+
+
+def test_spectrogram_to_img_all_neg_inf(orc):
+    spec = np.full((3, 2), -np.inf, np.float32)
+    img = orc.spec_to_img(spec, (0, 2), (-np.inf, -np.inf), 258)
+    assert img.shape == (2, 3) and not img.any()
+
+
+def _tile_fields(b):
+    rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
+    vals = np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)
+    return rev, bins, spb, idx, zero, vals
+
+
+# render_tiles.rs:408-416
+def test_waveform_tile_min_max_representative(orc):
+    b = orc.encode_waveform_tile([-1.0, 0.0, 0.5, 1.0], 3, 1, 0)
+    rev, bins, spb, idx, zero, v = _tile_fields(b)
+    assert (rev, bins, spb, idx, zero) == (3, 2, 2, 0, 0)
+    assert v[0].tolist() == [-1.0, 0.0, -0.5]
+    assert v[1].tolist() == [0.5, 1.0, 0.75]
+
+
+# render_tiles.rs:418-423
+def test_waveform_tile_partial_last_tile(orc):
+    b = orc.encode_waveform_tile(np.full(1025, 0.25, np.float32), 1, 0, 1)
+    assert _tile_fields(b)[1] == 1
+    assert len(b) == 24 + 12
+
+
+# render_tiles.rs:425-433
+def test_waveform_tile_large_bin_stats(orc):
+    wav = np.arange(64, dtype=np.float32) - 32.0
+    b = orc.encode_waveform_tile(wav, 1, 6, 0)
+    rev, bins, spb, idx, zero, v = _tile_fields(b)
+    assert bins == 1 and spb == 64
+    assert v[0].tolist() == [-32.0, 31.0, -0.5]
+
+
+def test_waveform_tile_out_of_range(orc):
+    b = orc.encode_waveform_tile(np.zeros(10, np.float32), 7, 2, 5)
+    assert len(b) == 24 and _tile_fields(b)[1] == 0
+
+
+# simd.rs:1111-1138 test_find_min_max_separate (incl. +-inf, empty)
+def test_find_min_max(orc):
+    assert orc.find_min_max([]) == (math.inf, -math.inf)
+    assert orc.find_min_max([3.0]) == (3.0, 3.0)
+    x = np.array([1.0, -2.0, np.inf, 5.0, -np.inf, 0.0] * 7, np.float32)
+    assert orc.find_min_max(x) == (-math.inf, math.inf)
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(1000).astype(np.float32)
+    assert orc.find_min_max(y) == (float(y.min()), float(y.max()))
+
+
+# simd.rs:1274-1295 test_sum
+def test_sum(orc):
+    assert orc.sum_simd_order([], 0) == 0.0
+    x = np.arange(1, 101, dtype=np.float32)
+    for al in range(8):
+        assert orc.sum_simd_order(x, al) == 5050.0
+
+
+# spectrogram.rs:57-98 framing params
+def test_framing_params(orc):
+    assert orc.framing_params(40.0, 48000, 4, 1) == (480, 1920, 2048)
+    assert orc.framing_params(40.0, 44100, 4, 1) == (441, 1764, 2048)
+    assert orc.framing_params(2048 / 48.0, 48000, 4, 1) == (512, 2048, 2048)
+    assert orc.framing_params(2048 / 48.0, 48000, 8, 1) == (256, 2048, 2048)
+    assert orc.framing_params(16384 / 96.0, 96000, 16, 1) == (1024, 16384, 16384)
+    assert orc.framing_params(40.0, 48000, 4, 2) == (480, 1920, 4096)
+    assert orc.framing_params(40.0, 22050, 4, 1) == (221, 884, 1024)  # 220.5 rounds half away
+
+
+def test_three_piece_framing_equals_closed_form(orc):
+    """The product uses T = 1 + (N + 2*(W//2) - W)//H and reflect indexing; the oracle keeps the
+    reference's front/mid/back construction.  They must agree frame for frame (N >= 2, W >= 3:
+    W == 2 makes the reference reflect-pad a 1-sample slice, which leaves memory uninitialised)."""
+    rng = np.random.default_rng(5)
+    cases = [(n, w, h) for w in (3, 4, 5, 8, 9, 16, 31) for h in (1, 2, 3, 4, 5, 8, 16, 33)
+             for n in (2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 64, 100, 257)
+             if h <= w]  # win = hop * t_overlap, so hop <= win always (spectrogram.rs:57-59)
+    for n, w, h in cases:
+        x = rng.standard_normal(n).astype(np.float32)
+        fr = orc.stft_frames(x, w, h)
+        T = orc.n_frames(n, w, h)
+        assert fr.shape[0] == T, (n, w, h)
+        idx = (np.arange(T)[:, None] * h + np.arange(w)[None, :] - w // 2)
+        per = 2 * (n - 1)
+        m = np.mod(idx, per)
+        m = np.where(m < n, m, per - m)
+        assert np.array_equal(fr, x[m]), (n, w, h)
+        assert orc.reflect_index(-1, n) == 1
+
+
+def test_truth_stft_matches_scipy(orc):
+    """Independent check of the f64 'truth' leg against scipy.fft.rfft."""
+    import scipy.fft
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(6000) * 0.3).astype(np.float32)
+    an = orc.Analyzer(48000, 2048 / 48.0, 4, 1, orc.LINEAR)
+    db, amp, pw = an.calc_spec_truth(x, want_amp=True, want_pow=True)
+    T = an.n_frames(x.size)
+    idx = np.arange(T)[:, None] * an.hop + np.arange(an.win)[None, :] - an.win // 2
+    per = 2 * (x.size - 1)
+    m = np.mod(idx, per)
+    m = np.where(m < x.size, m, per - m)
+    frames = x[m].astype(np.float64) * an.window.astype(np.float64)[None, :]
+    ref = scipy.fft.rfft(frames, n=an.n_fft, axis=1)
+    assert np.max(np.abs(np.abs(ref) - amp)) < 1e-15 + 1e-12 * np.max(np.abs(ref))
+    assert np.max(np.abs(np.abs(ref) ** 2 - pw)) < 1e-12 * np.max(pw)
+
+
+def test_f32_oracle_close_to_truth(orc):
+    rng = np.random.default_rng(4)
+    x = np.round(rng.standard_normal(20000) * 0.2 * 32768).clip(-32768, 32767).astype(np.float32) / 32768
+    for scale, n_mel in ((orc.LINEAR, 0), (orc.MEL, 128), (orc.MEL, 0)):
+        an = orc.Analyzer(48000, 40.0, 4, 1, scale, n_mel)
+        d32 = an.calc_spec(x)
+        d64 = an.calc_spec_truth(x)
+        assert d32.shape == d64.shape
+        assert np.max(np.abs(d32 - d64)) < 1e-3
+
+
+def test_zero_padded_window_centering(orc):
+    """win 1920 inside n_fft 2048: pad_left = 64 (stft.rs:35-39)."""
+    an = orc.Analyzer(48000, 40.0, 4, 1, orc.LINEAR)
+    assert (an.hop, an.win, an.n_fft) == (480, 1920, 2048)
+    x = np.zeros(4800, np.float32)
+    x[960] = 1.0  # tap i = 960 of frame 2 -> FFT index 64 + 960 = 1024 -> X[k] = w[960] * (-1)^k
+    _, st = an.calc_spec(x, want_stft=True)
+    w = an.window
+    k = np.arange(1025)
+    want = w[960] * np.where(k % 2 == 0, 1.0, -1.0)
+    assert np.allclose(st[2].real, want, atol=1e-9)
+    assert np.allclose(st[2].imag, 0, atol=1e-9)
