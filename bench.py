@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- STFT+mel+dB throughput (audio-hours/s) of the analysis hot path on N B200s.
+
+Workload (BASELINE.json configs[2], "C3"): 64 synthetic stereo tracks x 10 min at 48 kHz PER GPU
+(128 channels x 28.8 M samples = 14.75 GB f32), win 2048 / hop 512 Hann, 128-band mel, dB, global
+min/max (one 2-float NCCL max all-reduce across ranks) and u16 images.  A step = TrackManager's
+update_specs + update_spec_imgs over that batch = thb_spec_batch + thb_update_spec_imgs.
+
+  value : whole-job audio-hours/s with the PCM already resident in HBM (torch CUDA events on the
+          stream the kernels run on, max over ranks).
+  e2e   : the same metric through the C ABI with HOST buffers: pinned PCM is copied host->device and
+          the u16 images device->host inside the timed region, every step.
+  roofline / cpu_baseline / clocks / gpu_launches: see the task contract; DESIGN.md "Measurement".
+  --impl reference: the CPU restatement of the reference (oracle/) on all host threads.
+
+Launch: python bench.py --gpus 1            or
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SR = 48000
+N_TRACKS = 64
+N_CH = 2
+SECONDS = 600
+WIN_MS = 2048 / 48.0
+T_OVERLAP = 4
+N_MEL = 128
+DB_RANGE = 100.0
+CMAP_LEN = 258
+METRIC = "STFT+mel+dB throughput"
+UNIT = "audio-hours/s"
+
+
+def workload_name(scale: float) -> str:
+    s = "" if scale == 1.0 else f" (scaled x{scale:g})"
+    return (f"C3: {N_TRACKS} stereo tracks x {SECONDS // 60} min @48 kHz per GPU, win 2048 hop 512 Hann, "
+            f"mel {N_MEL} dB, global min/max + u16 images{s}")
+
+
+def track_flags(track: int) -> int:
+    # one track > 0 dBFS (max_dB clamp), one with a 1 s zero gap (-inf frames)  
+    return (1 if track == 1 else 0) | (2 if track == 2 else 0)
+
+
+# -------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_ev.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_ev.wait(self.period)
+
+    def stop(self) -> dict:
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        loaded = [m for m, u in self.samples if u >= 50] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_ch: int, seconds: int, steps: int, warmup: int, threads: int, want_imgs: bool = True):
+    """Times the oracle port (reference-like f32, dense mel product, threaded like mod.rs:152) on
+    `n_ch` channels of `seconds` s.  Returns (audio_hours_per_s, ms_per_step)."""
+    from oracle import orc
+    n = SR * seconds
+    an = orc.Analyzer(SR, WIN_MS, T_OVERLAP, 1, orc.MEL, N_MEL)
+    wavs = []
+    for c in range(n_ch):
+        tr, ch = divmod(c, N_CH)
+        wavs.append(orc.synth_pcm(n, SR, tr, ch, track_flags(tr), n_threads=threads))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        an.update_specs_and_imgs(wavs, DB_RANGE, CMAP_LEN, n_threads=threads, want_imgs=want_imgs)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    hours = n_ch * seconds / 3600.0 * len(times)
+    return hours / total, 1000.0 * total / len(times)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    threads = host_cores()
+    # bounded sample of the same workload: 16 of the 128 channels, 60 s each per step
+    n_ch, seconds = (16, 60) if args.scale >= 1.0 else (4, 20)
+    val, ms = cpu_reference_run(n_ch, seconds, args.steps, args.warmup, threads)
+    sample = f"{n_ch} of {N_TRACKS * N_CH} channels x {seconds} s per step (audio-hours/s is duration-invariant)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(1.0), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import thesia_b200 as thb
+    from thesia_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: thesia_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_ch_total = max(2, int(round(N_TRACKS * N_CH * args.scale)) // 2 * 2)
+    n = SR * SECONDS if args.scale >= 1.0 else max(SR * 10, int(SR * SECONDS * max(args.scale, 0.02)))
+    setting = thb.SpecSetting(WIN_MS, T_OVERLAP, 1, thb.FreqScale.Mel, N_MEL)
+    hop, win, n_fft = setting.calc_framing_params(SR)
+    T = thb.n_frames(n, win, hop)
+
+    stream = torch.cuda.current_stream()
+    ctx = thb.Context(local_rank, stream.cuda_stream)
+    if world > 1:
+        obj = [thb.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(world, rank, obj[0])
+
+    # ---- synthetic PCM, generated on the device (rows 256-byte aligned) ----
+    row = (n + 63) // 64 * 64
+    pcm = torch.empty((n_ch_total, row), dtype=torch.float32, device=dev)
+    for c in range(n_ch_total):
+        tr, ch = divmod(c, N_CH)
+        # every rank analyses its own 64 tracks of the N x 64-track job (weak scaling)
+        ctx.synth_pcm(pcm[c, :n], SR, tr + rank * N_TRACKS, ch, track_flags(tr))
+    ctx.synchronize()
+    tracks_dev = [dict(pcm=pcm[c, :n], id=c // N_CH, ch=c % N_CH, sr=SR) for c in range(n_ch_total)]
+
+    def step_resident():
+        ctx.spec_batch(tracks_dev, setting)
+        return ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- value: device-resident ----
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        mn, mx = step_resident()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    k_ms, k_launches = ctx.profile_get("stft_mel_db")
+    img_ms, img_launches = ctx.profile_get("spec_to_img")
+    red_ms, _ = ctx.profile_get("minmax_reduce")
+    ctx.profile_enable(False)
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    hours_per_step = world * n_ch_total * (n / SR) / 3600.0
+    value = hours_per_step * args.steps / (ms_total / 1000.0)
+
+    # ---- roofline of the dominant kernel (pass 1: PCM -> dB spec + min/max) ----
+    peaks = measured_peaks()
+    alg_bytes = n_ch_total * (4 * n + 4 * T * N_MEL)  # 4 B/sample in + 4 B/bin out
+    k_avg_ms = k_ms / max(k_launches, 1)
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    log2n = int(np.log2(n_fft))
+    flops_frame = 2.5 * n_fft * log2n + 4 * (n_fft // 2 + 1) + 2 * 2 * (n_fft // 2 + 1) + N_MEL
+    alg_flops = n_ch_total * T * flops_frame
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("stft_mel_db_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "stft_mel_db", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
+        "achieved_fp32_tflops": alg_flops / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0,
+        "share_of_step": (k_ms / ms_total) if ms_total > 0 else None,
+        "spec_to_img_avg_ms": img_ms / max(img_launches, 1),
+        "spec_to_img_gbs": (n_ch_total * (4 * T * N_MEL + 2 * T * N_MEL)) / (img_ms / max(img_launches, 1) * 1e-3) / 1e9
+        if img_ms > 0 else None,
+        "minmax_allreduce_avg_ms": red_ms / max(args.steps, 1),
+    }
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h2d_bytes = n_ch_total * n * 4
+        img_bytes = n_ch_total * N_MEL * T * 2
+        host_pcm_p, host_img_p = C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().thb_host_alloc(h2d_bytes, C.byref(host_pcm_p)))
+        _lib.check(_lib.lib().thb_host_alloc(img_bytes, C.byref(host_img_p)))
+        host_pcm = np.ctypeslib.as_array(C.cast(host_pcm_p, C.POINTER(C.c_float)), shape=(n_ch_total, n))
+        host_pcm_t = torch.from_numpy(host_pcm)
+        host_pcm_t.copy_(pcm[:, :n])  # fill the pinned input once (outside the timed region)
+        torch.cuda.synchronize()
+        tracks_host = [dict(pcm=host_pcm[c], id=c // N_CH, ch=c % N_CH, sr=SR) for c in range(n_ch_total)]
+        img_stride = N_MEL * T
+
+        def step_e2e():
+            ctx.spec_batch(tracks_host, setting)
+            r = ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
+            for c in range(n_ch_total):
+                ctx.img_read_into(c // N_CH, c % N_CH, host_img_p.value + 2 * c * img_stride, img_stride)
+            return r
+
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        step_e2e()  # warm-up (staging pool growth)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            mn_e, mx_e = step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        assert (mn_e, mx_e) == (mn, mx), "host-buffer and device-resident runs disagree on the dB range"
+        e2e = {"value": hours_per_step * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": img_bytes + 8, "steps": e2e_steps, "ms_per_step": 1000.0 * dt / e2e_steps,
+               "host_memory": "pinned (thb_host_alloc)"}
+        _lib.lib().thb_host_free(host_pcm_p)
+        _lib.lib().thb_host_free(host_img_p)
+
+    # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_cores()
+        n_ch_cpu, sec_cpu = (16, 60) if args.scale >= 1.0 else (4, 20)
+        v, _ = cpu_reference_run(n_ch_cpu, sec_cpu, 1, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_ch_cpu} of {N_TRACKS * N_CH} channels x {sec_cpu} s, 1 warm-up + 1 timed pass"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.scale), "channels_per_gpu": n_ch_total, "samples_per_channel": n,
+                       "frames_per_channel": T, "hop": hop, "win": win, "n_fft": n_fft, "n_mel": N_MEL,
+                       "parallelism": f"channels sharded, {world} rank(s), one 2-float NCCL max all-reduce",
+                       "l2": "inputs (14.75 GB per GPU) are far larger than the 126 MB L2; no flush needed",
+                       "dB_range": [mn, mx]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="<1 shrinks the workload (debug only; invalid as a result)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and args.scale >= 1.0:
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/* thesia_b200.h -- C ABI of the B200-native analysis hot path for Sytronik/thesia.
+ *
+ * The reference (Rust, src-tauri/) has no FFI for this path; everything is in-crate calls.
+ * Each entry point below replaces one in-crate seam and cites it (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the Rust `extern "C"` block and the three call
+ * sites a maintainer would change.
+ *
+ * Conventions:
+ *  - plain pointers and sizes only; the caller owns every host buffer, the library never keeps a
+ *    host pointer past the call.  Device-side results are retained under the (id, ch) key until
+ *    thb_release().
+ *  - every function returns 0 (THB_OK) or a negative thb_status; thb_last_error() gives text.
+ *    The Rust shim maps non-zero to panic!/anyhow::Error (the reference unwrap()s here:
+ *    stft.rs:47, release profile panic = "abort").
+ *  - thb_spec_batch / thb_update_spec_imgs / thb_minmax_global / thb_spec_to_img assume one
+ *    caller at a time per ctx (the reference serialises them on its "write-lock-worker" thread,
+ *    interface.rs:12-56).  thb_waveform_tile / thb_waveform_level are thread-safe (the reference
+ *    serves tiles from concurrent IPC threads, lib.rs:343-367).
+ *  - `pcm` pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).
+ *    Host memory from thb_host_alloc() is pinned and copies from it are asynchronous.
+ *  - There is no CPU fallback: without a CUDA device thb_ctx_create() fails with THB_ERR_CUDA.
+ *    The functions in the "host parameter" group are pure host arithmetic and need no device.
+ */
+#ifndef THESIA_B200_H
+#define THESIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THB_ABI_VERSION 1
+
+typedef enum thb_status {
+    THB_OK = 0,
+    THB_ERR_INVALID = -1,      /* bad argument (NULL, len < 2, hop == 0, ...) */
+    THB_ERR_UNSUPPORTED = -2,  /* n_fft not a power of two or > 32768 */
+    THB_ERR_CUDA = -3,         /* CUDA runtime error / no device */
+    THB_ERR_NOMEM = -4,
+    THB_ERR_NOT_FOUND = -5,    /* unknown (id, ch) */
+    THB_ERR_NCCL = -6,
+    THB_ERR_SMALL_BUFFER = -7  /* caller buffer too small; *written / dims tell the need */
+} thb_status;
+
+typedef struct thb_ctx thb_ctx;
+
+/* FreqScale (src-common/src/lib.rs:106-110) */
+#define THB_FREQ_LINEAR 0u
+#define THB_FREQ_MEL 1u
+
+/* SpecSetting (src-tauri/src/core/spectrogram.rs:30-38) + the n_mel of calc_mel_fb
+ * (src-common/src/lib.rs:46-53); n_mel == 0 selects calc_mel_fb_default's rule (lib.rs:91-103),
+ * which is what TrackManager always uses. */
+typedef struct thb_setting {
+    double win_ms;
+    uint32_t t_overlap;
+    uint32_t f_overlap;
+    uint32_t freq_scale; /* THB_FREQ_LINEAR | THB_FREQ_MEL */
+    uint32_t n_mel;      /* 0 = reference default rule */
+} thb_setting;
+
+/* One (id, ch) channel = `tracklist[id].channel(ch)` (src-tauri/src/core/track.rs:92-94) with its
+ * sample rate.  The last four fields shard a long file by FRAME RANGE across GPUs: `pcm` then
+ * points at sample `pcm_offset` of a file of `full_len` samples and only frames
+ * [frame_begin, frame_begin + frame_count) are computed; reflect padding is applied against the
+ * true file ends.  All four zero = the whole channel. */
+typedef struct thb_track {
+    const float *pcm; /* host or device */
+    uint64_t len;     /* samples available at pcm */
+    uint64_t id;
+    uint32_t ch;
+    uint32_t sr;
+    uint64_t full_len;
+    uint64_t pcm_offset;
+    uint64_t frame_begin;
+    uint64_t frame_count; /* 0 = all frames from frame_begin */
+} thb_track;
+
+/* Per-channel result of thb_spec_batch: Array2<f32> (T, B) of calc_spec
+ * (spectrogram.rs:187-212).  spec_host, when non-NULL on input, receives the dB values
+ * (row-major (n_frames, n_bins), capacity spec_host_cap floats). */
+typedef struct thb_spec_out {
+    uint64_t n_frames; /* T computed (frame_count) */
+    uint64_t total_frames; /* T of the whole file */
+    uint32_t n_bins;   /* B: n_fft/2+1 (Linear) or n_mel (Mel) */
+    uint32_t hop, win, n_fft;
+    float *spec_host;
+    uint64_t spec_host_cap;
+} thb_spec_out;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* One ctx per process and device (the reference keeps its state in process globals,
+ * lib.rs:36-42).  `cuda_stream` may be NULL (library creates its own non-blocking stream) or a
+ * cudaStream_t the caller owns (e.g. torch.cuda.current_stream().cuda_stream). */
+int thb_ctx_create(int device, void *cuda_stream, thb_ctx **out);
+void thb_ctx_destroy(thb_ctx *ctx);
+int thb_set_stream(thb_ctx *ctx, void *cuda_stream);
+int thb_synchronize(thb_ctx *ctx);
+const char *thb_last_error(const thb_ctx *ctx); /* ctx may be NULL: last global error */
+int thb_abi_version(void);
+
+/* pinned host memory for PCM / result buffers */
+int thb_host_alloc(size_t bytes, void **out);
+int thb_host_free(void *p);
+
+/* ---- host parameter arithmetic (no device needed; integer-exact parity) ------------------- */
+/* SpecSetting::calc_framing_params (spectrogram.rs:57-98) */
+int thb_framing_params(const thb_setting *s, uint32_t sr, uint64_t *hop, uint64_t *win, uint64_t *n_fft);
+/* frame count of perform_stft (stft.rs:16-124): 1 + (N + 2*(W/2) - W) / H */
+uint64_t thb_n_frames(uint64_t len, uint64_t win, uint64_t hop);
+/* B of calc_spec for this (setting, sr): n_fft/2+1 or n_mel (default rule when n_mel == 0) */
+int thb_n_bins(const thb_setting *s, uint32_t sr, uint32_t *n_bins);
+/* calc_normalized_win(Hann, win, n_fft) (windows.rs:12-38): out[win] */
+int thb_hann_window(uint64_t win, uint64_t n_fft, float *out);
+/* calc_mel_fb(sr, n_fft, n_mel, 0, None, true) / calc_mel_fb_default (src-common/src/lib.rs:46-103):
+ * out is (n_fft/2+1, n_mel) row-major; n_mel == 0 -> default rule; *n_mel_out gets the count.
+ * out may be NULL to query n_mel only. */
+int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t *n_mel_out);
+/* FreqScale::hz_range_to_idx (src-common/src/lib.rs:144-159) */
+int thb_hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uint64_t n_bins,
+                        uint64_t *i0, uint64_t *i1);
+
+/* ---- TrackManager::update_specs (src-tauri/src/core/mod.rs:137-164) -------------------------
+ * = SpectrogramAnalyzer::prepare (spectrogram.rs:116-154) + calc_spec per (id, ch)
+ * (spectrogram.rs:187-212 -> perform_stft stft.rs:16-124 -> norm -> [mel dot] -> dB
+ * decibel.rs:170-214).  The dB spectrogram of every track stays resident on the device under
+ * (id, ch), replacing any previous one, together with its local (min, max). */
+int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_setting *setting,
+                   thb_spec_out *outs /* [n], may be NULL */);
+/* Install a caller-computed dB spectrogram (T, B) row-major f32 (host or device memory) under
+ * (id, ch) as if thb_spec_batch had produced it: its (min, max) is reduced on the device and it
+ * takes part in thb_update_spec_imgs.  Lets a host restore cached specs, and lets tests drive the
+ * image path with the reference's own vectors (drawing.rs:43-56). */
+int thb_spec_put(thb_ctx *ctx, uint64_t id, uint32_t ch, uint32_t sr, uint32_t freq_scale,
+                 const float *spec, uint64_t n_frames, uint32_t n_bins);
+/* copy a retained dB spectrogram to the host: out (T, B) row-major, cap in floats */
+int thb_spec_read(thb_ctx *ctx, uint64_t id, uint32_t ch, float *out, uint64_t cap,
+                  uint64_t *n_frames, uint32_t *n_bins);
+/* device pointer of a retained dB spectrogram (T, B) row-major f32 (valid until release/replace) */
+int thb_spec_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const float **dptr,
+                        uint64_t *n_frames, uint32_t *n_bins);
+/* local (min, max) of one retained spectrogram = find_min_max(spec) (simd.rs:14-36) */
+int thb_spec_minmax(thb_ctx *ctx, uint64_t id, uint32_t ch, float *mn, float *mx);
+/* TrackManager::remove_tracks (mod.rs:86-100) */
+int thb_release(thb_ctx *ctx, uint64_t id, uint32_t ch);
+int thb_release_all(thb_ctx *ctx);
+
+/* ---- TrackManager::update_spec_imgs (mod.rs:168-230) ----------------------------------------
+ * thb_minmax_global: global (min, max) over every retained spectrogram (mod.rs:169-178), reduced
+ * across ranks with one ncclAllReduce(max) of {max, -min} when a communicator is attached, then
+ * max <- min(max, 0); min <- max(min, max - dB_range) (mod.rs:179-180). */
+int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB);
+/* convert_spectrogram_to_img (visualize/drawing.rs:4-33) for one retained spectrogram:
+ * out is (i1 - i0, T) row-major u16 on the HOST. */
+int thb_spec_to_img(thb_ctx *ctx, uint64_t id, uint32_t ch, uint64_t i0, uint64_t i1, float min_dB,
+                    float max_dB, uint32_t colormap_length, uint16_t *out, uint64_t cap);
+/* The whole of update_spec_imgs: global min/max over ALL retained spectrograms (+ all-reduce),
+ * i_freq_range from hz_range_to_idx((0, max_sr/2), sr, B) (mod.rs:208-213; max_sr == 0 -> max over
+ * retained tracks), quantise + transpose into device-resident images.  `only_ids` (n_only track
+ * ids) restricts the quantise step to those tracks -- the reference's `ids_need_update` when
+ * neither the dB range nor max_sr moved (mod.rs:194-203); NULL = every track. */
+int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length, uint32_t max_sr,
+                         const uint64_t *only_ids, size_t n_only, float *min_dB, float *max_dB);
+/* TrackManager::get_spectrogram (mod.rs:133-135): copy image (H, W = T) to the host */
+int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t cap,
+                 uint64_t *height, uint64_t *width);
+/* device view of a retained image: rows are `pitch` u16 apart */
+int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr,
+                       uint64_t *height, uint64_t *width, uint64_t *pitch);
+
+/* ---- encode_waveform_tile (src-tauri/src/core/render_tiles.rs:232-279) ----------------------
+ * Byte-identical wire format: u64 revision, u32 bin_count, u32 samples_per_bin, u32 tile_index,
+ * u32 0, then per bin f32 min, f32 max, f32 mean (little endian).  `out` is HOST memory. */
+int thb_waveform_tile(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level,
+                      uint32_t tile_index, uint8_t *out, size_t cap, size_t *written);
+/* every tile of one level, concatenated in tile order (what a full redraw at that zoom asks for) */
+int thb_waveform_level(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level,
+                       uint8_t *out, size_t cap, size_t *written);
+/* same, for n channels in one launch; the encoded levels stay on the device (dev_out[i], valid until
+ * the next call) and are copied to host_out[i] when host_out != NULL */
+int thb_waveform_level_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, uint64_t revision,
+                             uint32_t level, uint8_t **host_out, const size_t *caps, size_t *written,
+                             const uint8_t **dev_out);
+uint64_t thb_waveform_level_bytes(uint64_t len, uint32_t level);
+
+/* ---- multi-GPU: one process per GPU, one communicator per box ---------
+ * NCCL is dlopen'ed ("libnccl.so.2") on first use.  Rank 0 creates the id, the host program
+ * distributes the 128 bytes (torch.distributed / MPI / a file), every rank calls thb_comm_init. */
+int thb_comm_unique_id(uint8_t id[128]);
+int thb_comm_init(thb_ctx *ctx, int n_ranks, int rank, const uint8_t id[128]);
+int thb_comm_destroy(thb_ctx *ctx);
+
+/* ---- measurement support --------------------------------------------------------------------
+ * Per-kernel CUDA-event timing on the ctx stream and a launch counter (bench.py's roofline /
+ * gpu_launches).  Kernel names: "stft_mel_db", "stft_lin_db", "minmax_reduce", "spec_to_img",
+ * "envelope". */
+int thb_profile_enable(thb_ctx *ctx, int on);
+int thb_profile_reset(thb_ctx *ctx);
+int thb_profile_get(thb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *launches);
+uint64_t thb_launch_count(const thb_ctx *ctx);
+/* deterministic integer-arithmetic synthetic PCM, written to DEVICE memory
+ * `dev_out` (len floats); thesia_b200/synth.py restates it in numpy bit for bit. */
+int thb_synth_pcm(thb_ctx *ctx, float *dev_out, uint64_t len, uint32_t sr, uint32_t track, uint32_t channel,
+                  uint32_t flags);
+#define THB_SYNTH_LOUD 1u     /* scale x1.5 so that max_dB hits the min(max, 0) clamp */
+#define THB_SYNTH_ZERO_GAP 2u /* one second of exact zeros (produces -inf frames) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THESIA_B200_H */

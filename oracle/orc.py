@@ -79,6 +79,7 @@ def _load() -> C.CDLL:
         "orc_perform_stft_f32": (_u64, [_pf32, _u64, _u64, _u64, _u64, _pf32, _pf32, _pf32]),
         "orc_update_specs_and_imgs": (None, [C.c_void_p, C.POINTER(_pf32), _pu64, _u64, C.POINTER(_pf32),
                                              C.POINTER(_pu16), _f32, _u32, _int, _pf32, _pf32]),
+        "orc_synth_pcm": (None, [_pf32, _u64, _u32, _u32, _u32, _u32, _int]),
         "orc_max_threads": (_int, []),
     }
     for name_, (res, args) in sig.items():
@@ -336,6 +337,15 @@ class Analyzer:
         lib().orc_update_specs_and_imgs(self._h, pcm_arr, len_arr, n, spec_arr, img_arr, dB_range,
                                         colormap_length, n_threads, C.byref(mn), C.byref(mx))
         return specs, imgs, mn.value, mx.value
+
+
+def synth_pcm(length: int, sr: int, track: int, channel: int = 0, flags: int = 0, n_threads: int = 1,
+              out: np.ndarray = None) -> np.ndarray:
+    if out is None:
+        out = np.empty(length, np.float32)
+    assert out.dtype == np.float32 and out.size == length and out.flags.c_contiguous
+    lib().orc_synth_pcm(_p(out, _pf32), length, sr, track, channel, flags, n_threads)
+    return out
 
 
 def max_threads() -> int:

@@ -558,7 +558,12 @@ static void orc_frame_f32(const orc_analyzer *a, const float *x, uint64_t n, uin
     const uint64_t pad_l = (NF - W) / 2; /* stft.rs:36-37 */
     memset(buf, 0, sizeof(float) * NF);
     int64_t s0 = (int64_t)(t * a->hop) - (int64_t)(W / 2);
-    for (uint64_t i = 0; i < W; i++) buf[pad_l + i] = orc_sample_reflect(x, n, s0 + (int64_t)i) * a->window[i];
+    if (s0 >= 0 && (uint64_t)s0 + W <= n) { /* mid frames: a plain slice (stft.rs:83-85) */
+        const float *xs = x + s0;
+        for (uint64_t i = 0; i < W; i++) buf[pad_l + i] = xs[i] * a->window[i];
+    } else {
+        for (uint64_t i = 0; i < W; i++) buf[pad_l + i] = orc_sample_reflect(x, n, s0 + (int64_t)i) * a->window[i];
+    }
     orc_rfft_f32(a->p32, buf, re, im, work);
     if (stft_re) { memcpy(stft_re, re, sizeof(float) * a->n_freq); memcpy(stft_im, im, sizeof(float) * a->n_freq); }
     for (uint64_t k = 0; k < a->n_freq; k++) mag[k] = hypotf(re[k], im[k]); /* Complex::norm */
@@ -566,23 +571,54 @@ static void orc_frame_f32(const orc_analyzer *a, const float *x, uint64_t n, uin
 }
 
 /* dense (T,F)x(F,M) f32 product, row block at a time -- the reference's `linspec.dot(&mel_fb)`
-   (spectrogram.rs:207) is an sgemm over ALL F*M weights, zeros included. */
+   (spectrogram.rs:207) is an sgemm over ALL F*M weights, zeros included (OpenBLAS via ndarray's
+   `blas` feature).  Register-blocked 4 rows x 16 columns so that the CPU baseline is not
+   handicapped by a naive loop; FMA where the CPU has it, like OpenBLAS' kernels. */
+#ifdef __FMA__
+#define ORC_MAC(acc, a, b) (acc) = __builtin_fmaf((a), (b), (acc))
+#else
+#define ORC_MAC(acc, a, b) (acc) += (a) * (b)
+#endif
 static void orc_dense_mel_rows_f32(const float *mag, uint64_t rows, uint64_t F, const float *fb,
                                    uint64_t M, float *out) {
-    for (uint64_t r = 0; r < rows; r++) {
+    const uint64_t M16 = M & ~(uint64_t)15;
+    uint64_t r = 0;
+    for (; r + 4 <= rows; r += 4) {
+        const float *a0 = mag + (r + 0) * F, *a1 = mag + (r + 1) * F, *a2 = mag + (r + 2) * F, *a3 = mag + (r + 3) * F;
+        for (uint64_t m0 = 0; m0 < M16; m0 += 16) {
+            float c0[16] = {0}, c1[16] = {0}, c2[16] = {0}, c3[16] = {0};
+            for (uint64_t k = 0; k < F; k++) {
+                const float *w = fb + k * M + m0;
+                const float v0 = a0[k], v1 = a1[k], v2 = a2[k], v3 = a3[k];
+#pragma omp simd
+                for (int j = 0; j < 16; j++) {
+                    ORC_MAC(c0[j], v0, w[j]); ORC_MAC(c1[j], v1, w[j]);
+                    ORC_MAC(c2[j], v2, w[j]); ORC_MAC(c3[j], v3, w[j]);
+                }
+            }
+            for (int j = 0; j < 16; j++) {
+                out[(r + 0) * M + m0 + j] = c0[j]; out[(r + 1) * M + m0 + j] = c1[j];
+                out[(r + 2) * M + m0 + j] = c2[j]; out[(r + 3) * M + m0 + j] = c3[j];
+            }
+        }
+        for (uint64_t m = M16; m < M; m++) {
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            for (uint64_t k = 0; k < F; k++) {
+                const float w = fb[k * M + m];
+                ORC_MAC(c0, a0[k], w); ORC_MAC(c1, a1[k], w); ORC_MAC(c2, a2[k], w); ORC_MAC(c3, a3[k], w);
+            }
+            out[(r + 0) * M + m] = c0; out[(r + 1) * M + m] = c1; out[(r + 2) * M + m] = c2; out[(r + 3) * M + m] = c3;
+        }
+    }
+    for (; r < rows; r++) {
         float *o = out + r * M;
         for (uint64_t m = 0; m < M; m++) o[m] = 0.f;
         const float *mr = mag + r * F;
         for (uint64_t k = 0; k < F; k++) {
             const float v = mr[k];
             const float *w = fb + k * M;
-#ifdef __FMA__ /* OpenBLAS sgemm kernels use FMA where the CPU has it */
 #pragma omp simd
-            for (uint64_t m = 0; m < M; m++) o[m] = __builtin_fmaf(v, w[m], o[m]);
-#else
-#pragma omp simd
-            for (uint64_t m = 0; m < M; m++) o[m] += v * w[m];
-#endif
+            for (uint64_t m = 0; m < M; m++) ORC_MAC(o[m], v, w[m]);
         }
     }
 }
@@ -741,6 +777,50 @@ ORC_API void orc_update_specs_and_imgs(const orc_analyzer *a, const float *const
             if (imgs[c])
                 orc_spec_to_img(specs[c], orc_n_frames(lens[c], a->win, a->hop), NB, 0, NB, *min_dB,
                                 *max_dB, 1, colormap_length, imgs[c]);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic PCM twin of thb_synth_pcm (integer arithmetic; bit-identical to  */
+/* thesia_b200/synth.py and to the device generator) -- feeds the CPU baseline */
+/* ------------------------------------------------------------------------- */
+static inline int orc_para_sine(uint32_t phase) {
+    uint32_t x = (phase >> 15) & 0xffffu;
+    int y = (int)(((uint64_t)x * (65536ull - x)) >> 14);
+    return (phase >> 31) ? -y : y;
+}
+static inline uint32_t orc_mix32(uint32_t h) {
+    h ^= h >> 15; h *= 0x85ebca77u;
+    h ^= h >> 13; h *= 0xc2b2ae3du;
+    h ^= h >> 16;
+    return h;
+}
+static inline int orc_synth_base(uint64_t n, uint64_t len, uint32_t sr, uint32_t track, uint32_t flags) {
+    uint64_t f0_mhz = 55000ull + 13750ull * (track % 61u);
+    uint64_t inc0 = (f0_mhz << 32) / (1000ull * sr);
+    uint32_t ph0 = (uint32_t)(n * inc0);
+    uint64_t inc_a = (50ull << 32) / sr;
+    uint64_t dinc = 1932735283ull - inc_a;
+    uint64_t n2 = n * n, two_len = 2ull * len;
+    uint64_t t_int = n2 / two_len, t_rem = n2 % two_len;
+    uint32_t ph1 = (uint32_t)(inc_a * n + dinc * t_int + (dinc * t_rem) / two_len);
+    uint32_t h = orc_mix32((uint32_t)n * 0x9e3779b1u + track * 0x7f4a7c15u + 0x7e51au);
+    int a0 = (8192 * orc_para_sine(ph0)) >> 16;
+    int a1 = (3277 * orc_para_sine(ph1)) >> 16;
+    int nz = (((int)(h >> 16) - 32768) * 1638) >> 15;
+    int v = a0 + a1 + nz;
+    if ((flags & 2u) && n >= sr && n < 2ull * sr) v = 0;
+    if (flags & 1u) v *= 16;
+    return v;
+}
+ORC_API void orc_synth_pcm(float *out, uint64_t len, uint32_t sr, uint32_t track, uint32_t channel,
+                           uint32_t flags, int n_threads) {
+#pragma omp parallel for schedule(static) num_threads(n_threads > 1 ? n_threads : 1)
+    for (uint64_t n = 0; n < len; n++) {
+        int v;
+        if (channel == 0) v = orc_synth_base(n, len, sr, track, flags);
+        else v = n >= 7 ? (int)(((int64_t)orc_synth_base(n - 7, len, sr, track, flags) * 26214) >> 15) : 0;
+        out[n] = (float)v / 32768.0f;
     }
 }
 

@@ -1,0 +1,381 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Stated tolerances (DESIGN.md "Parity"):
+  * hop / win / n_fft / T / n_bins / i_freq_range / tile headers / envelope min, max: bit-exact.
+  * power  |P_gpu - P_truth| <= 1e-4 * max(P_truth, FLOOR * max_k P_truth[frame]),  FLOOR = 1e-5
+    (an f32 FFT -- the reference's included -- cannot hold 1e-4 RELATIVE error on bins more than
+    50 dB under the frame's peak; the f32 oracle itself measures 5.9e-5 against this bound).
+  * dB     |dB_gpu - dB_truth| <= 1e-3 dB wherever P_truth is above that floor; exactly -inf where
+    the truth is -inf (all-zero frames); below the floor the GPU must be no worse than 3x the
+    reference-like f32 oracle's own worst error (+1e-3 dB).
+  * envelope mean <= 1e-6 absolute; u16 image: bit-exact given the GPU's own dB, <= 1 LSB end to end.
+"truth" = the oracle's f64 leg; "f32 oracle" = its reference-like f32 leg.
+"""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+import thesia_b200 as thb
+from thesia_b200 import _lib
+from thesia_b200.analysis import TrackList
+from thesia_b200.synth import LOUD, ZERO_GAP, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+FLOOR = 1e-5
+POW_RTOL = 1e-4
+DB_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = thb.Context(0)
+    yield c
+    c.close()
+
+
+def _scale(orc, fs):
+    return orc.MEL if fs == thb.FreqScale.Mel else orc.LINEAR
+
+
+def check_spec(orc, gpu_db, wav, sr, setting: thb.SpecSetting, tag=""):
+    an = orc.Analyzer(sr, setting.win_ms, setting.t_overlap, setting.f_overlap, _scale(orc, setting.freq_scale),
+                      setting.n_mel)
+    truth_db, truth_amp = an.calc_spec_truth(wav, want_amp=True, n_threads=8)
+    f32_db = an.calc_spec(wav, n_threads=8)
+    assert gpu_db.shape == truth_db.shape, (tag, gpu_db.shape, truth_db.shape)
+    g = gpu_db.astype(np.float64)
+    neg = np.isneginf(truth_db)
+    assert np.array_equal(np.isneginf(g), neg), f"{tag}: -inf pattern differs"
+    assert not np.isnan(g).any(), f"{tag}: NaN in GPU output"
+    P = truth_amp ** 2
+    with np.errstate(over="ignore", invalid="ignore"):
+        Pg = np.where(neg, 0.0, 10.0 ** (g / 10.0))
+    floor = FLOOR * P.max(axis=1, keepdims=True)
+    rel = np.abs(Pg - P) / np.maximum(np.maximum(P, floor), 1e-300)
+    worst_pow = float(rel.max()) if rel.size else 0.0
+    above = (P > floor) & ~neg
+    with np.errstate(invalid="ignore"):
+        ddb = np.where(~neg, np.abs(g - truth_db), 0.0)
+        ddb32 = np.where(~neg, np.abs(f32_db.astype(np.float64) - truth_db), 0.0)
+    worst_db = float(ddb[above].max()) if above.any() else 0.0
+    assert worst_pow <= POW_RTOL, f"{tag}: power rel err {worst_pow:.3g}"
+    assert worst_db <= DB_TOL, f"{tag}: dB err above floor {worst_db:.3g}"
+    # below the floor: no worse than the reference-like f32 arithmetic (bins down to -90 dB rel.)
+    deep = (P > 1e-9 * P.max(axis=1, keepdims=True)) & ~neg
+    if deep.any():
+        assert ddb[deep].max() <= 3.0 * ddb32[deep].max() + 1e-3, \
+            f"{tag}: deep-bin dB err {ddb[deep].max():.3g} vs f32 oracle {ddb32[deep].max():.3g}"
+    return worst_pow, worst_db
+
+
+# ---------------------------------------------------------------------------------------------
+# reference KATs through the CUDA path
+# ---------------------------------------------------------------------------------------------
+def test_stft_works_through_gpu(ctx, orc):
+    """stft.rs:173-196: impulse(4, at 2), win 4, hop 2, n_fft 4 -> |X| = [[0,0,0],[1/4]*3,[1/4]*3]."""
+    s = thb.SpecSetting(4.0, 2, 1, thb.FreqScale.Linear)  # sr 1000 -> hop 2, win 4, n_fft 4
+    assert s.calc_framing_params(1000) == (2, 4, 4)
+    x = np.zeros(4, np.float32)
+    x[2] = 1.0
+    db = ctx.calc_spec(x, 1000, s)
+    assert db.shape == (3, 3)
+    assert np.all(np.isneginf(db[0]))
+    assert np.allclose(db[1:], 20 * math.log10(0.25), atol=1e-5)
+
+
+def test_stft_short_wav_through_gpu(ctx, orc):
+    """stft.rs:198-203: N = 2 < win = 8 (hop 6 is not reachable through SpecSetting: win = hop * t_overlap;
+    use win 8 hop 8)."""
+    s = thb.SpecSetting(8.0, 1, 1, thb.FreqScale.Linear)  # sr 1000 -> hop 8, win 8
+    x = np.array([0.0, 1.0], np.float32)
+    db = ctx.calc_spec(x, 1000, s)
+    assert db.shape == (orc.n_frames(2, 8, 8), 5)
+    check_spec(orc, db, x, 1000, s, "short")
+
+
+def test_spectrogram_to_img_kat_through_gpu(ctx):
+    """drawing.rs:43-56, exact."""
+    spec = np.array([[-100.0, -50.0, 0.0], [100.0, -200.0, -25.0]], np.float32)
+    ctx.spec_put(900, 0, 48000, thb.FreqScale.Linear, spec)
+    img = ctx.spec_to_img(900, 0, (0, 4), (-100.0, 0.0), 4)
+    assert img.tolist() == [[16384, 65535], [40960, 0], [65535, 53247], [0, 0]]
+    assert ctx.spec_minmax(900, 0) == (-200.0, 100.0)
+    ctx.release(900, 0)
+
+
+def _tile_fields(b):
+    rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
+    return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)
+
+
+def test_waveform_tile_kats_through_gpu(ctx):
+    """render_tiles.rs:408-433."""
+    b = ctx.waveform_tile(np.array([-1.0, 0.0, 0.5, 1.0], np.float32), 3, 1, 0)
+    rev, bins, spb, idx, zero, v = _tile_fields(b)
+    assert (rev, bins, spb, idx, zero) == (3, 2, 2, 0, 0)
+    assert v.tolist() == [[-1.0, 0.0, -0.5], [0.5, 1.0, 0.75]]
+    b = ctx.waveform_tile(np.full(1025, 0.25, np.float32), 1, 0, 1)
+    assert _tile_fields(b)[1] == 1 and len(b) == 36
+    wav = np.arange(64, dtype=np.float32) - 32.0
+    rev, bins, spb, idx, zero, v = _tile_fields(ctx.waveform_tile(wav, 1, 6, 0))
+    assert bins == 1 and spb == 64 and v[0].tolist() == [-32.0, 31.0, -0.5]
+    b = ctx.waveform_tile(np.zeros(10, np.float32), 7, 2, 5)  # tile beyond the end: header only
+    assert len(b) == 24 and _tile_fields(b)[:5] == (7, 0, 4, 5, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# spectrogram parity on the BASELINE configs (down-scaled durations)
+# ---------------------------------------------------------------------------------------------
+CASES = [
+    # tag, sr, setting, n_samples, synth flags
+    ("C1-linear-2048-512", 48000, thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear), 211353, 0),
+    ("C2-mel128-2048-256", 48000, thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128), 240000, ZERO_GAP),
+    ("C2-meldefault", 48000, thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 0), 120000, 0),
+    ("C3-mel128-2048-512", 48000, thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128), 288000, ZERO_GAP),
+    ("default-40ms-48k", 48000, thb.SpecSetting(), 150001, 0),               # win 1920 in n_fft 2048
+    ("default-40ms-44k1", 44100, thb.SpecSetting(), 132301, ZERO_GAP),       # win 1764, hop 441 (odd)
+    ("default-40ms-22k05", 22050, thb.SpecSetting(), 50000, 0),              # hop 221, n_fft 1024
+    ("default-40ms-8k", 8000, thb.SpecSetting(), 30000, 0),                  # n_fft 512
+    ("default-40ms-96k", 96000, thb.SpecSetting(), 200000, 0),               # n_fft 4096
+    ("C4-linear-16384-1024", 96000, thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Linear), 300000, 0),
+    ("C4-meldefault-16384", 96000, thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Mel), 200000, 0),
+    ("foverlap2", 48000, thb.SpecSetting(40.0, 4, 2, thb.FreqScale.Linear), 60000, 0),   # n_fft 4096, win 1920
+    ("nfft32768", 96000, thb.SpecSetting(300.0, 2, 1, thb.FreqScale.Mel, 64), 200000, 0),
+    ("tiny-1ms-8k", 8000, thb.SpecSetting(1.0, 1, 1, thb.FreqScale.Linear), 4000, 0),    # win 8, n_fft 8
+    ("toverlap32", 16000, thb.SpecSetting(32.0, 32, 1, thb.FreqScale.Mel), 20000, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_spec_parity(ctx, orc, case):
+    tag, sr, setting, n, flags = case
+    x = synth_pcm(n, sr, 7, 0, flags)
+    hop, win, n_fft = setting.calc_framing_params(sr)
+    assert (hop, win, n_fft) == orc.framing_params(setting.win_ms, sr, setting.t_overlap, setting.f_overlap)
+    db = ctx.calc_spec(x, sr, setting, id=1, ch=0)
+    assert db.shape[0] == orc.n_frames(n, win, hop)
+    worst = check_spec(orc, db, x, sr, setting, tag)
+    # the retained device copy is the same array
+    assert np.array_equal(ctx.spec_read(1, 0), db, equal_nan=True)
+    # local min/max == find_min_max of the very same values (bit-exact by value)
+    mn, mx = ctx.spec_minmax(1, 0)
+    assert (mn, mx) == orc.find_min_max(db), tag
+    print(tag, "worst power rel %.3g, worst dB %.3g" % worst)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 100, 1919, 1920, 1921, 2048, 2400])
+def test_edges_and_short_inputs(ctx, orc, n):
+    """reflect padding incl. the multi-wrap case (N much shorter than win/2) and N around win."""
+    rng = np.random.default_rng(n)
+    x = (np.round(rng.standard_normal(n) * 3000) / 32768).astype(np.float32)
+    for setting in (thb.SpecSetting(), thb.SpecSetting(40.0, 4, 1, thb.FreqScale.Linear)):
+        db = ctx.calc_spec(x, 48000, setting)
+        assert db.shape[0] == orc.n_frames(n, 1920, 480)
+        check_spec(orc, db, x, 48000, setting, f"N={n}")
+
+
+def test_device_resident_input_matches_host_input(ctx):
+    import torch
+    x = synth_pcm(100000, 48000, 3, 1, 0)
+    s = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    a = ctx.calc_spec(x, 48000, s, id=5)
+    xd = torch.from_numpy(x).cuda()
+    b = ctx.calc_spec(xd, 48000, s, id=6)
+    assert np.array_equal(a, b)
+
+
+def test_synth_device_matches_numpy_twin(ctx):
+    import torch
+    for (n, sr, tr, ch, fl) in [(100003, 48000, 0, 0, 0), (150000, 48000, 63, 1, ZERO_GAP), (50000, 96000, 9, 0, LOUD),
+                                (300000, 44100, 17, 1, LOUD | ZERO_GAP)]:
+        d = torch.empty(n, dtype=torch.float32, device="cuda")
+        ctx.synth_pcm(d, sr, tr, ch, fl)
+        ctx.synchronize()
+        assert np.array_equal(d.cpu().numpy(), synth_pcm(n, sr, tr, ch, fl)), (n, sr, tr, ch, fl)
+
+
+def test_frame_range_shards_equal_whole(ctx):
+    """Long-file sharding: frame ranges computed from PCM slices + halo, reflect only
+    at true file ends, concatenate to exactly the whole-file result."""
+    from thesia_b200.sharding import split_frames
+    x = synth_pcm(123457, 48000, 11, 0, 0)
+    for s in (thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128), thb.SpecSetting(40.0, 4, 1, thb.FreqScale.Linear)):
+        hop, win, _ = s.calc_framing_params(48000)
+        whole = ctx.calc_spec(x, 48000, s, id=20)
+        for parts in (2, 3, 8):
+            units = split_frames(21, 0, 48000, x.size, win, hop, parts)
+            assert sum(u.frame_count for u in units) == whole.shape[0]
+            pieces = []
+            for k, u in enumerate(units):
+                tr = dict(pcm=x[u.pcm_lo:u.pcm_hi].copy(), id=100 + k, ch=0, sr=48000, full_len=x.size,
+                          pcm_offset=u.pcm_lo, frame_begin=u.frame_begin, frame_count=u.frame_count)
+                pieces.append(ctx.spec_batch([tr], s, want_host=True)[0][2])
+            assert np.array_equal(np.concatenate(pieces, axis=0), whole)
+    with pytest.raises(thb.ThbError) as e:  # a slice that misses its halo is refused, not misread
+        u = split_frames(21, 0, 48000, x.size, 2048, 256, 2)[1]
+        ctx.spec_batch([dict(pcm=x[u.pcm_lo + 10:u.pcm_hi].copy(), id=1, ch=0, sr=48000, full_len=x.size,
+                             pcm_offset=u.pcm_lo + 10, frame_begin=u.frame_begin, frame_count=u.frame_count)],
+                       thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128))
+    assert e.value.code == _lib.THB_ERR_INVALID
+
+
+def test_error_behaviour(ctx):
+    with pytest.raises(thb.ThbError) as e:
+        ctx.calc_spec(np.zeros(1, np.float32), 48000, thb.SpecSetting())
+    assert e.value.code == _lib.THB_ERR_INVALID
+    with pytest.raises(thb.ThbError) as e:
+        ctx.calc_spec(np.zeros(5000, np.float32), 48000, thb.SpecSetting(40.0, 4, 3))  # n_fft = 6144
+    assert e.value.code == _lib.THB_ERR_UNSUPPORTED
+    with pytest.raises(thb.ThbError) as e:
+        ctx.spec_read(123456, 7)
+    assert e.value.code == _lib.THB_ERR_NOT_FOUND
+    with pytest.raises(thb.ThbError) as e:
+        ctx.calc_spec(np.zeros(5000, np.float32), 48000, thb.SpecSetting(0.0, 4, 1))
+    assert e.value.code == _lib.THB_ERR_INVALID
+
+
+# ---------------------------------------------------------------------------------------------
+# update_spec_imgs: global min/max + u16 images, TrackManager flow
+# ---------------------------------------------------------------------------------------------
+def test_global_minmax_and_images_batch(ctx, orc):
+    """C3 in miniature: 4 stereo tracks, one LOUD (max clamps to 0), one with a zero gap (-inf)."""
+    ctx.release_all()
+    s = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    sr, n = 48000, 144000
+    wavs, tracks = {}, []
+    for tr in range(4):
+        fl = (LOUD if tr == 1 else 0) | (ZERO_GAP if tr == 2 else 0)
+        for ch in range(2):
+            wavs[(tr, ch)] = synth_pcm(n, sr, tr, ch, fl)
+            tracks.append(dict(pcm=wavs[(tr, ch)], id=tr, ch=ch, sr=sr))
+    ctx.spec_batch(tracks, s)
+    mn, mx = ctx.update_spec_imgs(100.0, 258)
+    specs = {k: ctx.spec_read(*k) for k in wavs}
+    allv = np.concatenate([v.ravel() for v in specs.values()])
+    raw_mn, raw_mx = orc.find_min_max(allv)
+    assert raw_mx > 0.0 and raw_mn == -math.inf
+    assert (mn, mx) == orc.clamp_minmax(raw_mn, raw_mx, 100.0) == (-100.0, 0.0)
+    an = orc.Analyzer(sr, s.win_ms, s.t_overlap, s.f_overlap, orc.MEL, 128)
+    o_specs, o_imgs, o_mn, o_mx = an.update_specs_and_imgs([wavs[k] for k in sorted(wavs)], 100.0, 258, n_threads=8)
+    assert (o_mn, o_mx) == (mn, mx)
+    for j, k in enumerate(sorted(wavs)):
+        img = ctx.img_read(*k)
+        # bit-exact against the reference arithmetic applied to the GPU's own dB values
+        want = orc.spec_to_img(specs[k], (0, 128), (mn, mx), 258)
+        assert np.array_equal(img, want), k
+        # end to end against the all-CPU pipeline: <= 1 LSB where dB differs in the last digits
+        diff = np.abs(img.astype(np.int32) - o_imgs[j].astype(np.int32))
+        assert diff.max() <= 1, (k, diff.max())
+        assert (img == 0).any() == (o_imgs[j] == 0).any()
+    # set_dB_range only re-quantises (mod.rs:123-126)
+    mn2, mx2 = ctx.update_spec_imgs(40.0, 258)
+    assert (mn2, mx2) == (-40.0, 0.0)
+    assert np.array_equal(ctx.img_read(0, 0), orc.spec_to_img(specs[(0, 0)], (0, 128), (-40.0, 0.0), 258))
+    ctx.release_all()
+
+
+def test_all_silent_tracks_give_zero_images(ctx, orc):
+    ctx.release_all()
+    s = thb.SpecSetting()
+    ctx.spec_batch([dict(pcm=np.zeros(9600, np.float32), id=0, ch=0, sr=48000)], s)
+    mn, mx = ctx.update_spec_imgs(100.0, 258)
+    assert mn == -math.inf and mx == -math.inf  # min(-inf,0) ; max(-inf, -inf-100)
+    assert not ctx.img_read(0, 0).any()
+    ctx.release_all()
+
+
+def test_trackmanager_flow(ctx, orc):
+    """mod.rs:238-274 trackmanager_works, with synthetic tracks at the sample rates of the
+    reference's fixtures (8k, 16k, 22.05k, 24k, 44.1k, 48k, stereo 48k)."""
+    ctx.release_all()
+    srs = [8000, 16000, 22050, 24000, 44100, 48000, 48000]
+    id_list = list(range(len(srs)))
+    tl = TrackList()
+    tm = thb.TrackManager(ctx)
+    wavs = []
+    for i, sr in enumerate(srs):
+        n_ch = 2 if i == 6 else 1
+        wavs.append(np.stack([synth_pcm(sr * 2 + 17 * i, sr, i, ch, 0) for ch in range(n_ch)]))
+    added = tl.add_tracks(id_list[:3], wavs[:3], srs[:3])
+    tm.add_tracks(tl, added)
+    assert added == id_list[:3]
+    added = tl.add_tracks(id_list[3:], wavs[3:], srs[3:])
+    tm.add_tracks(tl, added)
+    assert added == id_list[3:]
+    assert len(tm.spec_imgs) == 0
+    updated, max_sr = tm.apply_track_list_changes(tl)
+    assert sorted(updated) == id_list and max_sr == 48000
+    assert len(tm.spec_imgs) == 8
+    # images: height = ceil(ratio * n_mel) rows, rows above the track's own Nyquist are zero
+    for i, sr in enumerate(srs):
+        img = tm.get_spectrogram((i, 0))
+        spec = tm.get_spec((i, 0))
+        B = spec.shape[1]
+        i0, i1 = orc.hz_range_to_idx(orc.MEL, 0.0, 24000.0, sr, B)
+        assert img.shape == (i1 - i0, spec.shape[0])
+        assert np.array_equal(img, orc.spec_to_img(spec, (i0, i1), (tm.min_dB, tm.max_dB), 258))
+        if i1 > B:
+            assert not img[B:].any()
+        an = orc.Analyzer(sr, 40.0, 4, 1, orc.MEL, 0)
+        assert B == an.n_bins
+    removed = tl.remove_tracks([0])
+    tm.remove_tracks(tl, removed)
+    updated, _ = tm.apply_track_list_changes(tl)
+    assert len(updated) == 0
+    assert tm.get_spectrogram((0, 0)) is None
+    # set_setting recomputes everything (mod.rs:107-115)
+    tm.set_setting(tl, thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear))
+    assert tm.get_spec((5, 0)).shape[1] == 1025
+    ctx.release_all()
+
+
+# ---------------------------------------------------------------------------------------------
+# envelope tiles
+# ---------------------------------------------------------------------------------------------
+def _check_tile(got: bytes, want: bytes, tag):
+    assert len(got) == len(want), tag
+    assert got[:24] == want[:24], tag  # header bit-exact
+    g = np.frombuffer(got, np.float32, offset=24).reshape(-1, 3)
+    w = np.frombuffer(want, np.float32, offset=24).reshape(-1, 3)
+    assert np.array_equal(g[:, :2], w[:, :2]), f"{tag}: min/max must be bit-exact"
+    assert np.abs(g[:, 2] - w[:, 2]).max(initial=0.0) <= 1e-6, tag
+
+
+@pytest.mark.parametrize("level", list(range(0, 13)) + [15, 17])
+def test_waveform_tiles_vs_oracle(ctx, orc, level):
+    n = 1024 * (1 << min(level, 9)) * 2 + 12345
+    x = synth_pcm(n, 48000, 4, 0, 0)
+    spb = 1 << level
+    n_tiles = -(-n // (1024 * spb))
+    for t in sorted({0, 1, n_tiles // 2, n_tiles - 1, n_tiles}):
+        _check_tile(ctx.waveform_tile(x, 9, level, t), orc.encode_waveform_tile(x, 9, level, t), (level, t))
+
+
+def test_waveform_level_and_batch(ctx, orc):
+    import torch
+    xs = [synth_pcm(n, 48000, i, i % 2, 0) for i, n in enumerate((300000, 1 << 18, 12345, 1025))]
+    for level in (0, 3, 9, 11):
+        got = ctx.waveform_level_batch(xs, 5, level)
+        got_dev = ctx.waveform_level_batch([torch.from_numpy(x).cuda() for x in xs], 5, level)
+        for x, g, gd in zip(xs, got, got_dev):
+            n_tiles = -(-x.size // (1024 << level))
+            want = b"".join(orc.encode_waveform_tile(x, 5, level, t) for t in range(n_tiles))
+            assert len(g) == len(want)
+            assert g == gd
+            off = 0
+            for t in range(n_tiles):
+                w = orc.encode_waveform_tile(x, 5, level, t)
+                _check_tile(g[off:off + len(w)], w, (level, t))
+                off += len(w)
+        assert ctx.waveform_level(xs[2], 5, level) == got[2]
+
+
+def test_waveform_unaligned_device_pointer(ctx, orc):
+    import torch
+    x = synth_pcm(70001, 48000, 2, 0, 0)
+    d = torch.from_numpy(np.concatenate([np.zeros(3, np.float32), x])).cuda()[3:]  # 12-byte offset
+    for level in (0, 2, 5, 8):
+        _check_tile(ctx.waveform_tile(d, 1, level, 0), orc.encode_waveform_tile(x, 1, level, 0), level)

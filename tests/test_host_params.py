@@ -1,0 +1,111 @@
+"""CPU tests of the product's host arithmetic through the C ABI (no GPU needed): the library must
+load, export every symbol include/thesia_b200.h declares, and reproduce the oracle's integer
+parameters and f32 tables exactly."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import thesia_b200 as thb
+from thesia_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "thesia_b200.h").read_text()
+    declared = set(re.findall(r"\b(thb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"thb_status"}
+    assert len(declared) >= 35
+    l = C.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(l, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_device_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(thb.ThbError) as e:
+        thb.Context()
+    assert e.value.code == _lib.THB_ERR_CUDA
+
+
+@pytest.mark.parametrize("case", [(40.0, 48000, 4, 1), (40.0, 44100, 4, 1), (2048 / 48.0, 48000, 8, 1),
+                                  (16384 / 96.0, 96000, 16, 1), (40.0, 22050, 4, 2), (1.0, 8000, 1, 1),
+                                  (23.3, 16000, 32, 1), (40.0, 96000, 4, 1)])
+def test_framing_params_match_oracle(orc, case):
+    win_ms, sr, t, f = case
+    s = thb.SpecSetting(win_ms, t, f)
+    assert s.calc_framing_params(sr) == orc.framing_params(win_ms, sr, t, f)
+
+
+def test_n_frames_matches_oracle(orc):
+    for n in (2, 3, 100, 1919, 1920, 1921, 48000, 2113529):
+        for w, h in ((1920, 480), (2048, 512), (2048, 256), (5, 5), (7, 1), (16384, 1024)):
+            assert thb.n_frames(n, w, h) == orc.n_frames(n, w, h)
+
+
+@pytest.mark.parametrize("win,n_fft", [(4, 4), (1920, 2048), (2048, 2048), (1764, 2048), (16384, 16384), (7, 8)])
+def test_window_bit_exact(orc, win, n_fft):
+    assert np.array_equal(thb.calc_normalized_win(win, n_fft), orc.normalized_hann(win, n_fft))
+
+
+@pytest.mark.parametrize("sr,n_fft,n_mel", [(48000, 2048, 128), (24000, 2048, 80), (44100, 2048, 347),
+                                            (96000, 16384, 128), (8000, 256, 40), (16000, 512, 1)])
+def test_mel_fb_bit_exact(orc, sr, n_fft, n_mel):
+    got = thb.calc_mel_fb(sr, n_fft, n_mel)
+    want = orc.mel_fb(sr, n_fft, n_mel)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("sr", [400, 8000, 16000, 22050, 24000, 44100, 48000, 88200, 96000])
+def test_mel_default_rule_matches_oracle(orc, sr):
+    for e in (5, 8, 10, 11, 12, 14):
+        n_fft = 2 ** e
+        got = thb.calc_mel_fb_default(sr, n_fft)
+        assert got.shape[1] == orc.mel_default_n(sr, n_fft), (sr, n_fft)
+        if e in (8, 11):
+            assert np.array_equal(got, orc.mel_fb_default(sr, n_fft))
+
+
+def test_mel_default_sizes_of_the_survey():
+    assert thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel).n_bins(48000) == 347
+    assert thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Mel).n_bins(96000) == 1621
+    assert thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear).n_bins(48000) == 1025
+    assert thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128).n_bins(48000) == 128
+
+
+def test_hz_range_to_idx_matches_oracle(orc):
+    for scale in (0, 1):
+        for sr in (8000, 22050, 44100, 48000):
+            for max_sr in (48000, 96000, 44100):
+                for nb in (128, 347, 1025):
+                    assert thb.hz_range_to_idx(scale, (0.0, max_sr / 2), sr, nb) == \
+                        orc.hz_range_to_idx(scale, 0.0, max_sr / 2, sr, nb)
+    assert thb.hz_range_to_idx(0, (100.0, 100.0), 48000, 10) == (0, 0)
+
+
+def test_waveform_level_bytes():
+    l = _lib.lib()
+    assert l.thb_waveform_level_bytes(4, 1) == 24 + 12 * 2
+    assert l.thb_waveform_level_bytes(1025, 0) == 2 * 24 + 12 * 1025
+    assert l.thb_waveform_level_bytes(0, 3) == 0
+
+
+def test_synth_twin_is_deterministic_and_pcm_like():
+    from thesia_b200.synth import synth_pcm, LOUD, ZERO_GAP
+    a = synth_pcm(48000 * 3, 48000, 5, 0, ZERO_GAP)
+    b = synth_pcm(48000 * 3, 48000, 5, 0, ZERO_GAP)
+    assert np.array_equal(a, b)
+    assert np.all(a[48000:96000] == 0) and np.any(a[:48000] != 0)
+    assert np.all(a * 32768 == np.round(a * 32768))
+    assert np.abs(a).max() < 0.45
+    c1 = synth_pcm(4800, 48000, 5, 1, 0)
+    c0 = synth_pcm(4800, 48000, 5, 0, 0)
+    assert np.all(c1[:7] == 0) and np.abs(c1[7:] - 0.8 * c0[:-7]).max() < 2 / 32768
+    assert np.abs(synth_pcm(4800, 48000, 2, 0, LOUD)).max() > 1.0

@@ -257,3 +257,10 @@ def test_zero_padded_window_centering(orc):
     want = w[960] * np.where(k % 2 == 0, 1.0, -1.0)
     assert np.allclose(st[2].real, want, atol=1e-9)
     assert np.allclose(st[2].imag, 0, atol=1e-9)
+
+
+def test_synth_c_twin_matches_numpy_twin(orc):
+    from thesia_b200.synth import synth_pcm
+    for (n, sr, tr, ch, fl) in [(100003, 48000, 0, 0, 0), (150000, 48000, 63, 1, 2), (50000, 96000, 9, 0, 1),
+                                (300000, 44100, 17, 1, 3)]:
+        assert np.array_equal(orc.synth_pcm(n, sr, tr, ch, fl, n_threads=4), synth_pcm(n, sr, tr, ch, fl))

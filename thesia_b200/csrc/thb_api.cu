@@ -1,0 +1,1196 @@
+// thb_api.cu -- the extern "C" surface of include/thesia_b200.h.
+//
+// Host-side orchestration only: plan cache (SpectrogramAnalyzer::prepare, spectrogram.rs:116-154),
+// the (id, ch) -> spectrogram store (TrackManager.specs / spec_imgs, mod.rs:33-44), stream-ordered
+// device memory, descriptor upload, kernel launches, the 2-float NCCL all-reduce and measurement
+// hooks.  All arithmetic on samples happens in the kernels; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+// the C ABI is the only thing this library exports (everything else is -fvisibility=hidden)
+#pragma GCC visibility push(default)
+#include "../../include/thesia_b200.h"
+#pragma GCC visibility pop
+#include "thb_host.hpp"
+#include "thb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct PlanKey {
+    uint32_t sr;
+    uint64_t hop, win, n_fft;
+    uint32_t freq_scale, n_mel_req;
+    bool operator<(const PlanKey &o) const {
+        return std::tie(sr, hop, win, n_fft, freq_scale, n_mel_req) <
+               std::tie(o.sr, o.hop, o.win, o.n_fft, o.freq_scale, o.n_mel_req);
+    }
+};
+
+struct Plan {
+    thb::PlanDev dev{};
+    std::vector<void *> allocs;
+};
+
+struct Spec {
+    uint64_t id = 0;
+    uint32_t ch = 0, sr = 0;
+    uint64_t T = 0, total_T = 0;
+    uint32_t B = 0, hop = 0, win = 0, n_fft = 0, freq_scale = 0;
+    float *d_spec = nullptr;
+    size_t spec_cap = 0;  // floats
+    uint16_t *d_img = nullptr;
+    size_t img_cap = 0;   // u16 elements
+    uint64_t img_H = 0, img_pitch = 0;
+    int slot = -1;
+};
+
+struct ProfEntry {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0.0;
+    uint64_t launches = 0;
+};
+
+// NCCL through dlopen: the library must load (and every non-collective call must work) on a box
+// without NCCL, and must share torch's copy when the host program is Python.
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load(std::string *err) {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            *err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+            return false;
+        }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            *err = "libnccl is missing a required symbol";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat32 = 7;
+constexpr int kNcclMax = 2;
+
+}  // namespace
+
+struct thb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D staging, overlapped with compute
+    std::mutex mu;
+    std::string last_error;
+
+    std::map<PlanKey, std::unique_ptr<Plan>> plans;
+    std::map<std::pair<uint64_t, uint32_t>, Spec> specs;
+
+    // {max, -min} slots, one per retained spectrogram
+    float *d_slots = nullptr;
+    int slot_cap = 0;
+    std::vector<int> free_slots;
+    float *d_send = nullptr;   // 2 floats: all-reduce buffer
+    float *d_range = nullptr;  // 2 floats: {min_dB, max_dB}
+    float *d_range_tmp = nullptr;
+    float *h_pinned = nullptr;  // small pinned scratch (64 floats)
+
+    // descriptor arena: pinned host mirror + device copy, re-used call after call
+    unsigned char *h_arena = nullptr, *d_arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    cudaEvent_t arena_ev = nullptr;
+    cudaEvent_t h2d_ev = nullptr;
+
+    std::vector<void *> env_outputs;  // device buffers of the last waveform call
+
+    void *nccl_comm = nullptr;
+    int n_ranks = 1, rank = 0;
+
+    bool profiling = false;
+    std::map<std::string, ProfEntry> prof;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t launch_count = 0;
+};
+
+namespace {
+
+int fail(thb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? THB_ERR_NOMEM : THB_ERR_CUDA,        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- measurement hooks -------------------------------------------------------------------------
+struct ProfScope {
+    thb_ctx *ctx;
+    ProfEntry *e = nullptr;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    ProfScope(thb_ctx *c, const char *name, int launches = 1) : ctx(c) {
+        ctx->launch_count += launches;
+        if (!ctx->profiling) return;
+        e = &ctx->prof[name];
+        e->launches += launches;
+        auto get = [&]() {
+            cudaEvent_t ev;
+            if (!ctx->event_pool.empty()) {
+                ev = ctx->event_pool.back();
+                ctx->event_pool.pop_back();
+            } else {
+                cudaEventCreate(&ev);
+            }
+            return ev;
+        };
+        start = get();
+        stop = get();
+        cudaEventRecord(start, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!e) return;
+        cudaEventRecord(stop, ctx->stream);
+        e->pending.emplace_back(start, stop);
+    }
+};
+
+void prof_collect(thb_ctx *ctx) {
+    for (auto &kv : ctx->prof) {
+        for (auto &pr : kv.second.pending) {
+            cudaEventSynchronize(pr.second);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) kv.second.total_ms += ms;
+            ctx->event_pool.push_back(pr.first);
+            ctx->event_pool.push_back(pr.second);
+        }
+        kv.second.pending.clear();
+    }
+}
+
+// ---- descriptor arena --------------------------------------------------------------------------
+int arena_begin(thb_ctx *ctx, size_t need) {
+    CK(cudaEventSynchronize(ctx->arena_ev));  // previous upload has been consumed by the copy engine
+    if (need > ctx->arena_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+        if (ctx->d_arena) cudaFree(ctx->d_arena);
+        ctx->h_arena = ctx->d_arena = nullptr;
+        size_t cap = 1 << 16;
+        while (cap < need) cap <<= 1;
+        CK(cudaMallocHost(&ctx->h_arena, cap));
+        CK(cudaMalloc(&ctx->d_arena, cap));
+        ctx->arena_cap = cap;
+    }
+    ctx->arena_used = 0;
+    return THB_OK;
+}
+template <typename T>
+T *arena_push(thb_ctx *ctx, size_t count, T **dev) {
+    size_t off = (ctx->arena_used + 255) & ~size_t(255);
+    ctx->arena_used = off + sizeof(T) * count;
+    *dev = reinterpret_cast<T *>(ctx->d_arena + off);
+    return reinterpret_cast<T *>(ctx->h_arena + off);
+}
+int arena_commit(thb_ctx *ctx) {
+    if (ctx->arena_used) {
+        CK(cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, ctx->arena_used, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->arena_ev, ctx->stream));
+    return THB_OK;
+}
+
+// ---- plan cache --------------------------------------------------------------------------------
+template <typename T>
+int upload(thb_ctx *ctx, Plan *pl, const std::vector<T> &v, const T **out) {
+    void *d = nullptr;
+    const size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    CK(cudaMalloc(&d, bytes));
+    pl->allocs.push_back(d);
+    if (!v.empty()) CK(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    *out = static_cast<const T *>(d);
+    return THB_OK;
+}
+
+int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) {
+    const thb::Framing f = thb::framing_params(s, sr);
+    if (f.hop == 0 || f.win < 3)
+        return fail(ctx, THB_ERR_INVALID, "window of %llu samples (hop %llu) is too short", (unsigned long long)f.win,
+                    (unsigned long long)f.hop);
+    if (!thb::is_pow2(f.n_fft) || f.n_fft < 4 || f.n_fft > 32768)
+        return fail(ctx, THB_ERR_UNSUPPORTED, "n_fft = %llu: only powers of two in [4, 32768] are supported",
+                    (unsigned long long)f.n_fft);
+    if (s.freq_scale > THB_FREQ_MEL) return fail(ctx, THB_ERR_INVALID, "freq_scale = %u", s.freq_scale);
+    PlanKey key{sr, f.hop, f.win, f.n_fft, s.freq_scale, s.freq_scale == THB_FREQ_MEL ? s.n_mel : 0u};
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) {
+        *out = it->second.get();
+        return THB_OK;
+    }
+    auto pl = std::make_unique<Plan>();
+    thb::PlanDev &d = pl->dev;
+    d.hop = static_cast<int>(f.hop);
+    d.win = static_cast<int>(f.win);
+    d.n_fft = static_cast<int>(f.n_fft);
+    d.nc = d.n_fft / 2;
+    d.pad_left = (d.n_fft - d.win) / 2;
+    d.n_freq = d.nc + 1;
+    // DIF pass plan: radix 8 while possible, the remaining 2 or 4 last
+    int L = 0;
+    while ((1 << L) < d.nc) L++;
+    d.n_pass = 0;
+    while (L >= 3) {
+        d.radix_log2[d.n_pass++] = 3;
+        L -= 3;
+    }
+    if (L) d.radix_log2[d.n_pass++] = L;
+    const std::vector<float> win = thb::normalized_hann(f.win, f.n_fft);
+    int rc = upload(ctx, pl.get(), win, &d.window);
+    if (rc) return rc;
+    const std::vector<float> tw = thb::twiddle_table(f.n_fft);
+    const float *twp = nullptr;
+    rc = upload(ctx, pl.get(), tw, &twp);
+    if (rc) return rc;
+    d.twiddle = reinterpret_cast<const float2 *>(twp);
+    d.n_mel = 0;
+    d.max_band_len = 0;
+    if (s.freq_scale == THB_FREQ_MEL) {
+        const thb::MelBank mb = thb::mel_bank(sr, f.n_fft, s.n_mel);
+        if (mb.n_mel == 0) return fail(ctx, THB_ERR_INVALID, "mel filterbank is empty for sr %u n_fft %d", sr, d.n_fft);
+        d.n_mel = static_cast<int>(mb.n_mel);
+        if ((rc = upload(ctx, pl.get(), mb.k0, &d.mel_k0))) return rc;
+        if ((rc = upload(ctx, pl.get(), mb.ptr, &d.mel_ptr))) return rc;
+        if ((rc = upload(ctx, pl.get(), mb.w, &d.mel_w))) return rc;
+        for (uint32_t m = 0; m < mb.n_mel; m++)
+            d.max_band_len = std::max<int>(d.max_band_len, static_cast<int>(mb.ptr[m + 1] - mb.ptr[m]));
+    }
+    d.n_bins = d.n_mel ? d.n_mel : d.n_freq;
+    CK(cudaStreamSynchronize(ctx->stream));  // the host vectors above die here
+    *out = pl.get();
+    ctx->plans[key] = std::move(pl);
+    return THB_OK;
+}
+
+// ---- slots -------------------------------------------------------------------------------------
+int slot_alloc(thb_ctx *ctx, int *slot) {
+    if (ctx->free_slots.empty()) {
+        const int new_cap = ctx->slot_cap ? ctx->slot_cap * 2 : 1024;
+        float *nd = nullptr;
+        CK(cudaMalloc(&nd, sizeof(float) * 2 * new_cap));
+        cudaError_t e = thb::launch_minmax_init(nd, new_cap, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax init: %s", cudaGetErrorString(e));
+        if (ctx->d_slots) {
+            CK(cudaMemcpyAsync(nd, ctx->d_slots, sizeof(float) * 2 * ctx->slot_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            // slot pointers inside live descriptors are rebuilt per call, so moving is safe
+            cudaFree(ctx->d_slots);
+        }
+        for (int i = new_cap - 1; i >= ctx->slot_cap; i--) ctx->free_slots.push_back(i);
+        ctx->d_slots = nd;
+        ctx->slot_cap = new_cap;
+    }
+    *slot = ctx->free_slots.back();
+    ctx->free_slots.pop_back();
+    return THB_OK;
+}
+
+void spec_free(thb_ctx *ctx, Spec &s) {
+    if (s.d_spec) cudaFreeAsync(s.d_spec, ctx->stream);
+    if (s.d_img) cudaFreeAsync(s.d_img, ctx->stream);
+    s.d_spec = nullptr;
+    s.d_img = nullptr;
+    if (s.slot >= 0) {
+        // a dead slot must not take part in the global reduce
+        thb::launch_minmax_init(ctx->d_slots + 2 * s.slot, 1, ctx->stream);
+        ctx->free_slots.push_back(s.slot);
+        s.slot = -1;
+    }
+}
+
+Spec *find_spec(thb_ctx *ctx, uint64_t id, uint32_t ch) {
+    auto it = ctx->specs.find({id, ch});
+    return it == ctx->specs.end() ? nullptr : &it->second;
+}
+
+int global_minmax_on_stream(thb_ctx *ctx, float dB_range) {
+    cudaError_t e;
+    {
+        ProfScope ps(ctx, "minmax_reduce", 2);
+        e = thb::launch_minmax_reduce(ctx->d_slots, ctx->slot_cap, ctx->d_send, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax reduce: %s", cudaGetErrorString(e));
+        if (ctx->nccl_comm) {
+            // the single collective of the path: {max, -min} under max  
+            const int r = g_nccl.AllReduce(ctx->d_send, ctx->d_send, 2, kNcclFloat32, kNcclMax, ctx->nccl_comm, ctx->stream);
+            if (r != 0)
+                return fail(ctx, THB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        }
+        e = thb::launch_minmax_finalize(ctx->d_send, dB_range, ctx->d_range, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax finalize: %s", cudaGetErrorString(e));
+    }
+    return THB_OK;
+}
+
+uint64_t level_bytes(uint64_t len, uint32_t level) {
+    const uint64_t spb = level < 41 ? (1ull << level) : (1ull << 40);
+    const uint64_t bins = (len + spb - 1) / spb;
+    const uint64_t tiles = (bins + 1023) / 1024;
+    return tiles * 24 + bins * 12;
+}
+
+void put_u32(uint8_t *p, uint32_t v) {
+    p[0] = v & 0xff; p[1] = (v >> 8) & 0xff; p[2] = (v >> 16) & 0xff; p[3] = (v >> 24) & 0xff;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int thb_abi_version(void) { return THB_ABI_VERSION; }
+
+const char *thb_last_error(const thb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int thb_ctx_create(int device, void *cuda_stream, thb_ctx **out) {
+    thb_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, THB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, THB_ERR_CUDA, "no CUDA device: thesia_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, THB_ERR_INVALID, "device %d of %d", device, n_dev);
+    CK(cudaSetDevice(device));
+    ctx = new thb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return fail(nullptr, THB_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        ctx->own_stream = true;
+    }
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->arena_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->h2d_ev, cudaEventDisableTiming);
+    cudaMalloc(&ctx->d_send, sizeof(float) * 2);
+    cudaMalloc(&ctx->d_range, sizeof(float) * 2);
+    cudaMalloc(&ctx->d_range_tmp, sizeof(float) * 2);
+    cudaMallocHost(&ctx->h_pinned, sizeof(float) * 64);
+    // keep freed blocks cached in the stream-ordered pool: the path re-allocates the same sizes
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !ctx->d_send || !ctx->d_range || !ctx->h_pinned) {
+        thb_ctx_destroy(ctx);
+        return fail(nullptr, THB_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return THB_OK;
+}
+
+void thb_ctx_destroy(thb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    thb_comm_destroy(ctx);
+    for (auto &kv : ctx->specs) spec_free(ctx, kv.second);
+    ctx->specs.clear();
+    for (void *p : ctx->env_outputs) cudaFreeAsync(p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->plans)
+        for (void *p : kv.second->allocs) cudaFree(p);
+    prof_collect(ctx);
+    for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
+    if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->d_send) cudaFree(ctx->d_send);
+    if (ctx->d_range) cudaFree(ctx->d_range);
+    if (ctx->d_range_tmp) cudaFree(ctx->d_range_tmp);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->arena_ev) cudaEventDestroy(ctx->arena_ev);
+    if (ctx->h2d_ev) cudaEventDestroy(ctx->h2d_ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int thb_set_stream(thb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return THB_OK;
+}
+
+int thb_synchronize(thb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_host_alloc(size_t bytes, void **out) {
+    thb_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, THB_ERR_INVALID, "out is NULL");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return THB_OK;
+}
+int thb_host_free(void *p) {
+    thb_ctx *ctx = nullptr;
+    if (p) CK(cudaFreeHost(p));
+    return THB_OK;
+}
+
+// ---- host parameter arithmetic -------------------------------------------------------------------
+int thb_framing_params(const thb_setting *s, uint32_t sr, uint64_t *hop, uint64_t *win, uint64_t *n_fft) {
+    if (!s || s->t_overlap == 0) return fail(nullptr, THB_ERR_INVALID, "setting is NULL or t_overlap == 0");
+    const thb::Framing f = thb::framing_params(*s, sr);
+    if (hop) *hop = f.hop;
+    if (win) *win = f.win;
+    if (n_fft) *n_fft = f.n_fft;
+    return THB_OK;
+}
+
+uint64_t thb_n_frames(uint64_t len, uint64_t win, uint64_t hop) { return thb::n_frames(len, win, hop); }
+
+int thb_n_bins(const thb_setting *s, uint32_t sr, uint32_t *n_bins) {
+    if (!s || !n_bins || s->t_overlap == 0) return fail(nullptr, THB_ERR_INVALID, "bad argument");
+    const thb::Framing f = thb::framing_params(*s, sr);
+    if (s->freq_scale == THB_FREQ_LINEAR) {
+        *n_bins = static_cast<uint32_t>(f.n_fft / 2 + 1);
+    } else if (s->n_mel) {
+        *n_bins = s->n_mel;
+    } else {
+        *n_bins = thb::mel_bank(sr, f.n_fft, 0).n_mel;
+    }
+    return THB_OK;
+}
+
+int thb_hann_window(uint64_t win, uint64_t n_fft, float *out) {
+    if (!out) return fail(nullptr, THB_ERR_INVALID, "out is NULL");
+    const std::vector<float> w = thb::normalized_hann(win, n_fft);
+    memcpy(out, w.data(), sizeof(float) * w.size());
+    return THB_OK;
+}
+
+int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t *n_mel_out) {
+    if (n_fft < 2 || (n_fft & 1)) return fail(nullptr, THB_ERR_INVALID, "n_fft must be even");
+    const thb::MelBank mb = thb::mel_bank(sr, n_fft, n_mel);
+    if (n_mel_out) *n_mel_out = mb.n_mel;
+    if (out) {
+        const std::vector<float> d = mb.dense();
+        memcpy(out, d.data(), sizeof(float) * d.size());
+    }
+    return THB_OK;
+}
+
+int thb_hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uint64_t n_bins, uint64_t *i0,
+                        uint64_t *i1) {
+    if (!i0 || !i1 || freq_scale > THB_FREQ_MEL) return fail(nullptr, THB_ERR_INVALID, "bad argument");
+    thb::hz_range_to_idx(freq_scale, hz0, hz1, sr, n_bins, i0, i1);
+    return THB_OK;
+}
+
+// ---- update_specs ---------------------------------------------------------------------------------
+int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_setting *setting, thb_spec_out *outs) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return THB_OK;
+    if (!tracks || !setting || setting->t_overlap == 0 || setting->f_overlap == 0 || !(setting->win_ms > 0.0))
+        return fail(ctx, THB_ERR_INVALID, "tracks/setting NULL, or win_ms/t_overlap/f_overlap not positive");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+
+    struct Item {
+        const Plan *plan;
+        uint64_t total_T, f_begin, f_count, full_len;
+        const float *d_pcm;
+        void *staging;
+    };
+    std::vector<Item> items(n);
+    std::map<const Plan *, std::vector<size_t>> groups;
+    // ---- validate everything before touching device state ----
+    for (size_t i = 0; i < n; i++) {
+        const thb_track &t = tracks[i];
+        if (!t.pcm) return fail(ctx, THB_ERR_INVALID, "track %zu: pcm is NULL", i);
+        const uint64_t full_len = t.full_len ? t.full_len : t.len;
+        if (full_len < 2) return fail(ctx, THB_ERR_INVALID, "track %zu: %llu samples (need >= 2; the reference's reflect pad is undefined below that)", i, (unsigned long long)full_len);
+        if (t.pcm_offset + t.len > full_len) return fail(ctx, THB_ERR_INVALID, "track %zu: slice exceeds the file", i);
+        const Plan *pl = nullptr;
+        int rc = get_plan(ctx, *setting, t.sr, &pl);
+        if (rc) return rc;
+        Item &it = items[i];
+        it.plan = pl;
+        it.full_len = full_len;
+        it.total_T = thb::n_frames(full_len, pl->dev.win, pl->dev.hop);
+        it.f_begin = t.frame_begin;
+        if (it.f_begin > it.total_T) return fail(ctx, THB_ERR_INVALID, "track %zu: frame_begin beyond the file", i);
+        it.f_count = t.frame_count ? t.frame_count : it.total_T - it.f_begin;
+        if (it.f_begin + it.f_count > it.total_T) return fail(ctx, THB_ERR_INVALID, "track %zu: frame range beyond the file", i);
+        // the slice must hold every sample the frame range touches (after reflection)
+        if (it.f_count) {
+            const long long W = pl->dev.win, H = pl->dev.hop, N = static_cast<long long>(full_len);
+            const long long lo = static_cast<long long>(it.f_begin) * H - W / 2;
+            const long long hi = static_cast<long long>(it.f_begin + it.f_count - 1) * H - W / 2 + W - 1;
+            long long need_lo = lo < 0 ? 0 : lo, need_hi = hi >= N ? N - 1 : hi;
+            if (lo < 0) need_hi = std::max(need_hi, std::min(N - 1, -lo));
+            if (hi >= N) need_lo = std::min(need_lo, std::max(0ll, 2 * (N - 1) - hi));
+            if (-lo >= N || hi >= 2 * N - 1) { need_lo = 0; need_hi = N - 1; }  // multi-wrap reflect
+            if (need_lo < static_cast<long long>(t.pcm_offset) || need_hi >= static_cast<long long>(t.pcm_offset + t.len))
+                return fail(ctx, THB_ERR_INVALID, "track %zu: frames [%llu,+%llu) need samples [%lld,%lld] but the slice holds [%llu,%llu)", i,
+                            (unsigned long long)it.f_begin, (unsigned long long)it.f_count, need_lo, need_hi,
+                            (unsigned long long)t.pcm_offset, (unsigned long long)(t.pcm_offset + t.len));
+        }
+        it.d_pcm = nullptr;
+        it.staging = nullptr;
+        groups[pl].push_back(i);
+    }
+    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * n + 4096);
+    if (rc) return rc;
+
+    // ---- device buffers; host PCM goes through stream-ordered staging ----
+    bool any_host = false;
+    for (size_t i = 0; i < n; i++) {
+        const thb_track &t = tracks[i];
+        Item &it = items[i];
+        Spec &sp = ctx->specs[{t.id, t.ch}];
+        if (sp.slot < 0) {
+            rc = slot_alloc(ctx, &sp.slot);
+            if (rc) return rc;
+        }
+        const thb::PlanDev &pd = it.plan->dev;
+        sp.id = t.id; sp.ch = t.ch; sp.sr = t.sr;
+        sp.T = it.f_count; sp.total_T = it.total_T;
+        sp.B = pd.n_bins; sp.hop = pd.hop; sp.win = pd.win; sp.n_fft = pd.n_fft;
+        sp.freq_scale = setting->freq_scale;
+        const size_t need = static_cast<size_t>(sp.T) * sp.B;
+        if (need > sp.spec_cap || !sp.d_spec) {
+            if (sp.d_spec) CK(cudaFreeAsync(sp.d_spec, ctx->stream));
+            sp.d_spec = nullptr;
+            CK(cudaMallocAsync(reinterpret_cast<void **>(&sp.d_spec), sizeof(float) * (need ? need : 1), ctx->stream));
+            sp.spec_cap = need;
+        }
+        if (is_device_ptr(t.pcm)) {
+            it.d_pcm = t.pcm;
+        } else {
+            any_host = true;
+            CK(cudaMallocAsync(&it.staging, sizeof(float) * t.len + 64, ctx->stream));
+            CK(cudaMemcpyAsync(it.staging, t.pcm, sizeof(float) * t.len, cudaMemcpyHostToDevice, ctx->stream));
+            it.d_pcm = static_cast<const float *>(it.staging);
+        }
+    }
+    if (any_host) CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
+
+    // ---- descriptors, one array per plan group ----
+    struct Launch {
+        const Plan *plan;
+        thb::TrackDesc *d_desc;
+        int count;
+        long long max_frames;
+    };
+    std::vector<Launch> launches;
+    for (auto &g : groups) {
+        thb::TrackDesc *d_desc = nullptr;
+        thb::TrackDesc *h = arena_push<thb::TrackDesc>(ctx, g.second.size(), &d_desc);
+        long long max_frames = 0;
+        for (size_t j = 0; j < g.second.size(); j++) {
+            const size_t i = g.second[j];
+            const thb_track &t = tracks[i];
+            const Item &it = items[i];
+            const Spec &sp = ctx->specs[{t.id, t.ch}];
+            h[j].pcm = it.d_pcm;
+            h[j].pcm_offset = static_cast<long long>(t.pcm_offset);
+            h[j].slice_len = static_cast<long long>(t.len);
+            h[j].full_len = static_cast<long long>(it.full_len);
+            h[j].frame_begin = static_cast<long long>(it.f_begin);
+            h[j].n_frames = static_cast<long long>(it.f_count);
+            h[j].out = sp.d_spec;
+            h[j].minmax = ctx->d_slots + 2 * sp.slot;
+            max_frames = std::max(max_frames, h[j].n_frames);
+        }
+        launches.push_back({g.first, d_desc, static_cast<int>(g.second.size()), max_frames});
+    }
+    rc = arena_commit(ctx);
+    if (rc) return rc;
+    // reset the {max, -min} slots of the channels being recomputed
+    for (const Launch &l : launches) {
+        cudaError_t e = thb::launch_minmax_init_tracks(l.d_desc, l.count, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax init: %s", cudaGetErrorString(e));
+        ctx->launch_count += 1;
+    }
+
+    // ---- K1/K2/K3: one launch per (sr, win, n_fft) group ----
+    for (const Launch &l : launches) {
+        const thb::PlanDev &pd = l.plan->dev;
+        ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", (l.count + 65534) / 65535);
+        cudaError_t e;
+        if (thb::stft_fast_supported(pd))
+            e = thb::launch_stft_fast(pd, l.d_desc, l.count, l.max_frames, ctx->sm_count, ctx->stream);
+        else
+            e = thb::launch_stft_generic(pd, l.d_desc, l.count, l.max_frames, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "stft launch: %s", cudaGetErrorString(e));
+    }
+    // ---- outputs ----
+    bool any_host_out = false;
+    for (size_t i = 0; i < n; i++) {
+        const Item &it = items[i];
+        if (it.staging) CK(cudaFreeAsync(it.staging, ctx->stream));
+        if (!outs) continue;
+        const Spec &sp = ctx->specs[{tracks[i].id, tracks[i].ch}];
+        outs[i].n_frames = sp.T;
+        outs[i].total_frames = sp.total_T;
+        outs[i].n_bins = sp.B;
+        outs[i].hop = sp.hop;
+        outs[i].win = sp.win;
+        outs[i].n_fft = sp.n_fft;
+        if (outs[i].spec_host) {
+            const uint64_t need = sp.T * sp.B;
+            if (outs[i].spec_host_cap < need) {
+                cudaStreamSynchronize(ctx->stream);
+                return fail(ctx, THB_ERR_SMALL_BUFFER, "track %zu: spec_host holds %llu floats, need %llu", i,
+                            (unsigned long long)outs[i].spec_host_cap, (unsigned long long)need);
+            }
+            if (need) CK(cudaMemcpyAsync(outs[i].spec_host, sp.d_spec, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
+            any_host_out = true;
+        }
+    }
+    // Host buffers belong to the caller again when we return.
+    if (any_host_out) CK(cudaStreamSynchronize(ctx->stream));
+    else if (any_host) CK(cudaEventSynchronize(ctx->h2d_ev));
+    return THB_OK;
+}
+
+int thb_spec_put(thb_ctx *ctx, uint64_t id, uint32_t ch, uint32_t sr, uint32_t freq_scale, const float *spec,
+                 uint64_t n_frames, uint32_t n_bins) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if ((!spec && n_frames * n_bins) || freq_scale > THB_FREQ_MEL) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec &sp = ctx->specs[{id, ch}];
+    if (sp.slot < 0) {
+        int rc = slot_alloc(ctx, &sp.slot);
+        if (rc) return rc;
+    }
+    sp.id = id; sp.ch = ch; sp.sr = sr; sp.T = n_frames; sp.total_T = n_frames; sp.B = n_bins;
+    sp.hop = sp.win = sp.n_fft = 0;
+    sp.freq_scale = freq_scale;
+    const size_t need = static_cast<size_t>(n_frames) * n_bins;
+    if (need > sp.spec_cap || !sp.d_spec) {
+        if (sp.d_spec) CK(cudaFreeAsync(sp.d_spec, ctx->stream));
+        sp.d_spec = nullptr;
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&sp.d_spec), sizeof(float) * (need ? need : 1), ctx->stream));
+        sp.spec_cap = need;
+    }
+    if (need) CK(cudaMemcpyAsync(sp.d_spec, spec, sizeof(float) * need, cudaMemcpyDefault, ctx->stream));
+    cudaError_t e = thb::launch_minmax_init(ctx->d_slots + 2 * sp.slot, 1, ctx->stream);
+    if (e == cudaSuccess) {
+        ProfScope ps(ctx, "minmax_array", 2);
+        e = thb::launch_minmax_array(sp.d_spec, need, ctx->d_slots + 2 * sp.slot, ctx->sm_count, ctx->stream);
+    }
+    if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax: %s", cudaGetErrorString(e));
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's buffer is free again
+    return THB_OK;
+}
+
+int thb_spec_read(thb_ctx *ctx, uint64_t id, uint32_t ch, float *out, uint64_t cap, uint64_t *n_frames, uint32_t *n_bins) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    if (n_frames) *n_frames = sp->T;
+    if (n_bins) *n_bins = sp->B;
+    if (!out) return THB_OK;
+    const uint64_t need = sp->T * sp->B;
+    if (cap < need) return fail(ctx, THB_ERR_SMALL_BUFFER, "need %llu floats", (unsigned long long)need);
+    if (need) CK(cudaMemcpyAsync(out, sp->d_spec, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_spec_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const float **dptr, uint64_t *n_frames, uint32_t *n_bins) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    if (dptr) *dptr = sp->d_spec;
+    if (n_frames) *n_frames = sp->T;
+    if (n_bins) *n_bins = sp->B;
+    return THB_OK;
+}
+
+int thb_spec_minmax(thb_ctx *ctx, uint64_t id, uint32_t ch, float *mn, float *mx) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_slots + 2 * sp->slot, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mx) *mx = ctx->h_pinned[0];
+    if (mn) *mn = -ctx->h_pinned[1];
+    return THB_OK;
+}
+
+int thb_release(thb_ctx *ctx, uint64_t id, uint32_t ch) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    auto it = ctx->specs.find({id, ch});
+    if (it == ctx->specs.end()) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    spec_free(ctx, it->second);
+    ctx->specs.erase(it);
+    return THB_OK;
+}
+
+int thb_release_all(thb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (auto &kv : ctx->specs) spec_free(ctx, kv.second);
+    ctx->specs.clear();
+    return THB_OK;
+}
+
+// ---- update_spec_imgs -----------------------------------------------------------------------------
+int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_slots) {
+        int s;
+        int rc = slot_alloc(ctx, &s);
+        if (rc) return rc;
+        ctx->free_slots.push_back(s);
+    }
+    int rc = global_minmax_on_stream(ctx, dB_range);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_range, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (min_dB) *min_dB = ctx->h_pinned[0];
+    if (max_dB) *max_dB = ctx->h_pinned[1];
+    return THB_OK;
+}
+
+static int img_prepare(thb_ctx *ctx, Spec &sp, uint64_t H) {
+    const uint64_t pitch = (sp.T + 63) & ~uint64_t(63);
+    const size_t need = static_cast<size_t>(H) * pitch;
+    if (need > sp.img_cap || !sp.d_img) {
+        if (sp.d_img) CK(cudaFreeAsync(sp.d_img, ctx->stream));
+        sp.d_img = nullptr;
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&sp.d_img), sizeof(uint16_t) * (need ? need : 1), ctx->stream));
+        sp.img_cap = need;
+    }
+    sp.img_H = H;
+    sp.img_pitch = pitch;
+    return THB_OK;
+}
+
+int thb_spec_to_img(thb_ctx *ctx, uint64_t id, uint32_t ch, uint64_t i0, uint64_t i1, float min_dB, float max_dB,
+                    uint32_t colormap_length, uint16_t *out, uint64_t cap) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!out || i1 < i0 || colormap_length == 0) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    const uint64_t H = i1 - i0;
+    if (cap < H * sp->T) return fail(ctx, THB_ERR_SMALL_BUFFER, "need %llu pixels", (unsigned long long)(H * sp->T));
+    if (H == 0 || sp->T == 0) return THB_OK;
+    // a scratch image, not the retained one
+    uint16_t *d_tmp = nullptr;
+    const uint64_t pitch = (sp->T + 63) & ~uint64_t(63);
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_tmp), sizeof(uint16_t) * H * pitch, ctx->stream));
+    int rc = arena_begin(ctx, sizeof(thb::ImgDesc) + 1024);
+    if (rc) return rc;
+    thb::ImgDesc *d_desc = nullptr;
+    thb::ImgDesc *h = arena_push<thb::ImgDesc>(ctx, 1, &d_desc);
+    h->spec = sp->d_spec; h->img = d_tmp; h->T = static_cast<long long>(sp->T); h->B = static_cast<int>(sp->B);
+    h->i0 = static_cast<int>(i0); h->H = static_cast<int>(H); h->pitch = static_cast<long long>(pitch);
+    float *d_rng = nullptr;
+    float *h_rng = arena_push<float>(ctx, 2, &d_rng);
+    h_rng[0] = min_dB; h_rng[1] = max_dB;
+    if ((rc = arena_commit(ctx))) return rc;
+    {
+        ProfScope ps(ctx, "spec_to_img");
+        cudaError_t e = thb::launch_spec_to_img(d_desc, 1, h->T, h->H, d_rng, colormap_length, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spec_to_img: %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemcpy2DAsync(out, sizeof(uint16_t) * sp->T, d_tmp, sizeof(uint16_t) * pitch, sizeof(uint16_t) * sp->T, H,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_tmp, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length, uint32_t max_sr,
+                         const uint64_t *only_ids, size_t n_only, float *min_dB, float *max_dB) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (colormap_length == 0) return fail(ctx, THB_ERR_INVALID, "colormap_length == 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_slots) {
+        int s;
+        int rc = slot_alloc(ctx, &s);
+        if (rc) return rc;
+        ctx->free_slots.push_back(s);
+    }
+    if (max_sr == 0)
+        for (auto &kv : ctx->specs) max_sr = std::max(max_sr, kv.second.sr);  // tracklist.max_sr() (track.rs:371-376)
+    const size_t n = ctx->specs.size();
+    int rc = arena_begin(ctx, (sizeof(thb::ImgDesc) + 64) * n + 1024);
+    if (rc) return rc;
+    thb::ImgDesc *d_desc = nullptr;
+    thb::ImgDesc *h = n ? arena_push<thb::ImgDesc>(ctx, n, &d_desc) : nullptr;
+    long long max_T = 0;
+    int max_H = 0;
+    size_t j = 0;
+    for (auto &kv : ctx->specs) {
+        Spec &sp = kv.second;
+        if (only_ids) {
+            bool wanted = false;
+            for (size_t q = 0; q < n_only && !wanted; q++) wanted = only_ids[q] == sp.id;
+            if (!wanted) continue;
+        }
+        uint64_t i0 = 0, i1 = 0;
+        // i_freq_range = hz_range_to_idx((0, max_sr / 2), sr, n_bins)  (mod.rs:208-213)
+        thb::hz_range_to_idx(sp.freq_scale, 0.0f, static_cast<float>(max_sr) / 2.0f, sp.sr, sp.B, &i0, &i1);
+        if ((rc = img_prepare(ctx, sp, i1 - i0))) return rc;
+        h[j].spec = sp.d_spec; h[j].img = sp.d_img; h[j].T = static_cast<long long>(sp.T); h[j].B = static_cast<int>(sp.B);
+        h[j].i0 = static_cast<int>(i0); h[j].H = static_cast<int>(i1 - i0); h[j].pitch = static_cast<long long>(sp.img_pitch);
+        max_T = std::max(max_T, h[j].T);
+        max_H = std::max(max_H, h[j].H);
+        j++;
+    }
+    if ((rc = arena_commit(ctx))) return rc;
+    if ((rc = global_minmax_on_stream(ctx, dB_range))) return rc;
+    if (j) {
+        ProfScope ps(ctx, "spec_to_img", static_cast<int>((j + 65534) / 65535));
+        cudaError_t e = thb::launch_spec_to_img(d_desc, static_cast<int>(j), max_T, max_H, ctx->d_range, colormap_length, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spec_to_img: %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_range, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (min_dB) *min_dB = ctx->h_pinned[0];
+    if (max_dB) *max_dB = ctx->h_pinned[1];
+    return THB_OK;
+}
+
+int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t cap, uint64_t *height, uint64_t *width) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp || !sp->d_img) return fail(ctx, THB_ERR_NOT_FOUND, "no image for (%llu, %u)", (unsigned long long)id, ch);
+    if (height) *height = sp->img_H;
+    if (width) *width = sp->T;
+    if (!out) return THB_OK;
+    if (cap < sp->img_H * sp->T) return fail(ctx, THB_ERR_SMALL_BUFFER, "need %llu pixels", (unsigned long long)(sp->img_H * sp->T));
+    if (sp->img_H && sp->T)
+        CK(cudaMemcpy2DAsync(out, sizeof(uint16_t) * sp->T, sp->d_img, sizeof(uint16_t) * sp->img_pitch,
+                             sizeof(uint16_t) * sp->T, sp->img_H, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr, uint64_t *height, uint64_t *width,
+                       uint64_t *pitch) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp || !sp->d_img) return fail(ctx, THB_ERR_NOT_FOUND, "no image for (%llu, %u)", (unsigned long long)id, ch);
+    if (dptr) *dptr = sp->d_img;
+    if (height) *height = sp->img_H;
+    if (width) *width = sp->T;
+    if (pitch) *pitch = sp->img_pitch;
+    return THB_OK;
+}
+
+// ---- waveform tiles ---------------------------------------------------------------------------------
+uint64_t thb_waveform_level_bytes(uint64_t len, uint32_t level) { return level_bytes(len, level); }
+
+int thb_waveform_level_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, uint64_t revision, uint32_t level,
+                             uint8_t **host_out, const size_t *caps, size_t *written, const uint8_t **dev_out) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return THB_OK;
+    if (!tracks) return fail(ctx, THB_ERR_INVALID, "tracks is NULL");
+    if (level > 40) return fail(ctx, THB_ERR_INVALID, "level %u", level);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (void *p : ctx->env_outputs) CK(cudaFreeAsync(p, ctx->stream));
+    ctx->env_outputs.clear();
+    int rc = arena_begin(ctx, (sizeof(thb::EnvDesc) + 64) * n + 1024);
+    if (rc) return rc;
+    thb::EnvDesc *d_desc = nullptr;
+    thb::EnvDesc *h = arena_push<thb::EnvDesc>(ctx, n, &d_desc);
+    std::vector<void *> staging(n, nullptr);
+    std::vector<uint64_t> bytes(n);
+    long long max_len = 0;
+    bool any_host = false;
+    for (size_t i = 0; i < n; i++) {
+        const thb_track &t = tracks[i];
+        if (!t.pcm && t.len) return fail(ctx, THB_ERR_INVALID, "track %zu: pcm is NULL", i);
+        bytes[i] = level_bytes(t.len, level);
+        if (host_out && host_out[i] && caps && caps[i] < bytes[i])
+            return fail(ctx, THB_ERR_SMALL_BUFFER, "track %zu: need %llu bytes", i, (unsigned long long)bytes[i]);
+        const float *d_pcm = t.pcm;
+        if (t.len && !is_device_ptr(t.pcm)) {
+            CK(cudaMallocAsync(&staging[i], sizeof(float) * t.len + 64, ctx->stream));
+            CK(cudaMemcpyAsync(staging[i], t.pcm, sizeof(float) * t.len, cudaMemcpyHostToDevice, ctx->stream));
+            d_pcm = static_cast<const float *>(staging[i]);
+            any_host = true;
+        }
+        void *d_out = nullptr;
+        CK(cudaMallocAsync(&d_out, bytes[i] ? bytes[i] : 4, ctx->stream));
+        ctx->env_outputs.push_back(d_out);
+        h[i].pcm = d_pcm;
+        h[i].len = static_cast<long long>(t.len);
+        h[i].out = static_cast<uint8_t *>(d_out);
+        max_len = std::max(max_len, h[i].len);
+        if (dev_out) dev_out[i] = static_cast<const uint8_t *>(d_out);
+        if (written) written[i] = bytes[i];
+    }
+    if ((rc = arena_commit(ctx))) return rc;
+    {
+        ProfScope ps(ctx, "envelope", static_cast<int>((n + 65534) / 65535));
+        cudaError_t e = thb::launch_envelope(d_desc, static_cast<int>(n), max_len, level, revision, 0, 0, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "envelope: %s", cudaGetErrorString(e));
+    }
+    bool any_out = false;
+    for (size_t i = 0; i < n; i++) {
+        if (staging[i]) CK(cudaFreeAsync(staging[i], ctx->stream));
+        if (host_out && host_out[i] && bytes[i]) {
+            CK(cudaMemcpyAsync(host_out[i], ctx->env_outputs[i], bytes[i], cudaMemcpyDeviceToHost, ctx->stream));
+            any_out = true;
+        }
+    }
+    if (any_out || any_host) CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_waveform_level(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level, uint8_t *out,
+                       size_t cap, size_t *written) {
+    thb_track t{};
+    t.pcm = pcm;
+    t.len = len;
+    uint8_t *outs[1] = {out};
+    size_t caps[1] = {cap};
+    size_t wr[1] = {0};
+    if (!out) {
+        if (written) *written = level_bytes(len, level);
+        return THB_OK;
+    }
+    int rc = thb_waveform_level_batch(ctx, &t, 1, revision, level, outs, caps, wr, nullptr);
+    if (written) *written = wr[0] ? wr[0] : level_bytes(len, level);
+    return rc;
+}
+
+int thb_waveform_tile(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level,
+                      uint32_t tile_index, uint8_t *out, size_t cap, size_t *written) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    // header arithmetic of encode_waveform_tile with its saturating ops (render_tiles.rs:233-242)
+    const uint64_t spb = level < 64 ? (1ull << level) : UINT64_MAX;
+    const uint64_t tile_samples = spb > UINT64_MAX / 1024 ? UINT64_MAX : spb * 1024;
+    const uint64_t start = (tile_index && tile_samples > UINT64_MAX / tile_index) ? UINT64_MAX : tile_samples * tile_index;
+    const uint64_t end_unclamped = start > UINT64_MAX - tile_samples ? UINT64_MAX : start + tile_samples;
+    const uint64_t end = std::min<uint64_t>(len, end_unclamped);
+    const uint64_t bin_count = start >= end ? 0 : (end - start + spb - 1) / spb;
+    const size_t need = 24 + 12 * bin_count;
+    if (written) *written = need;
+    if (!out) return THB_OK;
+    if (cap < need) return fail(ctx, THB_ERR_SMALL_BUFFER, "need %zu bytes", need);
+    if (bin_count == 0) {
+        for (int i = 0; i < 8; i++) out[i] = static_cast<uint8_t>(revision >> (8 * i));
+        put_u32(out + 8, 0);
+        put_u32(out + 12, static_cast<uint32_t>(std::min<uint64_t>(spb, 0xffffffffull)));
+        put_u32(out + 16, tile_index);
+        put_u32(out + 20, 0);
+        return THB_OK;
+    }
+    if (!pcm) return fail(ctx, THB_ERR_INVALID, "pcm is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    int rc = arena_begin(ctx, sizeof(thb::EnvDesc) + 1024);
+    if (rc) return rc;
+    thb::EnvDesc *d_desc = nullptr;
+    thb::EnvDesc *h = arena_push<thb::EnvDesc>(ctx, 1, &d_desc);
+    void *staging = nullptr;
+    const float *d_pcm = pcm;
+    if (!is_device_ptr(pcm)) {
+        // only the tile's own samples cross PCIe; the kernel indexes from the file start
+        const uint64_t cnt = end - start;
+        CK(cudaMallocAsync(&staging, sizeof(float) * cnt + 64, ctx->stream));
+        CK(cudaMemcpyAsync(staging, pcm + start, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+        d_pcm = static_cast<const float *>(staging) - start;
+    }
+    void *d_out = nullptr;
+    CK(cudaMallocAsync(&d_out, need, ctx->stream));
+    h->pcm = d_pcm;
+    h->len = static_cast<long long>(len);
+    h->out = static_cast<uint8_t *>(d_out);
+    if ((rc = arena_commit(ctx))) return rc;
+    {
+        ProfScope ps(ctx, "envelope");
+        cudaError_t e = thb::launch_envelope(d_desc, 1, static_cast<long long>(len), level, revision, tile_index, 1, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "envelope: %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(out, d_out, need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_out, ctx->stream));
+    if (staging) CK(cudaFreeAsync(staging, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+// ---- NCCL ---------------------------------------------------------------------------------------
+int thb_comm_unique_id(uint8_t id[128]) {
+    std::string err;
+    if (!id) return fail(nullptr, THB_ERR_INVALID, "id is NULL");
+    if (!g_nccl.load(&err)) return fail(nullptr, THB_ERR_NCCL, "%s", err.c_str());
+    NcclId nid;
+    const int r = g_nccl.GetUniqueId(&nid);
+    if (r != 0) return fail(nullptr, THB_ERR_NCCL, "ncclGetUniqueId: %d", r);
+    memcpy(id, nid.internal, 128);
+    return THB_OK;
+}
+
+int thb_comm_init(thb_ctx *ctx, int n_ranks, int rank, const uint8_t id[128]) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::string err;
+    if (!g_nccl.load(&err)) return fail(ctx, THB_ERR_NCCL, "%s", err.c_str());
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) {
+        g_nccl.CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    NcclId nid;
+    memcpy(nid.internal, id, 128);
+    const int r = g_nccl.CommInitRank(&ctx->nccl_comm, n_ranks, nid, rank);
+    if (r != 0) {
+        ctx->nccl_comm = nullptr;
+        return fail(ctx, THB_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return THB_OK;
+}
+
+int thb_comm_destroy(thb_ctx *ctx) {
+    if (!ctx) return THB_OK;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->n_ranks = 1;
+    ctx->rank = 0;
+    return THB_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+int thb_profile_enable(thb_ctx *ctx, int on) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profiling = on != 0;
+    return THB_OK;
+}
+int thb_profile_reset(thb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    ctx->prof.clear();
+    ctx->launch_count = 0;
+    return THB_OK;
+}
+int thb_profile_get(thb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *launches) {
+    if (!ctx || !kernel) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    auto it = ctx->prof.find(kernel);
+    if (total_ms) *total_ms = it == ctx->prof.end() ? 0.0 : it->second.total_ms;
+    if (launches) *launches = it == ctx->prof.end() ? 0 : it->second.launches;
+    return THB_OK;
+}
+uint64_t thb_launch_count(const thb_ctx *ctx) { return ctx ? ctx->launch_count : 0; }
+
+int thb_synth_pcm(thb_ctx *ctx, float *dev_out, uint64_t len, uint32_t sr, uint32_t track, uint32_t channel,
+                  uint32_t flags) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!dev_out || sr == 0 || len >= (1ull << 32)) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!is_device_ptr(dev_out)) return fail(ctx, THB_ERR_INVALID, "dev_out must be device memory");
+    cudaError_t e = thb::launch_synth_pcm(dev_out, len, sr, track, channel, flags, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "synth: %s", cudaGetErrorString(e));
+    return THB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// thb_host.cpp -- see thb_host.hpp.  Host arithmetic only; every formula cites the reference
+// line it reproduces so that the integer results (hop, win, n_fft, T, n_mel, i_freq_range) are
+// exact and the f32 tables (window, mel weights) are the reference's values.
+#include "thb_host.hpp"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace thb {
+
+bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+
+static uint64_t next_pow2(uint64_t x) {  // usize::next_power_of_two (0 -> 1)
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+Framing framing_params(const thb_setting &s, uint32_t sr) {
+    Framing f;
+    // hop = round(win_ms * sr / 1000 / t_overlap) with f64 round-half-away (spectrogram.rs:62-64,91-93)
+    const double win_float = s.win_ms * static_cast<double>(sr) / 1000.0;
+    const double h = std::round(win_float / static_cast<double>(s.t_overlap));
+    f.hop = (h > 0.0 && h == h) ? (h >= 1.8446744073709552e19 ? UINT64_MAX : static_cast<uint64_t>(h)) : 0;
+    f.win = f.hop * static_cast<uint64_t>(s.t_overlap);                   // :57-59
+    f.n_fft = next_pow2(f.win) * static_cast<uint64_t>(s.f_overlap);      // :95-97
+    return f;
+}
+
+uint64_t n_frames(uint64_t len, uint64_t win, uint64_t hop) {
+    // perform_stft frames the signal reflect-padded by win/2 on both sides with stride hop
+    // (stft.rs:50-95); the three pieces together are exactly the windows of that padded signal.
+    if (hop == 0) return 0;
+    const uint64_t padded = len + 2 * (win / 2);
+    return padded >= win ? (padded - win) / hop + 1 : 0;
+}
+
+std::vector<float> normalized_hann(uint64_t win, uint64_t n_fft) {
+    // cosine_window(0.5, 0.5, 0, 0, win, symmetric = false) / n_fft, all f32 (windows.rs:25,31-38,68-83)
+    std::vector<float> w(win);
+    const float pi = static_cast<float>(M_PI);
+    const float denom = static_cast<float>(win);  // size2 - 1 with size2 = win + 1
+    const float nf = static_cast<float>(n_fft);
+    for (uint64_t i = 0; i < win; i++) {
+        const float x = pi * static_cast<float>(i) / denom;
+        const float b_ = 0.5f * cosf(2.0f * x);
+        const float c_ = 0.0f * cosf(4.0f * x);
+        const float d_ = 0.0f * cosf(6.0f * x);
+        const float v = (0.5f - b_) + (c_ - d_);
+        w[i] = v / nf;
+    }
+    return w;
+}
+
+// Slaney-style mel <-> Hz in f32 (lib.rs:11-43): constants are f64 literals cast to f32.
+static const float kMinLogMel = 15.0f;
+static const float kMinLogHz = static_cast<float>(1000.);
+static const float kLogStep = static_cast<float>(0.06875177742094912);
+static const float kLinearScale = static_cast<float>(200. / 3.);
+
+float mel_to_hz(float mel) {
+    if (mel < kMinLogMel) return kLinearScale * mel;
+    return kMinLogHz * expf(kLogStep * (mel - kMinLogMel));
+}
+float mel_from_hz(float hz) {
+    if (hz < kMinLogHz) return hz / kLinearScale;
+    return kMinLogMel + logf(hz / kMinLogHz) / kLogStep;
+}
+
+// calc_mel_fb(sr, n_fft, n_mel, 0, None, true) built band by band in sparse form.
+static MelBank build_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel, bool *all_nonempty) {
+    MelBank b;
+    b.n_freq = static_cast<uint32_t>(n_fft / 2 + 1);
+    b.n_mel = n_mel;
+    b.k0.assign(n_mel, 0);
+    b.ptr.assign(n_mel + 1, 0);
+    const float f_nyquist = static_cast<float>(static_cast<double>(sr) / 2.);
+    const uint32_t F = b.n_freq;
+    // Array::linspace(0, f_nyquist, F)[i] = 0 + step * i  (lib.rs:64)
+    const float step = F > 1 ? (f_nyquist - 0.0f) / static_cast<float>(F - 1) : 0.0f;
+    // linspace(from_hz(0), from_hz(fmax), n_mel + 2) mapped through to_hz (lib.rs:65-66)
+    std::vector<float> edge(n_mel + 2);
+    {
+        const float m0 = mel_from_hz(0.0f), m1 = mel_from_hz(f_nyquist);
+        const float mstep = (m1 - m0) / static_cast<float>(n_mel + 1);
+        for (uint32_t i = 0; i < n_mel + 2; i++) edge[i] = mel_to_hz(m0 + mstep * static_cast<float>(i));
+    }
+    bool ok = true;
+    std::vector<float> wrow;
+    for (uint32_t m = 0; m < n_mel; m++) {
+        const float e0 = edge[m], e1 = edge[m + 1], e2 = edge[m + 2];
+        // first bin with f > e0 (the reference `continue`s over f <= e0, lib.rs:71-72)
+        uint64_t k = 0;
+        if (step > 0.0f) {
+            const double est = static_cast<double>(e0) / static_cast<double>(step);
+            k = est > 2.0 ? static_cast<uint64_t>(est) - 2 : 0;
+            if (k >= F) k = F - 1;
+            while (k > 0 && step * static_cast<float>(k) > e0) k--;  // guard against estimate overshoot
+        }
+        while (k < F && step * static_cast<float>(k) <= e0) k++;
+        wrow.clear();
+        const uint64_t kfirst = k;
+        for (; k < F; k++) {
+            const float f = step * static_cast<float>(k);
+            float v;
+            if (e0 < f && f < e1) v = (f - e0) / (e1 - e0);              // rising slope  (:73-74)
+            else if (f == e1) v = 1.0f;                                   // (:75-76)
+            else if (e1 < f && f < e2) v = (e2 - f) / (e2 - e1);          // falling slope (:77-78)
+            else break;                                                   // (:79-81)
+            wrow.push_back(v);
+        }
+        // w /= w.sum().max(epsilon) (lib.rs:84-86).  ndarray sums a contiguous row with eight
+        // interleaved partial sums over the full row of F entries; zeros do not change them.
+        float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint64_t body = (static_cast<uint64_t>(F) / 8) * 8;
+        float acc = 0.0f;
+        for (size_t i = 0; i < wrow.size(); i++) {
+            const uint64_t kk = kfirst + i;
+            if (kk < body) p[kk & 7] += wrow[i];
+        }
+        acc = acc + (p[0] + p[4]);
+        acc = acc + (p[1] + p[5]);
+        acc = acc + (p[2] + p[6]);
+        acc = acc + (p[3] + p[7]);
+        for (size_t i = 0; i < wrow.size(); i++) {
+            const uint64_t kk = kfirst + i;
+            if (kk >= body) acc = acc + wrow[i];
+        }
+        float s = acc;
+        if (!(s > FLT_EPSILON)) s = FLT_EPSILON;
+        bool any = false;
+        // trim zero weights at both ends (a slope value can be exactly 0 only by underflow)
+        size_t lo = 0, hi = wrow.size();
+        for (size_t i = 0; i < wrow.size(); i++) wrow[i] = wrow[i] / s;
+        while (lo < hi && wrow[lo] == 0.0f) lo++;
+        while (hi > lo && wrow[hi - 1] == 0.0f) hi--;
+        b.k0[m] = static_cast<uint32_t>(kfirst + lo);
+        for (size_t i = lo; i < hi; i++) {
+            b.w.push_back(wrow[i]);
+            if (wrow[i] > 0.0f) any = true;
+        }
+        b.ptr[m + 1] = static_cast<uint32_t>(b.w.size());
+        if (!any) ok = false;
+    }
+    if (all_nonempty) *all_nonempty = ok;
+    return b;
+}
+
+MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
+    if (n_mel != 0) return build_bank(sr, n_fft, n_mel, nullptr);
+    // calc_mel_fb_default (lib.rs:91-103)
+    const float v = fmaf(mel_from_hz(static_cast<float>(sr) / 2.0f) /
+                             mel_from_hz(static_cast<float>(sr) / static_cast<float>(n_fft)),
+                         2.0f, -1.0f);
+    uint64_t n = (v > 0.0f && v == v) ? static_cast<uint64_t>(v) : 0;  // `as usize`
+    const uint64_t n_freq = n_fft / 2 + 1;
+    if (n > n_freq) n = n_freq;
+    for (;;) {
+        bool ok = false;
+        MelBank b = build_bank(sr, n_fft, static_cast<uint32_t>(n), &ok);
+        if (ok || n == 0) return b;  // n == 0: `all` over an empty iterator is true in the reference
+        n -= 1;
+    }
+}
+
+std::vector<float> MelBank::dense() const {
+    std::vector<float> d(static_cast<size_t>(n_freq) * n_mel, 0.0f);
+    for (uint32_t m = 0; m < n_mel; m++)
+        for (uint32_t i = ptr[m]; i < ptr[m + 1]; i++)
+            d[static_cast<size_t>(k0[m] + (i - ptr[m])) * n_mel + m] = w[i];
+    return d;
+}
+
+void hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uint64_t n_bins,
+                     uint64_t *i0, uint64_t *i1) {
+    if (hz0 >= hz1) {  // lib.rs:150-152
+        *i0 = 0;
+        *i1 = 0;
+        return;
+    }
+    const float half_sr = static_cast<float>(sr) / 2.0f;
+    float r0, r1;
+    if (freq_scale == THB_FREQ_LINEAR) {  // calc_ratio_to_max_freq (lib.rs:135-141)
+        r0 = hz0 / half_sr;
+        r1 = hz1 / half_sr;
+    } else {
+        const float d = mel_from_hz(half_sr);
+        r0 = mel_from_hz(hz0) / d;
+        r1 = mel_from_hz(hz1) / d;
+    }
+    float a = floorf(r0 * static_cast<float>(n_bins));
+    if (!(a > 0.0f)) a = 0.0f;
+    const float c = ceilf(r1 * static_cast<float>(n_bins));
+    *i0 = static_cast<uint64_t>(a);
+    *i1 = c > 0.0f ? static_cast<uint64_t>(c) : 0;
+}
+
+std::vector<float> twiddle_table(uint64_t n_fft) {
+    std::vector<float> t(2 * n_fft);
+    for (uint64_t i = 0; i < n_fft; i++) {
+        const double ang = -2.0 * M_PI * static_cast<double>(i) / static_cast<double>(n_fft);
+        t[2 * i] = static_cast<float>(std::cos(ang));
+        t[2 * i + 1] = static_cast<float>(std::sin(ang));
+    }
+    return t;
+}
+
+}  // namespace thb

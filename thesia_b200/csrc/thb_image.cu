@@ -1,0 +1,175 @@
+// thb_image.cu -- K3 tail (global {max,-min} reduce + clamp rules) and K4 (dB -> u16, transposed).
+//
+// K4 = convert_spectrogram_to_img (visualize/drawing.rs:4-33): out[i][j] = q(spec[j][i0 + i]),
+// q(v) = clamp(round((v - min_dB) / (max_dB - min_dB) * (65535 - min_value) + min_value), 0, 65535)
+// with min_value = max(1, round(65535 / colormap_length)); rows >= B are 0; (-inf, -inf) range
+// gives an all-zero image.  Multiply and add are NOT fused (Rust never contracts), so a pixel is
+// bit-identical to the reference's whenever the dB input is.
+// HBM-bound: reads 4 B and writes 2 B per pixel; a 32(bins) x 64(frames) shared-memory tile turns
+// the reference's strided gather into coalesced 128 B reads and 128 B writes.
+#include "thb_device.cuh"
+#include "thb_kernels.cuh"
+
+namespace thb {
+namespace {
+
+__global__ void minmax_init_kernel(float *slots, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * n) slots[i] = -CUDART_INF_F;
+}
+
+__global__ void minmax_init_tracks_kernel(const TrackDesc *__restrict__ tracks, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        tracks[i].minmax[0] = -CUDART_INF_F;
+        tracks[i].minmax[1] = -CUDART_INF_F;
+    }
+}
+
+// grid-stride {max, -min} of a flat array: warp shuffle -> one atomic pair per warp
+__global__ void __launch_bounds__(256) minmax_array_kernel(const float *__restrict__ x, unsigned long long n,
+                                                           float *slot) {
+    float a = -CUDART_INF_F, b = -CUDART_INF_F;
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = __ldg(x + i);
+        a = fmaxf(a, v);
+        b = fmaxf(b, -v);
+    }
+    a = warp_max(a);
+    b = warp_max(b);
+    if ((threadIdx.x & 31) == 0) {
+        atomic_max_float(&slot[0], a);
+        atomic_max_float(&slot[1], b);
+    }
+}
+
+// one warp: max over all slots of {max, -min}  (the rayon reduce of mod.rs:169-178)
+__global__ void minmax_reduce_kernel(const float *__restrict__ slots, int n_slots, float *send) {
+    float a = -CUDART_INF_F, b = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < n_slots; i += 32) {
+        a = fmaxf(a, slots[2 * i]);
+        b = fmaxf(b, slots[2 * i + 1]);
+    }
+    a = warp_max(a);
+    b = warp_max(b);
+    if (threadIdx.x == 0) {
+        send[0] = a;
+        send[1] = b;
+    }
+}
+
+// max <- min(max, 0); min <- max(min, max - dB_range)   (mod.rs:179-180)
+__global__ void minmax_finalize_kernel(const float *__restrict__ send, float dB_range, float *range) {
+    const float mx = fminf(send[0], 0.0f);
+    const float mn = fmaxf(-send[1], __fsub_rn(mx, dB_range));
+    range[0] = mn;
+    range[1] = mx;
+}
+
+constexpr int kTileT = 64;  // frames per tile (image columns)
+constexpr int kTileB = 32;  // bins per tile   (image rows)
+
+__global__ void __launch_bounds__(256) spec_to_img_kernel(const ImgDesc *__restrict__ descs,
+                                                          const float *__restrict__ range,
+                                                          float min_value_f, float u16_span) {
+    __shared__ uint16_t tile[kTileB][kTileT + 2];
+    const ImgDesc d = descs[blockIdx.z];
+    const long long t0 = static_cast<long long>(blockIdx.x) * kTileT;
+    const int r0 = blockIdx.y * kTileB;  // image row (relative to i0)
+    if (t0 >= d.T || r0 >= d.H) return;
+    const float dB_min = range[0], dB_max = range[1];
+    const bool all_zero = (dB_min == dB_max) && (dB_max == -CUDART_INF_F);
+    const float span = __fsub_rn(dB_max, dB_min);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+    // read: each warp takes frames warp, warp+8, ...; lanes run along the bins axis (contiguous)
+#pragma unroll
+    for (int i = 0; i < kTileT / 8; i++) {
+        const int tt = warp + 8 * i;
+        const long long t = t0 + tt;
+        const int bin = d.i0 + r0 + lane;
+        uint16_t px = 0;
+        if (t < d.T && (r0 + lane) < d.H && bin < d.B && !all_zero) {
+            const float v = __ldg(&d.spec[t * d.B + bin]);
+            const float zero_to_one = __fdiv_rn(__fsub_rn(v, dB_min), span);
+            const float scaled = __fadd_rn(__fmul_rn(zero_to_one, u16_span), min_value_f);
+            const float r = roundf(scaled);  // f32::round: half away from zero
+            // clamp(0, 65535) then `as u16`; NaN -> 0
+            px = (r != r) ? 0 : static_cast<uint16_t>(fminf(fmaxf(r, 0.0f), 65535.0f));
+        }
+        tile[lane][tt] = px;
+    }
+    __syncthreads();
+    // write: each warp takes image rows warp, warp+8, ...; lanes run along time, 2 pixels each
+#pragma unroll
+    for (int i = 0; i < kTileB / 8; i++) {
+        const int rr = warp + 8 * i;
+        if (r0 + rr >= d.H) continue;
+        uint16_t *orow = d.img + static_cast<long long>(r0 + rr) * d.pitch;
+        const long long t = t0 + 2 * lane;
+        if (t + 1 < d.T && ((reinterpret_cast<uintptr_t>(orow + t) & 3) == 0)) {
+            const uint32_t two = static_cast<uint32_t>(tile[rr][2 * lane]) |
+                                 (static_cast<uint32_t>(tile[rr][2 * lane + 1]) << 16);
+            *reinterpret_cast<uint32_t *>(orow + t) = two;
+        } else {
+            if (t < d.T) orow[t] = tile[rr][2 * lane];
+            if (t + 1 < d.T) orow[t + 1] = tile[rr][2 * lane + 1];
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_minmax_init(float *d_slots, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    minmax_init_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(d_slots, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_init_tracks(const TrackDesc *d_tracks, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    minmax_init_tracks_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_tracks, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_array(const float *d_x, unsigned long long n, float *d_slot, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned long long blocks = (n + 255) / 256;
+    const unsigned long long cap = static_cast<unsigned long long>(sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    minmax_array_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d_x, n, d_slot);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_send, cudaStream_t st) {
+    minmax_reduce_kernel<<<1, 32, 0, st>>>(d_slots, n_slots, d_send);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d_range, cudaStream_t st) {
+    minmax_finalize_kernel<<<1, 1, 0, st>>>(d_send, dB_range, d_range);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, int max_H,
+                               const float *d_range, uint32_t colormap_length, cudaStream_t st) {
+    if (n <= 0 || max_T <= 0 || max_H <= 0) return cudaSuccess;
+    // min_value = max(1, round(65535 / colormap_length) as u16)   (drawing.rs:20-21)
+    double r = colormap_length ? std::round(65535.0 / static_cast<double>(colormap_length)) : 65535.0;
+    if (r > 65535.0) r = 65535.0;
+    uint32_t min_value = static_cast<uint32_t>(r);
+    if (min_value < 1) min_value = 1;
+    const float u16_span = static_cast<float>(65535u - min_value);
+    const unsigned gx = static_cast<unsigned>((max_T + kTileT - 1) / kTileT);
+    const unsigned gy = static_cast<unsigned>((max_H + kTileB - 1) / kTileB);
+    for (int t0 = 0; t0 < n; t0 += 65535) {
+        const int nt = n - t0 < 65535 ? n - t0 : 65535;
+        dim3 grid(gx, gy, static_cast<unsigned>(nt));
+        spec_to_img_kernel<<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace thb

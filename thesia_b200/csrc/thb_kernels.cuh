@@ -1,0 +1,81 @@
+// thb_kernels.cuh -- launch interface between the C-ABI layer (thb_api.cu) and the sm_100a
+// kernels (thb_stft.cu, thb_image.cu, thb_envelope.cu).  Device pointers only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace thb {
+
+// One channel (or one frame-range shard of a channel) as the STFT kernels see it.
+struct TrackDesc {
+    const float *pcm;        // device; pcm[0] is sample `pcm_offset` of the file
+    long long pcm_offset;
+    long long slice_len;     // samples available at pcm
+    long long full_len;      // samples in the whole file (reflect happens at 0 and full_len-1)
+    long long frame_begin;   // first frame of this shard
+    long long n_frames;      // frames to compute
+    float *out;              // (n_frames, n_bins) row-major dB
+    float *minmax;           // 2 floats: {max, -min} of this channel (atomic-max accumulated)
+};
+
+// Everything that depends only on (sr, win, n_fft, n_mel): uploaded once per SrWinNfft key.
+struct PlanDev {
+    int hop, win, n_fft, nc;          // nc = n_fft / 2
+    int pad_left;                     // (n_fft - win) / 2  (stft.rs:36)
+    int n_freq, n_bins, n_mel;        // n_mel == 0 -> linear
+    int n_pass;
+    int radix_log2[8];                // DIF pass radices (log2), product = nc
+    const float *window;              // [win]
+    const float2 *twiddle;            // [n_fft] exp(-2 pi i t / n_fft)
+    const uint32_t *mel_k0;           // [n_mel]
+    const uint32_t *mel_ptr;          // [n_mel + 1]
+    const float *mel_w;               // [nnz]
+    int max_band_len;
+};
+
+struct ImgDesc {
+    const float *spec;   // (T, B) dB
+    uint16_t *img;       // (H, pitch) u16
+    long long T;
+    int B;
+    int i0, H;           // rows i0 .. i0+H of the bins axis
+    long long pitch;     // elements between image rows
+};
+
+struct EnvDesc {
+    const float *pcm;    // device, whole channel
+    long long len;
+    uint8_t *out;        // device, tiles of this level concatenated in wire format
+};
+
+// ---- launchers (all asynchronous on `st`) ----
+// generic shared-memory path, any power-of-two n_fft in [4, 32768]
+cudaError_t launch_stft_generic(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
+                                long long max_frames, cudaStream_t st);
+// warp-per-frame register path for n_fft == 2048 (nc == 1024)
+bool stft_fast_supported(const PlanDev &plan);
+cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
+                             long long max_frames, int sm_count, cudaStream_t st);
+
+cudaError_t launch_minmax_init(float *d_slots, int n, cudaStream_t st);
+// reset the {max, -min} slot of every channel in a descriptor array
+cudaError_t launch_minmax_init_tracks(const TrackDesc *d_tracks, int n, cudaStream_t st);
+// {max, -min} of an arbitrary f32 array accumulated into slot[0..1] (find_min_max, simd.rs:14-36)
+cudaError_t launch_minmax_array(const float *d_x, unsigned long long n, float *d_slot, int sm_count, cudaStream_t st);
+// d_send[0..1] = max over live slots of {max, -min}
+cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_send, cudaStream_t st);
+// d_range = {min_dB, max_dB} after the clamp rules of mod.rs:179-180
+cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d_range, cudaStream_t st);
+
+cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, int max_H,
+                               const float *d_range, uint32_t colormap_length, cudaStream_t st);
+
+// tiles [tile_begin, tile_begin + tile_count) of every channel; tile_count == 0 -> to the end
+cudaError_t launch_envelope(const EnvDesc *d_descs, int n, long long max_len, uint32_t level,
+                            uint64_t revision, uint32_t tile_begin, uint32_t tile_count,
+                            cudaStream_t st);
+
+cudaError_t launch_synth_pcm(float *d_out, unsigned long long len, uint32_t sr, uint32_t track,
+                             uint32_t channel, uint32_t flags, cudaStream_t st);
+
+}  // namespace thb
