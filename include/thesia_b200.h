@@ -204,7 +204,7 @@ uint64_t thb_launch_count(const thb_ctx *ctx);
  * `dev_out` (len floats); thesia_b200/synth.py restates it in numpy bit for bit. */
 int thb_synth_pcm(thb_ctx *ctx, float *dev_out, uint64_t len, uint32_t sr, uint32_t track, uint32_t channel,
                   uint32_t flags);
-#define THB_SYNTH_LOUD 1u     /* scale x1.5 so that max_dB hits the min(max, 0) clamp */
+#define THB_SYNTH_LOUD 1u     /* scale x32 (f32 audio above 0 dBFS) so that max_dB hits the min(max, 0) clamp */
 #define THB_SYNTH_ZERO_GAP 2u /* one second of exact zeros (produces -inf frames) */
 
 #ifdef __cplusplus

@@ -810,7 +810,7 @@ static inline int orc_synth_base(uint64_t n, uint64_t len, uint32_t sr, uint32_t
     int nz = (((int)(h >> 16) - 32768) * 1638) >> 15;
     int v = a0 + a1 + nz;
     if ((flags & 2u) && n >= sr && n < 2ull * sr) v = 0;
-    if (flags & 1u) v *= 16;
+    if (flags & 1u) v *= 32;
     return v;
 }
 ORC_API void orc_synth_pcm(float *out, uint64_t len, uint32_t sr, uint32_t track, uint32_t channel,

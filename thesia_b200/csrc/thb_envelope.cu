@@ -181,7 +181,7 @@ __device__ __forceinline__ int synth_base(unsigned long long n, unsigned long lo
     const int nz = ((static_cast<int>(h >> 16) - 32768) * 1638) >> 15;
     int v = a0 + a1 + nz;
     if ((flags & 2u) && n >= sr && n < 2ull * sr) v = 0;
-    if (flags & 1u) v <<= 4;
+    if (flags & 1u) v *= 32;
     return v;
 }
 __global__ void synth_pcm_kernel(float *out, unsigned long long len, unsigned sr, unsigned track,

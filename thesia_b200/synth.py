@@ -3,7 +3,7 @@ integer arithmetic only, so host and device agree bit for bit (SURVEY.md section
 
 x = 0.25 * tone(55 Hz + 13.75 Hz * (track % 61)) + 0.1 * chirp(50 Hz -> 0.45 sr) + 0.05 * noise,
 quantised like 16-bit PCM (v / 32768); channel 1 = channel 0 delayed 7 samples * 0.8;
-LOUD (flag 1) multiplies by 16 (> 0 dBFS, exercises the max_dB clamp); ZERO_GAP (flag 2) zeroes
+LOUD (flag 1) multiplies by 32 (> 0 dBFS, exercises the max_dB clamp); ZERO_GAP (flag 2) zeroes
 samples [sr, 2 sr).
 """
 import numpy as np
@@ -50,7 +50,7 @@ def _base(n, length, sr, track, flags):
     if flags & ZERO_GAP:
         v = np.where((n >= np.uint64(sr)) & (n < np.uint64(2 * sr)), 0, v)
     if flags & LOUD:
-        v = v * 16
+        v = v * 32
     return v
 
 
