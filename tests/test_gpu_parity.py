@@ -6,9 +6,10 @@ Stated tolerances (DESIGN.md "Parity"):
     (an f32 FFT -- the reference's included -- cannot hold 1e-4 RELATIVE error on bins more than
     50 dB under the frame's peak; the f32 oracle itself measures 5.9e-5 against this bound).
   * dB     |dB_gpu - dB_truth| <= 1e-3 dB wherever P_truth is above that floor; exactly -inf for
-    all-zero frames; below the floor the power bound above applies (absolute), and down to
-    -90 dB under the frame peak the GPU must be no worse than 3x the reference-like f32 oracle's
-    own worst error (+1e-3 dB).
+    all-zero frames; below the floor the power bound above applies (absolute), and over ALL bins the
+    amplitude error normalised by the frame's peak amplitude must be no worse than 3x the
+    reference-like f32 oracle's own worst (+1.5e-6, the f32 quantisation of a dB value): an f32 FFT's error is absolute, set by the
+    frame's energy, so a per-bin dB comparison of the deepest bin only measures luck.
   * envelope mean <= 1e-6 absolute; u16 image: bit-exact given the GPU's own dB, <= 1 LSB end to end.
 "truth" = the oracle's f64 leg; "f32 oracle" = its reference-like f32 leg.
 """
@@ -68,11 +69,18 @@ def check_spec(orc, gpu_db, wav, sr, setting: thb.SpecSetting, tag=""):
     worst_db = float(ddb[above].max()) if above.any() else 0.0
     assert worst_pow <= POW_RTOL, f"{tag}: power rel err {worst_pow:.3g}"
     assert worst_db <= DB_TOL, f"{tag}: dB err above floor {worst_db:.3g}"
-    # below the floor: no worse than the reference-like f32 arithmetic (bins down to -90 dB rel.)
-    deep = (P > 1e-9 * P.max(axis=1, keepdims=True)) & ~neg
-    if deep.any():
-        assert ddb[deep].max() <= 3.0 * ddb32[deep].max() + 1e-3, \
-            f"{tag}: deep-bin dB err {ddb[deep].max():.3g} vs f32 oracle {ddb32[deep].max():.3g}"
+    # below the floor an f32 FFT's error is ABSOLUTE (set by the frame's energy, not by the bin): compare the
+    # amplitude error normalised by the frame's peak amplitude with the reference-like f32 oracle's own worst
+    peak = np.sqrt(P.max(axis=1, keepdims=True))
+    live = (peak[:, 0] > 0)
+    if live.any():
+        with np.errstate(over="ignore", invalid="ignore"):
+            amp_g = np.where(np.isneginf(g), 0.0, 10.0 ** (g / 20.0))
+            amp_o = np.where(np.isneginf(f32_db), 0.0, 10.0 ** (f32_db.astype(np.float64) / 20.0))
+        eg = (np.abs(amp_g - truth_amp)[live] / peak[live]).max()
+        eo = (np.abs(amp_o - truth_amp)[live] / peak[live]).max()
+        # + 1.5e-6: an f32 dB value near -150 dB is itself quantised to 8.8e-7 relative in amplitude
+        assert eg <= 3.0 * eo + 1.5e-6, f"{tag}: amplitude err / frame peak {eg:.3g} vs f32 oracle {eo:.3g}"
     return worst_pow, worst_db
 
 
@@ -180,6 +188,16 @@ def test_edges_and_short_inputs(ctx, orc, n):
         db = ctx.calc_spec(x, 48000, setting)
         assert db.shape[0] == orc.n_frames(n, 1920, 480)
         check_spec(orc, db, x, 48000, setting, f"N={n}")
+
+
+@pytest.mark.parametrize("gain", [1e-16, 3e-12, 1e9, 4e15])
+def test_extreme_levels(ctx, orc, gain):
+    """f32 audio far from full scale: |X|^2 would under/overflow f32; the reference's hypot does not."""
+    x = (synth_pcm(40000, 48000, 5, 0, ZERO_GAP).astype(np.float64) * gain).astype(np.float32)
+    for setting in (thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear),
+                    thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)):
+        db = ctx.calc_spec(x, 48000, setting)
+        check_spec(orc, db, x, 48000, setting, f"gain={gain:g}")
 
 
 def test_device_resident_input_matches_host_input(ctx):

@@ -302,10 +302,12 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     d.twiddle = reinterpret_cast<const float2 *>(twp);
     d.n_mel = 0;
     d.max_band_len = 0;
+    d.mel_nnz = 0;
     if (s.freq_scale == THB_FREQ_MEL) {
         const thb::MelBank mb = thb::mel_bank(sr, f.n_fft, s.n_mel);
         if (mb.n_mel == 0) return fail(ctx, THB_ERR_INVALID, "mel filterbank is empty for sr %u n_fft %d", sr, d.n_fft);
         d.n_mel = static_cast<int>(mb.n_mel);
+        d.mel_nnz = static_cast<int>(mb.w.size());
         if ((rc = upload(ctx, pl.get(), mb.k0, &d.mel_k0))) return rc;
         if ((rc = upload(ctx, pl.get(), mb.ptr, &d.mel_ptr))) return rc;
         if ((rc = upload(ctx, pl.get(), mb.w, &d.mel_w))) return rc;
@@ -313,6 +315,54 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
             d.max_band_len = std::max<int>(d.max_band_len, static_cast<int>(mb.ptr[m + 1] - mb.ptr[m]));
     }
     d.n_bins = d.n_mel ? d.n_mel : d.n_freq;
+    d.ms_groups = d.ms_words = d.ms_max_reach = 0;
+    d.ms_blob = nullptr;
+    std::vector<uint32_t> ms_blob;
+    if (d.n_mel && d.n_fft == 2048) {
+        const thb::MelSchedule sc = thb::mel_schedule(thb::mel_bank(sr, f.n_fft, s.n_mel));
+        d.ms_groups = static_cast<int>(sc.n_groups);
+        d.ms_max_reach = static_cast<int>(sc.max_reach);
+        ms_blob.insert(ms_blob.end(), sc.T.begin(), sc.T.end());
+        const uint32_t w_base = sc.n_groups * 34;
+        for (uint32_t g = 0; g < sc.n_groups; g++) ms_blob.push_back(w_base + sc.woff[g]);
+        for (int32_t v : sc.start) ms_blob.push_back(static_cast<uint32_t>(v));
+        for (float v : sc.w) {
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            ms_blob.push_back(u);
+        }
+        while (ms_blob.size() & 3) ms_blob.push_back(0);
+        d.ms_words = static_cast<int>(ms_blob.size());
+        if ((rc = upload(ctx, pl.get(), ms_blob, &d.ms_blob))) return rc;
+    }
+    d.fast_wpad = nullptr;
+    d.fast_tw = nullptr;
+    std::vector<float> wpad, ftw;
+    if (d.n_fft == 2048) {
+        // tables of the warp-per-frame kernel (thb_stft_fast.cu)
+        wpad.assign(2048, 0.0f);
+        for (int a = 0; a < d.win; a++) wpad[a + d.pad_left] = 0.5f * win[a];
+        ftw.resize(2 * (31 * 32 + 16 * 32));
+        const double tau = 6.283185307179586476925286766559;
+        for (int k1 = 1; k1 < 32; k1++)
+            for (int lane = 0; lane < 32; lane++) {
+                const double a = -tau * static_cast<double>((lane * k1) % 1024) / 1024.0;
+                ftw[2 * ((k1 - 1) * 32 + lane)] = static_cast<float>(std::cos(a));
+                ftw[2 * ((k1 - 1) * 32 + lane) + 1] = static_cast<float>(std::sin(a));
+            }
+        for (int j = 0; j < 16; j++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int k_own = (lane ? lane : 32) + 32 * (31 - j);
+                float c = tw[2 * (k_own % 2048)], s = tw[2 * (k_own % 2048) + 1];
+                if (k_own == 1024) { c = -1.0f; s = 0.0f; }
+                ftw[2 * (31 * 32 + j * 32 + lane)] = c;
+                ftw[2 * (31 * 32 + j * 32 + lane) + 1] = s;
+            }
+        if ((rc = upload(ctx, pl.get(), wpad, &d.fast_wpad))) return rc;
+        const float *ftwp = nullptr;
+        if ((rc = upload(ctx, pl.get(), ftw, &ftwp))) return rc;
+        d.fast_tw = reinterpret_cast<const float2 *>(ftwp);
+    }
     CK(cudaStreamSynchronize(ctx->stream));  // the host vectors above die here
     *out = pl.get();
     ctx->plans[key] = std::move(pl);

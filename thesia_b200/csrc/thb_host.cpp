@@ -4,6 +4,7 @@
 #include "thb_host.hpp"
 
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -162,6 +163,44 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
         if (ok || n == 0) return b;  // n == 0: `all` over an empty iterator is true in the reference
         n -= 1;
     }
+}
+
+MelSchedule mel_schedule(const MelBank &b) {
+    MelSchedule sc;
+    sc.n_groups = (b.n_mel + 31) / 32;
+    sc.T.resize(sc.n_groups);
+    sc.woff.resize(sc.n_groups);
+    sc.start.assign(static_cast<size_t>(sc.n_groups) * 32, 0);
+    for (uint32_t g = 0; g < sc.n_groups; g++) {
+        // every bank may be hit by at most two lanes: a 2-way conflict costs one extra wavefront per
+        // step, pulling a band further back costs a whole extra step for the group
+        int used[32] = {};
+        uint32_t lead[32] = {}, len[32] = {};
+        uint32_t T = 4;
+        for (uint32_t l = 0; l < 32; l++) {
+            const uint32_t m = g * 32 + l;
+            const int64_t k0 = m < b.n_mel ? b.k0[m] : l;
+            len[l] = m < b.n_mel ? b.ptr[m + 1] - b.ptr[m] : 0;
+            uint32_t o = 0;
+            while (used[static_cast<uint32_t>(((k0 - o) % 32 + 32) % 32)] >= 2) o++;
+            used[static_cast<uint32_t>(((k0 - o) % 32 + 32) % 32)]++;
+            lead[l] = o;
+            sc.start[g * 32 + l] = static_cast<int32_t>(k0 - o);
+            T = std::max(T, o + len[l]);
+        }
+        T = (T + 3) & ~3u;
+        sc.T[g] = T;
+        sc.woff[g] = static_cast<uint32_t>(sc.w.size());
+        sc.w.resize(sc.w.size() + static_cast<size_t>(T) * 32, 0.0f);
+        for (uint32_t l = 0; l < 32; l++) {
+            const uint32_t m = g * 32 + l;
+            for (uint32_t i = 0; i < len[l]; i++)
+                sc.w[sc.woff[g] + static_cast<size_t>(lead[l] + i) * 32 + l] = b.w[b.ptr[m] + i];
+            const int64_t reach = static_cast<int64_t>(sc.start[g * 32 + l]) + T - 1;
+            if (reach > static_cast<int64_t>(sc.max_reach)) sc.max_reach = static_cast<uint32_t>(reach);
+        }
+    }
+    return sc;
 }
 
 std::vector<float> MelBank::dense() const {

@@ -35,6 +35,20 @@ struct MelBank {
     std::vector<float> w;       // weights of band m: w[ptr[m] .. ptr[m+1]) for bins k0[m]...
     std::vector<float> dense() const;  // (n_freq, n_mel) row-major
 };
+// Lane schedule of the sparse mel product for a warp: bands are taken 32 at a time (lane = band
+// within the group); every lane walks `T[g]` consecutive bins starting at `start`, with its weights
+// interleaved as w[woff[g] + 32 t + lane] (zero where the band has no weight).  `start` is pulled
+// back by up to 31 bins so that the 32 lanes of a group always hit 32 different shared-memory
+// banks (start mod 32 distinct); it can therefore be as low as -31.
+struct MelSchedule {
+    uint32_t n_groups = 0;
+    std::vector<uint32_t> T;      // [n_groups], multiple of 4
+    std::vector<uint32_t> woff;   // [n_groups]
+    std::vector<int32_t> start;   // [n_groups * 32]
+    std::vector<float> w;         // interleaved weights
+    uint32_t max_reach = 0;       // largest bin index any lane reads
+};
+MelSchedule mel_schedule(const MelBank &b);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

@@ -31,6 +31,16 @@ struct PlanDev {
     const uint32_t *mel_ptr;          // [n_mel + 1]
     const float *mel_w;               // [nnz]
     int max_band_len;
+    int mel_nnz;
+    // n_fft == 2048 warp-per-frame path (thb_stft_fast.cu); null otherwise
+    const float *fast_wpad;           // [2048] 0.5 * window centred in the FFT buffer, zeros outside
+    const float2 *fast_tw;            // [31*32] W_1024^(lane*k1) then [16*32] split twiddles
+    // warp schedule of the sparse mel product (thb_host.hpp MelSchedule); mel only
+    int ms_groups;
+    int ms_words;                     // size of ms_blob in 32-bit words
+    int ms_max_reach;                 // largest bin index read
+    // blob = T[groups] | woff[groups] | start[groups*32] | weights (interleaved)
+    const uint32_t *ms_blob;
 };
 
 struct ImgDesc {
