@@ -7,9 +7,11 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -130,6 +132,11 @@ struct thb_ctx {
     size_t arena_cap = 0, arena_used = 0;
     cudaEvent_t arena_ev = nullptr;
     cudaEvent_t h2d_ev = nullptr;
+
+    // tiles the frame-pair STFT kernel hands back to the scalar kernel (thb_kernels.cuh RescueList)
+    uint2 *d_rescue_items = nullptr;
+    unsigned *d_rescue_count = nullptr;
+    size_t rescue_cap = 0;
 
     std::vector<void *> env_outputs;  // device buffers of the last waveform call
 
@@ -335,6 +342,26 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         d.ms_words = static_cast<int>(ms_blob.size());
         if ((rc = upload(ctx, pl.get(), ms_blob, &d.ms_blob))) return rc;
     }
+    d.mp_groups = d.mp_words = d.mp_max_reach = 0;
+    d.mp_blob = nullptr;
+    std::vector<uint32_t> mp_blob;
+    if (d.n_mel && d.n_fft == 2048) {
+        const thb::MelSchedule sc = thb::mel_schedule_pair(thb::mel_bank(sr, f.n_fft, s.n_mel));
+        d.mp_groups = static_cast<int>(sc.n_groups);
+        d.mp_max_reach = static_cast<int>(sc.max_reach);
+        mp_blob.insert(mp_blob.end(), sc.T.begin(), sc.T.end());
+        const uint32_t w_base = sc.n_groups * 34;
+        for (uint32_t g = 0; g < sc.n_groups; g++) mp_blob.push_back(w_base + sc.woff[g]);
+        for (int32_t v : sc.start) mp_blob.push_back(static_cast<uint32_t>(v));
+        for (float v : sc.w) {
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            mp_blob.push_back(u);
+        }
+        while (mp_blob.size() & 3) mp_blob.push_back(0);
+        d.mp_words = static_cast<int>(mp_blob.size());
+        if ((rc = upload(ctx, pl.get(), mp_blob, &d.mp_blob))) return rc;
+    }
     d.fast_wpad = nullptr;
     d.fast_tw = nullptr;
     std::vector<float> wpad, ftw;
@@ -508,6 +535,8 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     prof_collect(ctx);
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->d_rescue_items) cudaFree(ctx->d_rescue_items);
+    if (ctx->d_rescue_count) cudaFree(ctx->d_rescue_count);
     if (ctx->d_send) cudaFree(ctx->d_send);
     if (ctx->d_range) cudaFree(ctx->d_range);
     if (ctx->d_range_tmp) cudaFree(ctx->d_range_tmp);
@@ -661,7 +690,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         it.staging = nullptr;
         groups[pl].push_back(i);
     }
-    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * n + 4096);
+    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * 4 * n + 4096);
     if (rc) return rc;
 
     // ---- device buffers; host PCM goes through stream-ordered staging ----
@@ -698,17 +727,27 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     if (any_host) CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
 
     // ---- descriptors, one array per plan group ----
+    // THB_STFT_KERNEL = generic | fast | pair pins one implementation (A/B measurements); default: best
+    const char *force = getenv("THB_STFT_KERNEL");
+    const bool want_pair = !force || !strcmp(force, "pair"), want_fast = want_pair || !strcmp(force, "fast");
     struct Launch {
         const Plan *plan;
-        thb::TrackDesc *d_desc;
+        thb::TrackDesc *d_desc;  // every channel of the group, whole frame range
         int count;
         long long max_frames;
+        // frame-pair kernel: the interior, 8-byte aligned, even-length part of every channel; the rest (file
+        // edges with reflect padding, odd leftovers, unaligned channels) as separate descriptors for the scalar kernel
+        thb::TrackDesc *d_pair = nullptr, *d_edge = nullptr;
+        int n_pair = 0, n_edge = 0;
+        long long max_pair_frames = 0, max_edge_frames = 0;
+        size_t pair_tiles = 0;
     };
     std::vector<Launch> launches;
+    size_t max_pair_tiles = 0;
     for (auto &g : groups) {
         thb::TrackDesc *d_desc = nullptr;
         thb::TrackDesc *h = arena_push<thb::TrackDesc>(ctx, g.second.size(), &d_desc);
-        long long max_frames = 0;
+        Launch L{g.first, d_desc, static_cast<int>(g.second.size()), 0};
         for (size_t j = 0; j < g.second.size(); j++) {
             const size_t i = g.second[j];
             const thb_track &t = tracks[i];
@@ -722,12 +761,76 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             h[j].n_frames = static_cast<long long>(it.f_count);
             h[j].out = sp.d_spec;
             h[j].minmax = ctx->d_slots + 2 * sp.slot;
-            max_frames = std::max(max_frames, h[j].n_frames);
+            L.max_frames = std::max(L.max_frames, h[j].n_frames);
         }
-        launches.push_back({g.first, d_desc, static_cast<int>(g.second.size()), max_frames});
+        const thb::PlanDev &pd = g.first->dev;
+        if (want_pair && thb::stft_pair_supported(pd) && thb::stft_fast_supported(pd)) {
+            std::vector<thb::TrackDesc> pairs, edges;
+            const long long W = pd.win, H = pd.hop, half = W / 2, padl = pd.pad_left;
+            for (size_t j = 0; j < g.second.size(); j++) {
+                const thb::TrackDesc &f = h[j];
+                const long long fb = f.frame_begin, fe = fb + f.n_frames;  // [fb, fe)
+                auto ceil_div = [](long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; };
+                long long lo = std::max({fb, ceil_div(half, H), ceil_div(f.pcm_offset + half + padl, H)});
+                long long hi = fe - 1;
+                const long long c2 = f.full_len - W + half, c4 = f.pcm_offset + f.slice_len - 2048 + half + padl;
+                hi = (c2 < 0 || c4 < 0) ? -1 : std::min({hi, c2 / H, c4 / H});
+                long long cnt = hi >= lo ? hi - lo + 1 : 0;
+                const uintptr_t addr = reinterpret_cast<uintptr_t>(f.pcm);
+                const bool aligned = (addr & 3) == 0 && (H & 1) == 0 &&
+                                     ((static_cast<long long>(addr >> 2) + lo * H - half - padl - f.pcm_offset) & 1) == 0;
+                cnt = aligned ? (cnt & ~1ll) : 0;
+                if (cnt < 2) {
+                    if (f.n_frames) edges.push_back(f);
+                    continue;
+                }
+                thb::TrackDesc pr = f;
+                pr.frame_begin = lo;
+                pr.n_frames = cnt;
+                pr.out = f.out + (lo - fb) * pd.n_bins;
+                pairs.push_back(pr);
+                L.max_pair_frames = std::max(L.max_pair_frames, cnt);
+                L.pair_tiles += static_cast<size_t>((cnt + thb::kStftTileFrames - 1) / thb::kStftTileFrames);
+                if (lo > fb) {
+                    thb::TrackDesc e = f;
+                    e.n_frames = lo - fb;
+                    edges.push_back(e);
+                }
+                if (lo + cnt < fe) {
+                    thb::TrackDesc e = f;
+                    e.frame_begin = lo + cnt;
+                    e.n_frames = fe - (lo + cnt);
+                    e.out = f.out + (lo + cnt - fb) * pd.n_bins;
+                    edges.push_back(e);
+                }
+            }
+            for (const thb::TrackDesc &e : edges) L.max_edge_frames = std::max(L.max_edge_frames, e.n_frames);
+            L.n_pair = static_cast<int>(pairs.size());
+            L.n_edge = static_cast<int>(edges.size());
+            if (L.n_pair) {
+                thb::TrackDesc *hp = arena_push<thb::TrackDesc>(ctx, pairs.size(), &L.d_pair);
+                memcpy(hp, pairs.data(), sizeof(thb::TrackDesc) * pairs.size());
+            }
+            if (L.n_edge) {
+                thb::TrackDesc *he = arena_push<thb::TrackDesc>(ctx, edges.size(), &L.d_edge);
+                memcpy(he, edges.data(), sizeof(thb::TrackDesc) * edges.size());
+            }
+            max_pair_tiles = std::max(max_pair_tiles, L.pair_tiles);
+        }
+        launches.push_back(L);
     }
     rc = arena_commit(ctx);
     if (rc) return rc;
+    if (max_pair_tiles > ctx->rescue_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_rescue_items) cudaFree(ctx->d_rescue_items);
+        ctx->d_rescue_items = nullptr;
+        size_t cap = 4096;
+        while (cap < max_pair_tiles) cap <<= 1;
+        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_items), sizeof(uint2) * cap));
+        if (!ctx->d_rescue_count) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_count), sizeof(unsigned)));
+        ctx->rescue_cap = cap;
+    }
     // reset the {max, -min} slots of the channels being recomputed
     for (const Launch &l : launches) {
         cudaError_t e = thb::launch_minmax_init_tracks(l.d_desc, l.count, ctx->stream);
@@ -735,15 +838,28 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         ctx->launch_count += 1;
     }
 
-    // ---- K1/K2/K3: one launch per (sr, win, n_fft) group ----
+    // ---- K1/K2/K3: per (sr, win, n_fft) group ----
     for (const Launch &l : launches) {
         const thb::PlanDev &pd = l.plan->dev;
-        ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", (l.count + 65534) / 65535);
-        cudaError_t e;
-        if (thb::stft_fast_supported(pd))
-            e = thb::launch_stft_fast(pd, l.d_desc, l.count, l.max_frames, ctx->sm_count, ctx->stream);
-        else
-            e = thb::launch_stft_generic(pd, l.d_desc, l.count, l.max_frames, ctx->stream);
+        const int chunks = (l.count + 65534) / 65535;
+        cudaError_t e = cudaSuccess;
+        if (l.n_pair || l.n_edge) {
+            ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", (l.n_pair ? 2 : 0) + (l.n_edge ? 1 : 0));
+            if (l.n_pair) {
+                const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, static_cast<unsigned>(ctx->rescue_cap), 0};
+                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned), ctx->stream));
+                e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, l.max_pair_frames, rl, ctx->stream);
+                if (e == cudaSuccess) e = thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
+            }
+            if (e == cudaSuccess && l.n_edge)
+                e = thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream);
+        } else {
+            ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", chunks);
+            if (want_fast && thb::stft_fast_supported(pd))
+                e = thb::launch_stft_fast(pd, l.d_desc, l.count, l.max_frames, ctx->sm_count, ctx->stream);
+            else
+                e = thb::launch_stft_generic(pd, l.d_desc, l.count, l.max_frames, ctx->stream);
+        }
         if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "stft launch: %s", cudaGetErrorString(e));
     }
     // ---- outputs ----

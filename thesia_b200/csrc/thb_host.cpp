@@ -203,6 +203,45 @@ MelSchedule mel_schedule(const MelBank &b) {
     return sc;
 }
 
+MelSchedule mel_schedule_pair(const MelBank &b) {
+    MelSchedule sc;
+    sc.n_groups = (b.n_mel + 31) / 32;
+    sc.T.resize(sc.n_groups);
+    sc.woff.resize(sc.n_groups);
+    sc.start.assign(static_cast<size_t>(sc.n_groups) * 32, 0);
+    for (uint32_t g = 0; g < sc.n_groups; g++) {
+        int used[4][8] = {};
+        uint32_t lead[32] = {}, len[32] = {};
+        uint32_t T = 4;
+        for (uint32_t l = 0; l < 32; l++) {
+            const uint32_t m = g * 32 + l;
+            const int64_t k0 = m < b.n_mel ? b.k0[m] : 2 * l;
+            len[l] = m < b.n_mel ? b.ptr[m + 1] - b.ptr[m] : 0;
+            uint32_t o = static_cast<uint32_t>(k0 & 1);  // even start
+            auto unit = [&](uint32_t oo) { return static_cast<uint32_t>((((k0 - oo) / 2) % 8 + 8) % 8); };
+            while (used[l / 8][unit(o)] >= 2) o += 2;
+            used[l / 8][unit(o)]++;
+            lead[l] = o;
+            sc.start[g * 32 + l] = static_cast<int32_t>(k0 - o);
+            T = std::max(T, o + len[l]);
+        }
+        T = (T + 3) & ~3u;
+        sc.T[g] = T;
+        sc.woff[g] = static_cast<uint32_t>(sc.w.size());
+        sc.w.resize(sc.w.size() + static_cast<size_t>(T) * 32, 0.0f);
+        for (uint32_t l = 0; l < 32; l++) {
+            const uint32_t m = g * 32 + l;
+            for (uint32_t i = 0; i < len[l]; i++) {
+                const uint32_t t = lead[l] + i;
+                sc.w[sc.woff[g] + static_cast<size_t>(t / 2) * 64 + 2 * l + (t & 1)] = b.w[b.ptr[m] + i];
+            }
+            const int64_t reach = static_cast<int64_t>(sc.start[g * 32 + l]) + T - 1;
+            if (reach > static_cast<int64_t>(sc.max_reach)) sc.max_reach = static_cast<uint32_t>(reach);
+        }
+    }
+    return sc;
+}
+
 std::vector<float> MelBank::dense() const {
     std::vector<float> d(static_cast<size_t>(n_freq) * n_mel, 0.0f);
     for (uint32_t m = 0; m < n_mel; m++)

@@ -49,6 +49,10 @@ struct MelSchedule {
     uint32_t max_reach = 0;       // largest bin index any lane reads
 };
 MelSchedule mel_schedule(const MelBank &b);
+// Variant for the frame-pair kernel: magnitudes are float2 (two frames) read two bins at a time with
+// 16-byte loads, so `start` is even and the bank rule applies per quarter warp to start/2 mod 8;
+// weights are stored as float2 (steps 2t, 2t+1): w[woff[g] + 64 (t/2) + 2 lane + (t & 1)].
+MelSchedule mel_schedule_pair(const MelBank &b);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

@@ -41,7 +41,20 @@ struct PlanDev {
     int ms_max_reach;                 // largest bin index read
     // blob = T[groups] | woff[groups] | start[groups*32] | weights (interleaved)
     const uint32_t *ms_blob;
+    // same, for the two-frames-per-warp kernel (thb_stft_pair.cu): even starts, float2 weight steps
+    int mp_groups, mp_words, mp_max_reach;
+    const uint32_t *mp_blob;
 };
+
+// Tiles (64 consecutive frames of one descriptor) that the frame-pair kernel could not finish exactly
+// and the scalar kernel redoes: items[i] = {descriptor index, tile index}.
+struct RescueList {
+    uint2 *items;
+    unsigned *count;
+    unsigned capacity;
+    unsigned track_base;
+};
+constexpr int kStftTileFrames = 64;
 
 struct ImgDesc {
     const float *spec;   // (T, B) dB
@@ -66,6 +79,14 @@ cudaError_t launch_stft_generic(const PlanDev &plan, const TrackDesc *d_tracks, 
 bool stft_fast_supported(const PlanDev &plan);
 cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
                              long long max_frames, int sm_count, cudaStream_t st);
+
+// two frames per warp in packed f32x2 arithmetic, n_fft == 2048
+bool stft_pair_supported(const PlanDev &plan);
+cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
+                             long long max_frames, RescueList rescue, cudaStream_t st);
+// the scalar kernel over the tiles on a rescue list (persistent grid; a no-op when the list is empty)
+cudaError_t launch_stft_fast_list(const PlanDev &plan, const TrackDesc *d_tracks, RescueList rescue,
+                                  int sm_count, cudaStream_t st);
 
 cudaError_t launch_minmax_init(float *d_slots, int n, cudaStream_t st);
 // reset the {max, -min} slot of every channel in a descriptor array

@@ -25,7 +25,7 @@ namespace thb {
 namespace {
 
 constexpr int kWarps = 8;          // frames in flight per CTA
-constexpr int kTileFrames = 64;    // consecutive frames of one channel per CTA
+constexpr int kTileFrames = kStftTileFrames;  // consecutive frames of one channel per CTA
 constexpr int kRow = 33;           // float2 row stride of the transpose tile (conflict-free both ways)
 constexpr int kTileFloat2 = 32 * kRow;
 
@@ -138,16 +138,22 @@ __device__ __forceinline__ FastSmem carve(unsigned char *raw) {
     return s;
 }
 
-template <bool MEL>
+// LIST = false: grid (tiles, descriptors).  LIST = true: a persistent grid walks the rescue list the
+// frame-pair kernel left behind (thb_stft_pair.cu) -- normally empty, so every CTA exits at once.
+template <bool MEL, bool LIST>
 __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev p,
-                                                                   const TrackDesc *__restrict__ tracks) {
+                                                                   const TrackDesc *__restrict__ tracks,
+                                                                   const RescueList rescue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red_max[kWarps], red_nmin[kWarps];
 
-    const TrackDesc d = tracks[blockIdx.y];
-    const long long f_begin = static_cast<long long>(blockIdx.x) * kTileFrames;
-    if (f_begin >= d.n_frames) return;
-    const long long f_end = min(f_begin + kTileFrames, d.n_frames);
+    unsigned n_items = 1;
+    if (LIST) {
+        n_items = min(*rescue.count, rescue.capacity);
+        if (blockIdx.x >= n_items) return;
+    } else if (static_cast<long long>(blockIdx.x) * kTileFrames >= tracks[blockIdx.y].n_frames) {
+        return;
+    }
 
     const FastSmem sm = carve(smem_raw);
     // ---- tables -> shared memory; tiles start out as zeros (the mel walk reads padding x 0) ----
@@ -169,6 +175,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
     const int half = p.win / 2;
     const int partner = (32 - lane) & 31;
     const int lane32 = lane ? lane : 32;
+
+    for (unsigned item = LIST ? blockIdx.x : 0; item < n_items; item += LIST ? gridDim.x : 1) {
+    const uint2 it = LIST ? rescue.items[item] : make_uint2(blockIdx.y, blockIdx.x);
+    const TrackDesc d = tracks[it.x];
+    const long long f_begin = static_cast<long long>(it.y) * kTileFrames;
+    const long long f_end = min(f_begin + kTileFrames, d.n_frames);
     float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
 
     for (long long f = f_begin + warp; f < f_end; f += kWarps) {
@@ -216,7 +228,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
 #pragma unroll
         for (int k1 = 0; k1 < 32; k1++) {
             float2 t = v[perm32(k1)];
-            if (k1) t = cmul(t, sm.tw1[(k1 - 1) * 32 + lane]);
+            if (k1) {  // same operation order as the packed kernel's cmul_s: the two kernels agree bit for bit
+                const float2 w = sm.tw1[(k1 - 1) * 32 + lane];
+                t = make_float2(fmaf(t.y, -w.y, t.x * w.x), fmaf(t.x, w.y, t.y * w.x));
+            }
             tile[k1 * kRow + lane] = t;
         }
         __syncwarp();
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
                 zn.y = __shfl_sync(0xffffffffu, sup.y, partner);
                 const float er = zk.x + zn.x, ei = zk.y - zn.y, dr = zk.x - zn.x, di = zk.y + zn.y;
                 const float2 w = sm.tw2[j * 32 + lane];
-                const float wr = w.x * dr - w.y * di, wi = w.x * di + w.y * dr;
+                const float wr = fmaf(di, -w.y, dr * w.x), wi = fmaf(dr, w.y, di * w.x);
                 const float ar = er + wi, ai = ei - wr, br = er - wi, bi = ei + wr;
                 const float sa = fmaf(ar, ar, ai * ai), sb = fmaf(br, br, bi * bi);
                 smax = fmaxf(smax, fmaxf(sa, sb));
@@ -330,6 +345,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
             atomic_max_float(&d.minmax[1], b);
         }
     }
+    __syncthreads();  // red_max / red_nmin are reused by the next item
+    }
 }
 
 size_t fast_smem_bytes(const PlanDev &p) {
@@ -349,18 +366,28 @@ cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int
                              int /*sm_count*/, cudaStream_t st) {
     if (n_tracks <= 0 || max_frames <= 0) return cudaSuccess;
     const size_t smem = fast_smem_bytes(plan);
-    auto kern = plan.n_mel ? stft2048_kernel<true> : stft2048_kernel<false>;
+    auto kern = plan.n_mel ? stft2048_kernel<true, false> : stft2048_kernel<false, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long tiles = (max_frames + kTileFrames - 1) / kTileFrames;
     for (int t0 = 0; t0 < n_tracks; t0 += 65535) {
         const int nt = min(65535, n_tracks - t0);
         dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(nt));
-        kern<<<grid, kWarps * 32, smem, st>>>(plan, d_tracks + t0);
+        kern<<<grid, kWarps * 32, smem, st>>>(plan, d_tracks + t0, RescueList{});
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t launch_stft_fast_list(const PlanDev &plan, const TrackDesc *d_tracks, RescueList rescue, int sm_count,
+                                  cudaStream_t st) {
+    const size_t smem = fast_smem_bytes(plan);
+    auto kern = plan.n_mel ? stft2048_kernel<true, true> : stft2048_kernel<false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<2 * sm_count, kWarps * 32, smem, st>>>(plan, d_tracks, rescue);
+    return cudaGetLastError();
 }
 
 }  // namespace thb
