@@ -135,7 +135,7 @@ struct thb_ctx {
 
     // tiles the frame-pair STFT kernel hands back to the scalar kernel (thb_kernels.cuh RescueList)
     uint2 *d_rescue_items = nullptr;
-    unsigned *d_rescue_count = nullptr;
+    unsigned *d_rescue_count = nullptr;  // [0] = count, [1 ..] = one flag per (descriptor, tile)
     size_t rescue_cap = 0;
 
     std::vector<void *> env_outputs;  // device buffers of the last waveform call
@@ -322,45 +322,17 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
             d.max_band_len = std::max<int>(d.max_band_len, static_cast<int>(mb.ptr[m + 1] - mb.ptr[m]));
     }
     d.n_bins = d.n_mel ? d.n_mel : d.n_freq;
-    d.ms_groups = d.ms_words = d.ms_max_reach = 0;
-    d.ms_blob = nullptr;
-    std::vector<uint32_t> ms_blob;
+    d.mi_words = d.mi_groups = d.mi_min_start = d.mi_max_reach = 0;
+    d.mi_blob = nullptr;
+    std::vector<uint32_t> mi_blob;
     if (d.n_mel && d.n_fft == 2048) {
-        const thb::MelSchedule sc = thb::mel_schedule(thb::mel_bank(sr, f.n_fft, s.n_mel));
-        d.ms_groups = static_cast<int>(sc.n_groups);
-        d.ms_max_reach = static_cast<int>(sc.max_reach);
-        ms_blob.insert(ms_blob.end(), sc.T.begin(), sc.T.end());
-        const uint32_t w_base = sc.n_groups * 34;
-        for (uint32_t g = 0; g < sc.n_groups; g++) ms_blob.push_back(w_base + sc.woff[g]);
-        for (int32_t v : sc.start) ms_blob.push_back(static_cast<uint32_t>(v));
-        for (float v : sc.w) {
-            uint32_t u;
-            memcpy(&u, &v, 4);
-            ms_blob.push_back(u);
-        }
-        while (ms_blob.size() & 3) ms_blob.push_back(0);
-        d.ms_words = static_cast<int>(ms_blob.size());
-        if ((rc = upload(ctx, pl.get(), ms_blob, &d.ms_blob))) return rc;
-    }
-    d.mp_groups = d.mp_words = d.mp_max_reach = 0;
-    d.mp_blob = nullptr;
-    std::vector<uint32_t> mp_blob;
-    if (d.n_mel && d.n_fft == 2048) {
-        const thb::MelSchedule sc = thb::mel_schedule_pair(thb::mel_bank(sr, f.n_fft, s.n_mel));
-        d.mp_groups = static_cast<int>(sc.n_groups);
-        d.mp_max_reach = static_cast<int>(sc.max_reach);
-        mp_blob.insert(mp_blob.end(), sc.T.begin(), sc.T.end());
-        const uint32_t w_base = sc.n_groups * 34;
-        for (uint32_t g = 0; g < sc.n_groups; g++) mp_blob.push_back(w_base + sc.woff[g]);
-        for (int32_t v : sc.start) mp_blob.push_back(static_cast<uint32_t>(v));
-        for (float v : sc.w) {
-            uint32_t u;
-            memcpy(&u, &v, 4);
-            mp_blob.push_back(u);
-        }
-        while (mp_blob.size() & 3) mp_blob.push_back(0);
-        d.mp_words = static_cast<int>(mp_blob.size());
-        if ((rc = upload(ctx, pl.get(), mp_blob, &d.mp_blob))) return rc;
+        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
+        mi_blob = mi.blob();
+        d.mi_words = static_cast<int>(mi_blob.size());
+        d.mi_groups = static_cast<int>(mi.n_groups);
+        d.mi_min_start = mi.min_start;
+        d.mi_max_reach = static_cast<int>(mi.max_reach);
+        if ((rc = upload(ctx, pl.get(), mi_blob, &d.mi_blob))) return rc;
     }
     d.fast_wpad = nullptr;
     d.fast_tw = nullptr;
@@ -790,7 +762,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 pr.out = f.out + (lo - fb) * pd.n_bins;
                 pairs.push_back(pr);
                 L.max_pair_frames = std::max(L.max_pair_frames, cnt);
-                L.pair_tiles += static_cast<size_t>((cnt + thb::kStftTileFrames - 1) / thb::kStftTileFrames);
+
                 if (lo > fb) {
                     thb::TrackDesc e = f;
                     e.n_frames = lo - fb;
@@ -815,6 +787,8 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 thb::TrackDesc *he = arena_push<thb::TrackDesc>(ctx, edges.size(), &L.d_edge);
                 memcpy(he, edges.data(), sizeof(thb::TrackDesc) * edges.size());
             }
+            const long long tf = thb::stft_pair_tile_frames();
+            L.pair_tiles = static_cast<size_t>(L.n_pair) * static_cast<size_t>((L.max_pair_frames + tf - 1) / tf);
             max_pair_tiles = std::max(max_pair_tiles, L.pair_tiles);
         }
         launches.push_back(L);
@@ -824,11 +798,13 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     if (max_pair_tiles > ctx->rescue_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_rescue_items) cudaFree(ctx->d_rescue_items);
+        if (ctx->d_rescue_count) cudaFree(ctx->d_rescue_count);
         ctx->d_rescue_items = nullptr;
+        ctx->d_rescue_count = nullptr;
         size_t cap = 4096;
         while (cap < max_pair_tiles) cap <<= 1;
         CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_items), sizeof(uint2) * cap));
-        if (!ctx->d_rescue_count) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_count), sizeof(unsigned)));
+        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_count), sizeof(unsigned) * (cap + 1)));
         ctx->rescue_cap = cap;
     }
     // reset the {max, -min} slots of the channels being recomputed
@@ -846,9 +822,12 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         if (l.n_pair || l.n_edge) {
             ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", (l.n_pair ? 2 : 0) + (l.n_edge ? 1 : 0));
             if (l.n_pair) {
-                const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, static_cast<unsigned>(ctx->rescue_cap), 0};
-                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned), ctx->stream));
-                e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, l.max_pair_frames, rl, ctx->stream);
+                const unsigned tf = static_cast<unsigned>(thb::stft_pair_tile_frames());
+                const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
+                                         static_cast<unsigned>(ctx->rescue_cap), tf,
+                                         static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf)};
+                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
+                e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, ctx->sm_count, ctx->stream);
                 if (e == cudaSuccess) e = thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
             }
             if (e == cudaSuccess && l.n_edge)

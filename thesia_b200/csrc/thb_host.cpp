@@ -165,81 +165,99 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
     }
 }
 
-MelSchedule mel_schedule(const MelBank &b) {
-    MelSchedule sc;
-    sc.n_groups = (b.n_mel + 31) / 32;
-    sc.T.resize(sc.n_groups);
-    sc.woff.resize(sc.n_groups);
-    sc.start.assign(static_cast<size_t>(sc.n_groups) * 32, 0);
-    for (uint32_t g = 0; g < sc.n_groups; g++) {
-        // every bank may be hit by at most two lanes: a 2-way conflict costs one extra wavefront per
-        // step, pulling a band further back costs a whole extra step for the group
-        int used[32] = {};
-        uint32_t lead[32] = {}, len[32] = {};
-        uint32_t T = 4;
-        for (uint32_t l = 0; l < 32; l++) {
-            const uint32_t m = g * 32 + l;
-            const int64_t k0 = m < b.n_mel ? b.k0[m] : l;
-            len[l] = m < b.n_mel ? b.ptr[m + 1] - b.ptr[m] : 0;
-            uint32_t o = 0;
-            while (used[static_cast<uint32_t>(((k0 - o) % 32 + 32) % 32)] >= 2) o++;
-            used[static_cast<uint32_t>(((k0 - o) % 32 + 32) % 32)]++;
-            lead[l] = o;
-            sc.start[g * 32 + l] = static_cast<int32_t>(k0 - o);
-            T = std::max(T, o + len[l]);
-        }
-        T = (T + 3) & ~3u;
-        sc.T[g] = T;
-        sc.woff[g] = static_cast<uint32_t>(sc.w.size());
-        sc.w.resize(sc.w.size() + static_cast<size_t>(T) * 32, 0.0f);
-        for (uint32_t l = 0; l < 32; l++) {
-            const uint32_t m = g * 32 + l;
-            for (uint32_t i = 0; i < len[l]; i++)
-                sc.w[sc.woff[g] + static_cast<size_t>(lead[l] + i) * 32 + l] = b.w[b.ptr[m] + i];
-            const int64_t reach = static_cast<int64_t>(sc.start[g * 32 + l]) + T - 1;
-            if (reach > static_cast<int64_t>(sc.max_reach)) sc.max_reach = static_cast<uint32_t>(reach);
+MelItems mel_items(const MelBank &b) {
+    MelItems it;
+    it.n_mel = b.n_mel;
+    struct Piece {
+        uint32_t band, k, len, wofs;
+    };
+    std::vector<Piece> pieces;
+    std::vector<std::vector<uint32_t>> of_band(b.n_mel);
+    for (uint32_t m = 0; m < b.n_mel; m++) {
+        const uint32_t len = b.ptr[m + 1] - b.ptr[m];
+        const uint32_t np = std::max<uint32_t>(1, (len + kMelPieceMax - 1) / kMelPieceMax);
+        const uint32_t base = len / np, rem = len % np;
+        uint32_t pos = 0;
+        for (uint32_t i = 0; i < np; i++) {
+            const uint32_t li = base + (i < rem ? 1 : 0);
+            of_band[m].push_back(static_cast<uint32_t>(pieces.size()));
+            pieces.push_back({m, b.k0[m] + pos, li, b.ptr[m] + pos});
+            pos += li;
         }
     }
-    return sc;
+    std::vector<uint32_t> order(pieces.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return pieces[x].len > pieces[y].len; });
+    it.n_groups = static_cast<uint32_t>((pieces.size() + 31) / 32);
+    it.T.resize(it.n_groups);
+    it.woff.resize(it.n_groups);
+    it.start.assign(static_cast<size_t>(it.n_groups) * 32, 0);
+    std::vector<uint32_t> slot_of(pieces.size());
+    for (uint32_t g = 0; g < it.n_groups; g++) {
+        uint32_t lead[32] = {}, T = 2;
+        int used[2][16] = {};
+        for (uint32_t l = 0; l < 32; l++) {
+            const size_t oi = static_cast<size_t>(g) * 32 + l;
+            if (oi >= order.size()) {
+                it.start[oi] = static_cast<int32_t>(l);  // idle lane: zero weights, harmless address
+                continue;
+            }
+            const Piece &pc = pieces[order[oi]];
+            uint32_t o = 0;
+            auto res = [&](uint32_t oo) { return ((static_cast<int64_t>(pc.k) - oo) % 16 + 16) % 16; };
+            while (o < 15 && used[l / 16][res(o)] >= 2) o++;
+            used[l / 16][res(o)]++;
+            lead[l] = o;
+            it.start[oi] = static_cast<int32_t>(pc.k) - static_cast<int32_t>(o);
+            slot_of[order[oi]] = static_cast<uint32_t>(oi);
+            T = std::max(T, o + pc.len);
+        }
+        T = (T + 1) & ~1u;
+        it.T[g] = T;
+        it.woff[g] = static_cast<uint32_t>(it.w.size());
+        it.w.resize(it.w.size() + static_cast<size_t>(T) * 32, 0.0f);
+        for (uint32_t l = 0; l < 32; l++) {
+            const size_t oi = static_cast<size_t>(g) * 32 + l;
+            it.min_start = std::min(it.min_start, it.start[oi]);
+            const int64_t reach = static_cast<int64_t>(it.start[oi]) + T - 1;
+            if (reach > static_cast<int64_t>(it.max_reach)) it.max_reach = static_cast<uint32_t>(reach);
+            if (oi >= order.size()) continue;
+            const Piece &pc = pieces[order[oi]];
+            for (uint32_t i = 0; i < pc.len; i++)
+                {
+                const uint32_t t = lead[l] + i;  // float2 steps: (t even, t odd) side by side per lane
+                it.w[it.woff[g] + static_cast<size_t>(t / 2) * 64 + 2 * l + (t & 1)] = b.w[pc.wofs + i];
+            }
+        }
+    }
+    it.piece_ptr.assign(b.n_mel + 1, 0);
+    for (uint32_t m = 0; m < b.n_mel; m++) {
+        for (uint32_t pi : of_band[m]) it.piece_ids.push_back(slot_of[pi]);
+        it.piece_ptr[m + 1] = static_cast<uint32_t>(it.piece_ids.size());
+    }
+    return it;
 }
 
-MelSchedule mel_schedule_pair(const MelBank &b) {
-    MelSchedule sc;
-    sc.n_groups = (b.n_mel + 31) / 32;
-    sc.T.resize(sc.n_groups);
-    sc.woff.resize(sc.n_groups);
-    sc.start.assign(static_cast<size_t>(sc.n_groups) * 32, 0);
-    for (uint32_t g = 0; g < sc.n_groups; g++) {
-        int used[4][8] = {};
-        uint32_t lead[32] = {}, len[32] = {};
-        uint32_t T = 4;
-        for (uint32_t l = 0; l < 32; l++) {
-            const uint32_t m = g * 32 + l;
-            const int64_t k0 = m < b.n_mel ? b.k0[m] : 2 * l;
-            len[l] = m < b.n_mel ? b.ptr[m + 1] - b.ptr[m] : 0;
-            uint32_t o = static_cast<uint32_t>(k0 & 1);  // even start
-            auto unit = [&](uint32_t oo) { return static_cast<uint32_t>((((k0 - oo) / 2) % 8 + 8) % 8); };
-            while (used[l / 8][unit(o)] >= 2) o += 2;
-            used[l / 8][unit(o)]++;
-            lead[l] = o;
-            sc.start[g * 32 + l] = static_cast<int32_t>(k0 - o);
-            T = std::max(T, o + len[l]);
-        }
-        T = (T + 3) & ~3u;
-        sc.T[g] = T;
-        sc.woff[g] = static_cast<uint32_t>(sc.w.size());
-        sc.w.resize(sc.w.size() + static_cast<size_t>(T) * 32, 0.0f);
-        for (uint32_t l = 0; l < 32; l++) {
-            const uint32_t m = g * 32 + l;
-            for (uint32_t i = 0; i < len[l]; i++) {
-                const uint32_t t = lead[l] + i;
-                sc.w[sc.woff[g] + static_cast<size_t>(t / 2) * 64 + 2 * l + (t & 1)] = b.w[b.ptr[m] + i];
-            }
-            const int64_t reach = static_cast<int64_t>(sc.start[g * 32 + l]) + T - 1;
-            if (reach > static_cast<int64_t>(sc.max_reach)) sc.max_reach = static_cast<uint32_t>(reach);
-        }
-    }
-    return sc;
+std::vector<uint32_t> MelItems::blob() const {
+    std::vector<uint32_t> o(8, 0);
+    auto put = [&](size_t hdr, const void *data, size_t words) {
+        o[hdr] = static_cast<uint32_t>(o.size());
+        const uint32_t *p = static_cast<const uint32_t *>(data);
+        o.insert(o.end(), p, p + words);
+    };
+    o[0] = n_groups;
+    o[1] = n_mel;
+    put(2, T.data(), T.size());
+    const size_t woff_at = o.size();
+    put(3, woff.data(), woff.size());
+    put(4, start.data(), start.size());
+    put(5, piece_ptr.data(), piece_ptr.size());
+    put(6, piece_ids.data(), piece_ids.size());
+    while (o.size() & 3) o.push_back(0);
+    put(7, w.data(), w.size());
+    for (size_t g = 0; g < woff.size(); g++) o[woff_at + g] += o[7];
+    while (o.size() & 3) o.push_back(0);
+    return o;
 }
 
 std::vector<float> MelBank::dense() const {

@@ -35,24 +35,30 @@ struct MelBank {
     std::vector<float> w;       // weights of band m: w[ptr[m] .. ptr[m+1]) for bins k0[m]...
     std::vector<float> dense() const;  // (n_freq, n_mel) row-major
 };
-// Lane schedule of the sparse mel product for a warp: bands are taken 32 at a time (lane = band
-// within the group); every lane walks `T[g]` consecutive bins starting at `start`, with its weights
-// interleaved as w[woff[g] + 32 t + lane] (zero where the band has no weight).  `start` is pulled
-// back by up to 31 bins so that the 32 lanes of a group always hit 32 different shared-memory
-// banks (start mod 32 distinct); it can therefore be as low as -31.
-struct MelSchedule {
-    uint32_t n_groups = 0;
-    std::vector<uint32_t> T;      // [n_groups], multiple of 4
-    std::vector<uint32_t> woff;   // [n_groups]
-    std::vector<int32_t> start;   // [n_groups * 32]
-    std::vector<float> w;         // interleaved weights
-    uint32_t max_reach = 0;       // largest bin index any lane reads
+// Warp schedule of the sparse mel product, shared by the two n_fft == 2048 kernels (they must add in the same
+// order to agree bit for bit).  Every band is cut into pieces of at most kMelPieceMax consecutive bins; the pieces
+// ("items") are sorted by length and dealt 32 at a time to the lanes of a warp ("groups"), so that a group costs
+// max-length steps and the sum over groups stays close to nnz / 32.  Lane l of group g walks T[g] bins from
+// start[g*32+l] with weights w[woff[g] + 64 (t/2) + 2 l + (t&1)] (zero outside the piece) and leaves a partial sum in slot
+// g*32+l; band m is the sum of its slots piece_ids[piece_ptr[m] .. piece_ptr[m+1]) in ascending-bin order.
+// `start` is pulled back by a few bins (zero weights) so that the 16 lanes of each half warp hit every 8-byte
+// shared-memory bank pair at most twice; it can be negative (>= -15).
+constexpr uint32_t kMelPieceMax = 16;
+struct MelItems {
+    uint32_t n_groups = 0, n_mel = 0;
+    std::vector<uint32_t> T;          // [n_groups], even
+    std::vector<uint32_t> woff;       // [n_groups], offset into w
+    std::vector<int32_t> start;       // [n_groups * 32]
+    std::vector<float> w;             // interleaved weights
+    std::vector<uint32_t> piece_ptr;  // [n_mel + 1]
+    std::vector<uint32_t> piece_ids;  // slots, ascending bins within a band
+    int32_t min_start = 0;
+    uint32_t max_reach = 0;           // largest bin index any lane reads
+    // one blob of 32-bit words for the device: header {n_groups, n_mel, off_T, off_woff, off_start, off_pptr,
+    // off_pids, off_w} then the arrays; woff entries are made absolute word offsets into the blob
+    std::vector<uint32_t> blob() const;
 };
-MelSchedule mel_schedule(const MelBank &b);
-// Variant for the frame-pair kernel: magnitudes are float2 (two frames) read two bins at a time with
-// 16-byte loads, so `start` is even and the bank rule applies per quarter warp to start/2 mod 8;
-// weights are stored as float2 (steps 2t, 2t+1): w[woff[g] + 64 (t/2) + 2 lane + (t & 1)].
-MelSchedule mel_schedule_pair(const MelBank &b);
+MelItems mel_items(const MelBank &b);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

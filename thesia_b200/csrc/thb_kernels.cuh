@@ -35,26 +35,23 @@ struct PlanDev {
     // n_fft == 2048 warp-per-frame path (thb_stft_fast.cu); null otherwise
     const float *fast_wpad;           // [2048] 0.5 * window centred in the FFT buffer, zeros outside
     const float2 *fast_tw;            // [31*32] W_1024^(lane*k1) then [16*32] split twiddles
-    // warp schedule of the sparse mel product (thb_host.hpp MelSchedule); mel only
-    int ms_groups;
-    int ms_words;                     // size of ms_blob in 32-bit words
-    int ms_max_reach;                 // largest bin index read
-    // blob = T[groups] | woff[groups] | start[groups*32] | weights (interleaved)
-    const uint32_t *ms_blob;
-    // same, for the two-frames-per-warp kernel (thb_stft_pair.cu): even starts, float2 weight steps
-    int mp_groups, mp_words, mp_max_reach;
-    const uint32_t *mp_blob;
+    // warp schedule of the sparse mel product (thb_host.hpp MelItems::blob); mel only, n_fft == 2048
+    int mi_words;                     // size of mi_blob in 32-bit words
+    int mi_groups, mi_min_start, mi_max_reach;
+    const uint32_t *mi_blob;
 };
 
-// Tiles (64 consecutive frames of one descriptor) that the frame-pair kernel could not finish exactly
-// and the scalar kernel redoes: items[i] = {descriptor index, tile index}.
+// Tiles (tile_frames consecutive frames of one descriptor) that the frame-pair kernel could not finish
+// exactly and the scalar kernel redoes: items[i] = {descriptor index, tile index}; flags[] (one word per
+// (descriptor, tile), zeroed before the launch) keeps a tile from being listed twice.
 struct RescueList {
     uint2 *items;
     unsigned *count;
+    unsigned *flags;
     unsigned capacity;
-    unsigned track_base;
+    unsigned tile_frames;
+    unsigned tiles_per_track;
 };
-constexpr int kStftTileFrames = 64;
 
 struct ImgDesc {
     const float *spec;   // (T, B) dB
@@ -82,8 +79,10 @@ cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int
 
 // two frames per warp in packed f32x2 arithmetic, n_fft == 2048
 bool stft_pair_supported(const PlanDev &plan);
-cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
-                             long long max_frames, RescueList rescue, cudaStream_t st);
+cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
+                             int sm_count, cudaStream_t st);
+// frames per work item of the frame-pair kernel (a multiple of twice its warps per CTA)
+int stft_pair_tile_frames();
 // the scalar kernel over the tiles on a rescue list (persistent grid; a no-op when the list is empty)
 cudaError_t launch_stft_fast_list(const PlanDev &plan, const TrackDesc *d_tracks, RescueList rescue,
                                   int sm_count, cudaStream_t st);

@@ -17,33 +17,16 @@
 //   dB     : log10 * 20 (decibel.rs:198-202) through MUFU.LG2; running {max, -min} per channel
 //            (find_min_max, mod.rs:169-178), one atomic pair per CTA.
 // The 0.5 of the real-split is folded into the window table (exact power-of-two scaling).
-#include "thb_device.cuh"
-#include "thb_kernels.cuh"
+#include "thb_stft2048.cuh"
 
 namespace thb {
 
 namespace {
 
-constexpr int kWarps = 8;          // frames in flight per CTA
-constexpr int kTileFrames = kStftTileFrames;  // consecutive frames of one channel per CTA
-constexpr int kRow = 33;           // float2 row stride of the transpose tile (conflict-free both ways)
-constexpr int kTileFloat2 = 32 * kRow;
+using namespace k2048;
 
-// cos / sin of 2 pi j / 32
-__device__ constexpr float kC32[32] = {
-    1.0f, 0.9807852506637573f, 0.9238795042037964f, 0.8314695954322815f, 0.7071067690849304f, 0.5555702447891235f,
-    0.3826834261417389f, 0.19509032368659973f, 0.0f, -0.19509032368659973f, -0.3826834261417389f, -0.5555702447891235f,
-    -0.7071067690849304f, -0.8314695954322815f, -0.9238795042037964f, -0.9807852506637573f, -1.0f,
-    -0.9807852506637573f, -0.9238795042037964f, -0.8314695954322815f, -0.7071067690849304f, -0.5555702447891235f,
-    -0.3826834261417389f, -0.19509032368659973f, 0.0f, 0.19509032368659973f, 0.3826834261417389f, 0.5555702447891235f,
-    0.7071067690849304f, 0.8314695954322815f, 0.9238795042037964f, 0.9807852506637573f};
-__device__ constexpr float kS32[32] = {
-    0.0f, 0.19509032368659973f, 0.3826834261417389f, 0.5555702447891235f, 0.7071067690849304f, 0.8314695954322815f,
-    0.9238795042037964f, 0.9807852506637573f, 1.0f, 0.9807852506637573f, 0.9238795042037964f, 0.8314695954322815f,
-    0.7071067690849304f, 0.5555702447891235f, 0.3826834261417389f, 0.19509032368659973f, 0.0f, -0.19509032368659973f,
-    -0.3826834261417389f, -0.5555702447891235f, -0.7071067690849304f, -0.8314695954322815f, -0.9238795042037964f,
-    -0.9807852506637573f, -1.0f, -0.9807852506637573f, -0.9238795042037964f, -0.8314695954322815f,
-    -0.7071067690849304f, -0.5555702447891235f, -0.3826834261417389f, -0.19509032368659973f};
+constexpr int kWarps = 8;        // frames in flight per CTA
+constexpr int kTileFrames = 64;  // consecutive frames of one channel per CTA (grid mode)
 
 // a * W_32^J,  W_32 = exp(-2 pi i / 32)
 template <int J>
@@ -80,8 +63,6 @@ __device__ __forceinline__ void dft8r(float2 &v0, float2 &v1, float2 &v2, float2
 }
 
 // In-register 32-point forward DFT.  Output X[k] is left in v[perm32(k)].
-__device__ __forceinline__ constexpr int perm32(int k) { return 8 * (k & 3) + (k >> 2); }
-
 template <int B>
 __device__ __forceinline__ void dft32_col(float2 (&v)[32]) {
     dft4(v[B], v[B + 8], v[B + 16], v[B + 24]);
@@ -100,41 +81,27 @@ __device__ __forceinline__ void dft32(float2 (&v)[32]) {
               v[8 * q + 7]);
 }
 
-__device__ __forceinline__ float lg2_ftz(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sqrt_ftz(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-constexpr float kDbPerLog2Pow = 3.01029995663981195f;   // 10 log10(2): dB per doubling of power
-constexpr float kDbPerLog2Amp = 6.02059991327962390f;   // 20 log10(2)
-// |X|^2 leaves the range where f32 squares are exact enough below / above these; such frames are
-// re-run once with the spectrum scaled by 2^(+-60) (exact) and the dB shifted back
-constexpr float kPowTiny = 8.2718061e-25f;   // 2^-80
-constexpr float kPowHuge = 1.2676506e+30f;   // 2^100
-constexpr float kRescueUp = 1.1529215e+18f;  // 2^60
-constexpr float kRescueDown = 8.6736174e-19f;  // 2^-60
-
 struct FastSmem {
-    float *wpad;      // [2048]   0.5 * window, zero outside the taps
-    float2 *tw1;      // [31][32] W_1024^(lane * k1), k1 = 1..31
-    float2 *tw2;      // [16][32] W_2048^(k_own(j, lane))
-    float2 *tiles;    // [kWarps][32 * 33]
-    const uint32_t *ms;  // mel schedule blob
+    float *wpad;         // [2048]   0.5 * window, zero outside the taps
+    float2 *tw1;         // [31][32] W_1024^(lane * k1), k1 = 1..31
+    float2 *tw2;         // [16][32] W_2048^(k_own(j, lane))
+    float *tiles;        // [kWarps][tile_floats]
+    const uint32_t *ms;  // MelItems blob
 };
 
-__device__ __forceinline__ FastSmem carve(unsigned char *raw) {
+// floats per warp tile: the float2 transpose tile, or magnitudes + mel partial sums, whichever is larger
+__host__ __device__ inline int fast_tile_floats(const PlanDev &p) {
+    const int t = tile_elems(p);
+    return t > 2 * 32 * kRow ? t : 2 * 32 * kRow;
+}
+
+__device__ __forceinline__ FastSmem carve(unsigned char *raw, int tile_floats) {
     FastSmem s;
     s.wpad = reinterpret_cast<float *>(raw);
     s.tw1 = reinterpret_cast<float2 *>(s.wpad + 2048);
     s.tw2 = s.tw1 + 31 * 32;
-    s.tiles = s.tw2 + 16 * 32;
-    s.ms = reinterpret_cast<const uint32_t *>(s.tiles + kWarps * kTileFloat2);
+    s.tiles = reinterpret_cast<float *>(s.tw2 + 16 * 32);
+    s.ms = reinterpret_cast<const uint32_t *>(s.tiles + kWarps * tile_floats);
     return s;
 }
 
@@ -147,6 +114,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red_max[kWarps], red_nmin[kWarps];
 
+    const int tile_frames = LIST ? static_cast<int>(rescue.tile_frames) : kTileFrames;
     unsigned n_items = 1;
     if (LIST) {
         n_items = min(*rescue.count, rescue.capacity);
@@ -155,210 +123,214 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
         return;
     }
 
-    const FastSmem sm = carve(smem_raw);
+    const int tile_floats = fast_tile_floats(p);
+    const FastSmem sm = carve(smem_raw, tile_floats);
     // ---- tables -> shared memory; tiles start out as zeros (the mel walk reads padding x 0) ----
     for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.wpad)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_wpad) + i);
     for (int i = threadIdx.x; i < (31 * 32 + 16 * 32) / 2; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.tw1)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_tw) + i);
-    for (int i = threadIdx.x; i < kWarps * kTileFloat2 / 2; i += blockDim.x)
+    for (int i = threadIdx.x; i < kWarps * tile_floats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MEL) {
-        for (int i = threadIdx.x; i < p.ms_words / 4; i += blockDim.x)
-            reinterpret_cast<uint4 *>(const_cast<uint32_t *>(sm.ms))[i] = __ldg(reinterpret_cast<const uint4 *>(p.ms_blob) + i);
+        for (int i = threadIdx.x; i < p.mi_words / 4; i += blockDim.x)
+            reinterpret_cast<uint4 *>(const_cast<uint32_t *>(sm.ms))[i] = __ldg(reinterpret_cast<const uint4 *>(p.mi_blob) + i);
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *tile = sm.tiles + warp * kTileFloat2;
-    float *mag = reinterpret_cast<float *>(tile) + 32;  // the mel walk may start up to 31 bins early
+    float2 *tile = reinterpret_cast<float2 *>(sm.tiles + warp * tile_floats);
+    float *mag = reinterpret_cast<float *>(tile) + kMagBase;
+    float *part = reinterpret_cast<float *>(tile) + part_base(p);
     const int half = p.win / 2;
     const int partner = (32 - lane) & 31;
     const int lane32 = lane ? lane : 32;
 
     for (unsigned item = LIST ? blockIdx.x : 0; item < n_items; item += LIST ? gridDim.x : 1) {
-    const uint2 it = LIST ? rescue.items[item] : make_uint2(blockIdx.y, blockIdx.x);
-    const TrackDesc d = tracks[it.x];
-    const long long f_begin = static_cast<long long>(it.y) * kTileFrames;
-    const long long f_end = min(f_begin + kTileFrames, d.n_frames);
-    float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
+        const uint2 it = LIST ? rescue.items[item] : make_uint2(blockIdx.y, blockIdx.x);
+        const TrackDesc d = tracks[it.x];
+        const long long f_begin = static_cast<long long>(it.y) * tile_frames;
+        const long long f_end = min(f_begin + tile_frames, d.n_frames);
+        float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
 
-    for (long long f = f_begin + warp; f < f_end; f += kWarps) {
-        float2 v[32];
-        // ---- load + window: v[n1] = z[32 n1 + lane] ----
-        const long long tap0 = (d.frame_begin + f) * p.hop - half;  // file index of window tap 0
-        const long long first = tap0 - p.pad_left;                  // file index of FFT position 0
-        const bool interior = tap0 >= 0 && tap0 + p.win <= d.full_len && first >= d.pcm_offset &&
-                              first + 2048 <= d.pcm_offset + d.slice_len;
-        if (interior) {
-            const float *src = d.pcm + (first - d.pcm_offset) + 2 * lane;
-            if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        for (long long f = f_begin + warp; f < f_end; f += kWarps) {
+            float2 v[32];
+            // ---- load + window: v[n1] = z[32 n1 + lane] ----
+            const long long tap0 = (d.frame_begin + f) * p.hop - half;  // file index of window tap 0
+            const long long first = tap0 - p.pad_left;                  // file index of FFT position 0
+            const bool interior = tap0 >= 0 && tap0 + p.win <= d.full_len && first >= d.pcm_offset &&
+                                  first + 2048 <= d.pcm_offset + d.slice_len;
+            if (interior) {
+                const float *src = d.pcm + (first - d.pcm_offset) + 2 * lane;
+                if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
 #pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) v[n1] = __ldg(reinterpret_cast<const float2 *>(src + 64 * n1));
+                    for (int n1 = 0; n1 < 32; n1++) v[n1] = __ldg(reinterpret_cast<const float2 *>(src + 64 * n1));
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; n1++) v[n1] = make_float2(__ldg(src + 64 * n1), __ldg(src + 64 * n1 + 1));
+                }
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    v[n1].x *= w.x;
+                    v[n1].y *= w.y;
+                }
             } else {
-#pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) v[n1] = make_float2(__ldg(src + 64 * n1), __ldg(src + 64 * n1 + 1));
-            }
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
-                v[n1].x *= w.x;
-                v[n1].y *= w.y;
-            }
-        } else {
-            // file edges: numpy-style reflect (utils.rs:111-137), taps outside the window are zero;
-            // staged through the warp's tile so that v[] keeps compile-time indices
-            float *stage = reinterpret_cast<float *>(tile);
-            for (int pos = lane; pos < 2048; pos += 32) {
-                const int a = pos - p.pad_left;
-                float x = 0.0f;
-                if (a >= 0 && a < p.win) {
-                    const long long s = reflect_index(tap0 + a, d.full_len);
-                    x = __ldg(&d.pcm[s - d.pcm_offset]) * sm.wpad[pos];
+                // file edges: numpy-style reflect (utils.rs:111-137), taps outside the window are zero;
+                // staged through the warp's tile so that v[] keeps compile-time indices
+                float *stage = reinterpret_cast<float *>(tile);
+                for (int pos = lane; pos < 2048; pos += 32) {
+                    const int a = pos - p.pad_left;
+                    float x = 0.0f;
+                    if (a >= 0 && a < p.win) {
+                        const long long s = reflect_index(tap0 + a, d.full_len);
+                        x = __ldg(&d.pcm[s - d.pcm_offset]) * sm.wpad[pos];
+                    }
+                    stage[pos] = x;
                 }
-                stage[pos] = x;
+                __syncwarp();
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) v[n1] = *reinterpret_cast<const float2 *>(stage + 64 * n1 + 2 * lane);
+                __syncwarp();
+            }
+            // ---- pass 1: DFT over n1, twiddle, transpose ----
+            dft32(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; k1++) {
+                float2 t = v[perm32(k1)];
+                if (k1) {  // same operation order as the packed kernel's cmul_s: the two kernels agree bit for bit
+                    const float2 w = sm.tw1[(k1 - 1) * 32 + lane];
+                    t = make_float2(fmaf(t.y, -w.y, t.x * w.x), fmaf(t.x, w.y, t.y * w.x));
+                }
+                tile[k1 * kRow + lane] = t;
             }
             __syncwarp();
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[n1] = *reinterpret_cast<const float2 *>(stage + 64 * n1 + 2 * lane);
+            for (int n2 = 0; n2 < 32; n2++) v[n2] = tile[lane * kRow + n2];
             __syncwarp();
-        }
-        // ---- pass 1: DFT over n1, twiddle, transpose ----
-        dft32(v);
+            // ---- pass 2: DFT over n2 -> Z[lane + 32 k2] in v[perm32(k2)] ----
+            dft32(v);
+            // ---- real split: 16 (k, 1024 - k) pairs per lane; |X| or dB ----
+            float *orow = d.out + f * p.n_bins;
+            float db_off = 0.0f;
+            for (int attempt = 0;; attempt++) {
+                float smax = 0.0f, fmx = -CUDART_INF_F, fnm = -CUDART_INF_F;  // this attempt's own max / -min
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) {
-            float2 t = v[perm32(k1)];
-            if (k1) {  // same operation order as the packed kernel's cmul_s: the two kernels agree bit for bit
-                const float2 w = sm.tw1[(k1 - 1) * 32 + lane];
-                t = make_float2(fmaf(t.y, -w.y, t.x * w.x), fmaf(t.x, w.y, t.y * w.x));
-            }
-            tile[k1 * kRow + lane] = t;
-        }
-        __syncwarp();
+                for (int j = 0; j < 16; j++) {
+                    const float2 own_a = v[perm32(31 - j)], own_b = v[perm32((32 - j) & 31)];
+                    const float2 zk = lane ? own_a : own_b;
+                    const float2 sup = v[perm32(j)];
+                    float2 zn;
+                    zn.x = __shfl_sync(0xffffffffu, sup.x, partner);
+                    zn.y = __shfl_sync(0xffffffffu, sup.y, partner);
+                    const float er = zk.x + zn.x, ei = zk.y - zn.y, dr = zk.x - zn.x, di = zk.y + zn.y;
+                    const float2 w = sm.tw2[j * 32 + lane];
+                    const float wr = fmaf(di, -w.y, dr * w.x), wi = fmaf(dr, w.y, di * w.x);
+                    const float ar = er + wi, ai = ei - wr, br = er - wi, bi = ei + wr;
+                    const float sa = fmaf(ar, ar, ai * ai), sb = fmaf(br, br, bi * bi);
+                    smax = fmaxf(smax, fmaxf(sa, sb));
+                    const int k_own = lane32 + 32 * (31 - j), k_par = 1024 - k_own;
+                    if (MEL) {
+                        mag[k_own] = sqrt_ftz(sa);
+                        mag[k_par] = sqrt_ftz(sb);
+                    } else {
+                        const float a = fmaf(kDbPerLog2Pow, lg2_ftz(sa), db_off), b = fmaf(kDbPerLog2Pow, lg2_ftz(sb), db_off);
+                        orow[k_own] = a;
+                        orow[k_par] = b;
+                        fmx = fmaxf(fmx, fmaxf(a, b));
+                        fnm = fmaxf(fnm, fmaxf(-a, -b));
+                    }
+                }
+                if (lane == 0) {  // k = 512 pairs with itself: X[512] = conj(2 Z'[512])
+                    const float2 z = v[perm32(16)];
+                    const float s5 = 4.0f * fmaf(z.x, z.x, z.y * z.y);
+                    smax = fmaxf(smax, s5);
+                    if (MEL) {
+                        mag[512] = sqrt_ftz(s5);
+                    } else {
+                        const float a = fmaf(kDbPerLog2Pow, lg2_ftz(s5), db_off);
+                        orow[512] = a;
+                        fmx = fmaxf(fmx, a);
+                        fnm = fmaxf(fnm, -a);
+                    }
+                }
+                smax = warp_max(smax);
+                const bool tiny = smax < kPowTiny && smax > 0.0f, huge = smax > kPowHuge;
+                if (attempt || !(tiny || huge)) {
+                    lmax = fmaxf(lmax, fmx);
+                    lnmin = fmaxf(lnmin, fnm);
+                    break;
+                }
+                const float sc = tiny ? kRescueUp : kRescueDown;
+                db_off = tiny ? -60.0f * kDbPerLog2Amp : 60.0f * kDbPerLog2Amp;
 #pragma unroll
-        for (int n2 = 0; n2 < 32; n2++) v[n2] = tile[lane * kRow + n2];
-        __syncwarp();
-        // ---- pass 2: DFT over n2 -> Z[lane + 32 k2] in v[perm32(k2)] ----
-        dft32(v);
-        // ---- real split: 16 (k, 1024 - k) pairs per lane; |X| or dB ----
-        float *orow = d.out + f * p.n_bins;
-        float db_off = 0.0f;
-        for (int attempt = 0;; attempt++) {
-            float smax = 0.0f, fmx = -CUDART_INF_F, fnm = -CUDART_INF_F;  // this attempt's own max / -min
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const float2 own_a = v[perm32(31 - j)], own_b = v[perm32((32 - j) & 31)];
-                const float2 zk = lane ? own_a : own_b;
-                const float2 sup = v[perm32(j)];
-                float2 zn;
-                zn.x = __shfl_sync(0xffffffffu, sup.x, partner);
-                zn.y = __shfl_sync(0xffffffffu, sup.y, partner);
-                const float er = zk.x + zn.x, ei = zk.y - zn.y, dr = zk.x - zn.x, di = zk.y + zn.y;
-                const float2 w = sm.tw2[j * 32 + lane];
-                const float wr = fmaf(di, -w.y, dr * w.x), wi = fmaf(dr, w.y, di * w.x);
-                const float ar = er + wi, ai = ei - wr, br = er - wi, bi = ei + wr;
-                const float sa = fmaf(ar, ar, ai * ai), sb = fmaf(br, br, bi * bi);
-                smax = fmaxf(smax, fmaxf(sa, sb));
-                const int k_own = lane32 + 32 * (31 - j), k_par = 1024 - k_own;
-                if (MEL) {
-                    mag[k_own] = sqrt_ftz(sa);
-                    mag[k_par] = sqrt_ftz(sb);
-                } else {
-                    const float a = fmaf(kDbPerLog2Pow, lg2_ftz(sa), db_off), b = fmaf(kDbPerLog2Pow, lg2_ftz(sb), db_off);
-                    orow[k_own] = a;
-                    orow[k_par] = b;
-                    fmx = fmaxf(fmx, fmaxf(a, b));
-                    fnm = fmaxf(fnm, fmaxf(-a, -b));
+                for (int i = 0; i < 32; i++) {
+                    v[i].x *= sc;
+                    v[i].y *= sc;
                 }
             }
-            if (lane == 0) {  // k = 512 pairs with itself: X[512] = conj(2 Z'[512])
-                const float2 z = v[perm32(16)];
-                const float s5 = 4.0f * fmaf(z.x, z.x, z.y * z.y);
-                smax = fmaxf(smax, s5);
-                if (MEL) {
-                    mag[512] = sqrt_ftz(s5);
-                } else {
-                    const float a = fmaf(kDbPerLog2Pow, lg2_ftz(s5), db_off);
-                    orow[512] = a;
-                    fmx = fmaxf(fmx, a);
-                    fnm = fmaxf(fnm, -a);
+            if (MEL) {
+                __syncwarp();
+                const MelView mv(sm.ms);
+                for (int g = 0; g < mv.n_groups; g++) {
+                    const float2 *wq = reinterpret_cast<const float2 *>(mv.base + mv.woff[g]) + lane;
+                    const float *mq = mag + mv.start[g * 32 + lane];
+                    const int steps2 = static_cast<int>(mv.T[g]) >> 1;
+                    float acc = 0.0f;
+#pragma unroll 2
+                    for (int t = 0; t < steps2; t++) {
+                        const float2 w = wq[32 * t];
+                        acc = fmaf(mq[2 * t], w.x, acc);
+                        acc = fmaf(mq[2 * t + 1], w.y, acc);
+                    }
+                    part[g * 32 + lane] = acc;
                 }
-            }
-            smax = warp_max(smax);
-            // a frame whose largest |X|^2 is far from 1 is redone once on an exactly rescaled spectrum
-            const bool tiny = smax < kPowTiny && smax > 0.0f, huge = smax > kPowHuge;
-            if (attempt || !(tiny || huge)) {
-                lmax = fmaxf(lmax, fmx);
-                lnmin = fmaxf(lnmin, fnm);
-                break;
-            }
-            const float sc = tiny ? kRescueUp : kRescueDown;
-            db_off = tiny ? -60.0f * kDbPerLog2Amp : 60.0f * kDbPerLog2Amp;
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                v[i].x *= sc;
-                v[i].y *= sc;
-            }
-        }
-        if (MEL) {
-            __syncwarp();
-            const uint32_t *T = sm.ms, *woff = sm.ms + p.ms_groups;
-            const int32_t *start = reinterpret_cast<const int32_t *>(sm.ms + 2 * p.ms_groups);
-            for (int g = 0; g < p.ms_groups; g++) {
-                const float *wq = reinterpret_cast<const float *>(sm.ms) + woff[g] + lane;
-                const float *mq = mag + start[g * 32 + lane];
-                const int steps = static_cast<int>(T[g]);
-                float acc = 0.0f;
-#pragma unroll 1
-                for (int t = 0; t < steps; t += 4) {
-                    acc = fmaf(wq[32 * t], mq[t], acc);
-                    acc = fmaf(wq[32 * t + 32], mq[t + 1], acc);
-                    acc = fmaf(wq[32 * t + 64], mq[t + 2], acc);
-                    acc = fmaf(wq[32 * t + 96], mq[t + 3], acc);
-                }
-                const int m = g * 32 + lane;
-                if (m < p.n_mel) {
+                __syncwarp();
+                for (int m = lane; m < mv.n_mel; m += 32) {
+                    const uint32_t p0 = mv.pptr[m], p1 = mv.pptr[m + 1];
+                    float acc = part[mv.pids[p0]];
+                    for (uint32_t i = p0 + 1; i < p1; i++) acc += part[mv.pids[i]];
+                    // exact zero stays -inf; db_off only shifts finite values
                     const float db = fmaf(kDbPerLog2Amp, lg2_ftz(acc), db_off);
                     orow[m] = db;
                     lmax = fmaxf(lmax, db);
                     lnmin = fmaxf(lnmin, -db);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
-    }
-    // ---- per-channel {max, -min}: warp shuffle -> shared -> one atomic pair per CTA ----
-    lmax = warp_max(lmax);
-    lnmin = warp_max(lnmin);
-    if (lane == 0) {
-        red_max[warp] = lmax;
-        red_nmin[warp] = lnmin;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        float a = lane < kWarps ? red_max[lane] : -CUDART_INF_F;
-        float b = lane < kWarps ? red_nmin[lane] : -CUDART_INF_F;
-        a = warp_max(a);
-        b = warp_max(b);
+        // ---- per-channel {max, -min}: warp shuffle -> shared -> one atomic pair per CTA ----
+        lmax = warp_max(lmax);
+        lnmin = warp_max(lnmin);
         if (lane == 0) {
-            atomic_max_float(&d.minmax[0], a);
-            atomic_max_float(&d.minmax[1], b);
+            red_max[warp] = lmax;
+            red_nmin[warp] = lnmin;
         }
-    }
-    __syncthreads();  // red_max / red_nmin are reused by the next item
+        __syncthreads();
+        if (warp == 0) {
+            float a = lane < kWarps ? red_max[lane] : -CUDART_INF_F;
+            float b = lane < kWarps ? red_nmin[lane] : -CUDART_INF_F;
+            a = warp_max(a);
+            b = warp_max(b);
+            if (lane == 0) {
+                atomic_max_float(&d.minmax[0], a);
+                atomic_max_float(&d.minmax[1], b);
+            }
+        }
+        __syncthreads();  // red_max / red_nmin are reused by the next item
     }
 }
 
 size_t fast_smem_bytes(const PlanDev &p) {
-    return sizeof(float) * 2048 + sizeof(float2) * (31 * 32 + 16 * 32) + sizeof(float2) * kWarps * kTileFloat2 +
-           sizeof(uint32_t) * static_cast<size_t>(p.n_mel ? p.ms_words : 0);
+    return sizeof(float) * 2048 + sizeof(float2) * (31 * 32 + 16 * 32) + sizeof(float) * kWarps * fast_tile_floats(p) +
+           sizeof(uint32_t) * static_cast<size_t>(p.n_mel ? p.mi_words : 0);
 }
 
 }  // namespace
 
 bool stft_fast_supported(const PlanDev &p) {
     if (p.n_fft != 2048 || !p.fast_wpad || !p.fast_tw) return false;
-    if (p.n_mel && (!p.ms_blob || p.ms_max_reach + 33 > 2 * kTileFloat2)) return false;
+    if (p.n_mel && (!p.mi_blob || p.mi_min_start < -(kMagBase - 1))) return false;
     return fast_smem_bytes(p) <= 112 * 1024;
 }
 

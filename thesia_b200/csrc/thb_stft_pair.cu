@@ -10,8 +10,7 @@
 //
 //   perform_stft (stft.rs:16-149), Complex::norm (spectrogram.rs:200), linspec.dot(mel_fb)
 //   (spectrogram.rs:207), dB_from_amp (decibel.rs:198-202), find_min_max (mod.rs:169-178).
-#include "thb_device.cuh"
-#include "thb_kernels.cuh"
+#include "thb_stft2048.cuh"
 
 #include <cstdlib>
 
@@ -19,10 +18,7 @@ namespace thb {
 
 namespace {
 
-constexpr int kTileFrames = 64;    // consecutive frames of one channel per CTA (32 pairs)
-constexpr int kRow = 33;           // float2 row stride of the transpose tile
-constexpr int kTileFloat2 = 1104;  // >= 32*33 for the transpose, >= 32 + 1025 + mel reach for the magnitudes
-constexpr int kMagBase = 32;       // the mel walk may start up to 31 bins before bin 0
+using namespace k2048;
 
 // ---- packed helpers: .x = frame A, .y = frame B ------------------------------------------------
 using f2 = float2;
@@ -46,21 +42,6 @@ __device__ __forceinline__ cx cmul_s(cx a, float c, float s) {
     r.im = pfma(a.re, bc(s), pmul(a.im, bc(c)));
     return r;
 }
-
-__device__ constexpr float kC32[32] = {
-    1.0f, 0.9807852506637573f, 0.9238795042037964f, 0.8314695954322815f, 0.7071067690849304f, 0.5555702447891235f,
-    0.3826834261417389f, 0.19509032368659973f, 0.0f, -0.19509032368659973f, -0.3826834261417389f, -0.5555702447891235f,
-    -0.7071067690849304f, -0.8314695954322815f, -0.9238795042037964f, -0.9807852506637573f, -1.0f,
-    -0.9807852506637573f, -0.9238795042037964f, -0.8314695954322815f, -0.7071067690849304f, -0.5555702447891235f,
-    -0.3826834261417389f, -0.19509032368659973f, 0.0f, 0.19509032368659973f, 0.3826834261417389f, 0.5555702447891235f,
-    0.7071067690849304f, 0.8314695954322815f, 0.9238795042037964f, 0.9807852506637573f};
-__device__ constexpr float kS32[32] = {
-    0.0f, 0.19509032368659973f, 0.3826834261417389f, 0.5555702447891235f, 0.7071067690849304f, 0.8314695954322815f,
-    0.9238795042037964f, 0.9807852506637573f, 1.0f, 0.9807852506637573f, 0.9238795042037964f, 0.8314695954322815f,
-    0.7071067690849304f, 0.5555702447891235f, 0.3826834261417389f, 0.19509032368659973f, 0.0f, -0.19509032368659973f,
-    -0.3826834261417389f, -0.5555702447891235f, -0.7071067690849304f, -0.8314695954322815f, -0.9238795042037964f,
-    -0.9807852506637573f, -1.0f, -0.9807852506637573f, -0.9238795042037964f, -0.8314695954322815f,
-    -0.7071067690849304f, -0.5555702447891235f, -0.3826834261417389f, -0.19509032368659973f};
 
 // a * W_32^J,  W_32 = exp(-2 pi i / 32) = cos - i sin
 template <int J>
@@ -104,8 +85,6 @@ __device__ __forceinline__ void dft8p(cx &v0, cx &v1, cx &v2, cx &v3, cx &v4, cx
 }
 
 // In-register 32-point forward DFT of both frames.  Output X[k] is left in v[perm32(k)].
-__device__ __forceinline__ constexpr int perm32(int k) { return 8 * (k & 3) + (k >> 2); }
-
 template <int B>
 __device__ __forceinline__ void dft32_col(cx (&v)[32]) {
     dft4p(v[B], v[B + 8], v[B + 16], v[B + 24]);
@@ -124,216 +103,198 @@ __device__ __forceinline__ void dft32p(cx (&v)[32]) {
               v[8 * q + 7]);
 }
 
-__device__ __forceinline__ float lg2_ftz(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sqrt_ftz(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-constexpr float kDbPerLog2Pow = 3.01029995663981195f;   // 10 log10(2)
-constexpr float kDbPerLog2Amp = 6.02059991327962390f;   // 20 log10(2)
-// frames whose largest |X|^2 leaves [2^-80, 2^100] are redone by the scalar kernel
-constexpr float kPowTiny = 8.2718061e-25f;
-constexpr float kPowHuge = 1.2676506e+30f;
-
 struct PairSmem {
     float *wpad;         // [2048]   0.5 * window, zero outside the taps
     float2 *tw1;         // [31][32] W_1024^(lane * k1), k1 = 1..31
     float2 *tw2;         // [16][32] W_2048^(k_own(j, lane))
-    float2 *tiles;       // [NW][kTileFloat2]
-    const uint32_t *ms;  // mel schedule blob (pair layout)
+    float2 *tiles;       // [NW][tile_f2]
+    const uint32_t *ms;  // MelItems blob
 };
 
 template <int NW>
-__device__ __forceinline__ PairSmem carve(unsigned char *raw) {
+__device__ __forceinline__ PairSmem carve(unsigned char *raw, int tile_f2) {
     PairSmem s;
     s.wpad = reinterpret_cast<float *>(raw);
     s.tw1 = reinterpret_cast<float2 *>(s.wpad + 2048);
     s.tw2 = s.tw1 + 31 * 32;
     s.tiles = s.tw2 + 16 * 32;
-    s.ms = reinterpret_cast<const uint32_t *>(s.tiles + NW * kTileFloat2);
+    s.ms = reinterpret_cast<const uint32_t *>(s.tiles + NW * tile_f2);
     return s;
 }
 
-// NW = warps (frame pairs in flight) per CTA; one CTA per SM, so NW also sets the register budget
+// NW = warps per CTA; one persistent CTA per SM, so NW also sets the register budget (65536 / (32 NW)).
+// Work item = (descriptor, tile of 8 NW consecutive frames = 4 frame pairs per warp); CTAs take items round
+// robin, warps never meet at a block barrier after the tables are loaded.
+//
+// Contract (the launcher guarantees it, thb_api.cu): every frame of every descriptor is interior (no reflect
+// padding, the whole n_fft span inside the slice), 8-byte aligned, and n_frames is even.  Edge frames, odd
+// leftovers and unaligned channels go through the scalar kernel.
 template <bool MEL, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
-                                                                        RescueList rescue) {
+                                                                        long long n_items, RescueList rescue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float red_max[NW], red_nmin[NW];
-    __shared__ int tile_flag;
-    if (threadIdx.x == 0) tile_flag = 0;
+    constexpr int kTile = 8 * NW;
 
-    const TrackDesc d = tracks[blockIdx.y];
-    const long long f_begin = static_cast<long long>(blockIdx.x) * kTileFrames;
-    if (f_begin >= d.n_frames) return;
-    const long long f_end = min(f_begin + kTileFrames, d.n_frames);
-
-    const PairSmem sm = carve<NW>(smem_raw);
+    const int tile_f2 = tile_elems(p);
+    const PairSmem sm = carve<NW>(smem_raw, tile_f2);
     for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.wpad)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_wpad) + i);
     for (int i = threadIdx.x; i < (31 * 32 + 16 * 32) / 2; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.tw1)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_tw) + i);
-    for (int i = threadIdx.x; i < NW * kTileFloat2 / 2; i += blockDim.x)
+    for (int i = threadIdx.x; i < NW * tile_f2 / 2; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MEL) {
-        for (int i = threadIdx.x; i < p.mp_words / 4; i += blockDim.x)
-            reinterpret_cast<uint4 *>(const_cast<uint32_t *>(sm.ms))[i] = __ldg(reinterpret_cast<const uint4 *>(p.mp_blob) + i);
+        for (int i = threadIdx.x; i < p.mi_words / 4; i += blockDim.x)
+            reinterpret_cast<uint4 *>(const_cast<uint32_t *>(sm.ms))[i] = __ldg(reinterpret_cast<const uint4 *>(p.mi_blob) + i);
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *tile = sm.tiles + warp * kTileFloat2;
+    float2 *tile = sm.tiles + warp * tile_f2;
     float2 *mag = tile + kMagBase;  // mag[k] = (|X_A[k]|, |X_B[k]|)
+    float2 *part = tile + part_base(p);
     const int half = p.win / 2;
     const int partner = (32 - lane) & 31;
     const int lane32 = lane ? lane : 32;
-    float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
+    const long long tiles_per_track = rescue.tiles_per_track;
 
-    // Contract (the launcher guarantees it, thb_api.cu): every frame of this descriptor is interior (no reflect
-    // padding, the whole n_fft span inside the slice), 8-byte aligned, and n_frames is even.  Edge frames and odd
-    // leftovers go through the scalar kernel.
-    for (long long fa = f_begin + 2 * warp; fa < f_end; fa += 2 * NW) {
-        const long long fb = fa + 1;
-        cx v[32];
-        // ---- load + window: v[n1] = z[32 n1 + lane] of both frames ----
-        const long long first_a = (d.frame_begin + fa) * p.hop - half - p.pad_left;  // file index of FFT position 0
-        const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
-        const float *src_b = src_a + p.hop;
-        // eight columns at a time: 16 global loads in flight per lane without holding all 64 raw pairs
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const long long track = item / tiles_per_track, tile_idx = item - track * tiles_per_track;
+        const TrackDesc d = tracks[track];
+        const long long f_begin = tile_idx * kTile;
+        if (f_begin >= d.n_frames) continue;
+        const long long f_end = min(f_begin + kTile, d.n_frames);
+        float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
+        bool flagged = false;
+
+        for (long long fa = f_begin + 2 * warp; fa < f_end; fa += 2 * NW) {
+            const long long fb = fa + 1;
+            cx v[32];
+            // ---- load + window: v[n1] = z[32 n1 + lane] of both frames ----
+            const long long first_a = (d.frame_begin + fa) * p.hop - half - p.pad_left;  // file index of FFT position 0
+            const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
+            const float *src_b = src_a + p.hop;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float2 xa[8], xb[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                xa[i] = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * (8 * c + i)));
-                xb[i] = __ldg(reinterpret_cast<const float2 *>(src_b + 64 * (8 * c + i)));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int n1 = 8 * c + i;
+            for (int n1 = 0; n1 < 32; n1++) {
+                const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1));
+                const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 64 * n1));
                 const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
-                v[n1].re = make_float2(xa[i].x * w.x, xb[i].x * w.x);
-                v[n1].im = make_float2(xa[i].y * w.y, xb[i].y * w.y);
+                v[n1].re = make_float2(xa.x * w.x, xb.x * w.x);
+                v[n1].im = make_float2(xa.y * w.y, xb.y * w.y);
             }
-            __syncwarp();
-        }
-        // ---- pass 1: DFT over n1, twiddle, transpose (real plane, then imaginary plane) ----
-        dft32p(v);
+            // ---- pass 1: DFT over n1, twiddle, transpose (real plane, then imaginary plane) ----
+            dft32p(v);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) {
-            if (k1) {
-                const float2 w = sm.tw1[(k1 - 1) * 32 + lane];
-                v[perm32(k1)] = cmul_s(v[perm32(k1)], w.x, w.y);
-            }
-            tile[k1 * kRow + lane] = v[perm32(k1)].re;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; n2++) v[n2].re = tile[lane * kRow + n2];
-        __syncwarp();
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) tile[k1 * kRow + lane] = v[perm32(k1)].im;
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; n2++) v[n2].im = tile[lane * kRow + n2];
-        __syncwarp();
-        // ---- pass 2: DFT over n2 -> Z[lane + 32 k2] in v[perm32(k2)] ----
-        dft32p(v);
-        // ---- real split: 16 (k, 1024 - k) pairs per lane; |X| or dB ----
-        float *orow_a = d.out + fa * p.n_bins, *orow_b = d.out + fb * p.n_bins;
-        f2 smax = make_float2(0.0f, 0.0f);
-        f2 fmx = make_float2(-CUDART_INF_F, -CUDART_INF_F), fnm = fmx;  // this pair's own max / -min (linear)
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const cx own_a = v[perm32(31 - j)], own_b = v[perm32((32 - j) & 31)];
-            cx zk, zn;
-            zk.re.x = lane ? own_a.re.x : own_b.re.x;
-            zk.re.y = lane ? own_a.re.y : own_b.re.y;
-            zk.im.x = lane ? own_a.im.x : own_b.im.x;
-            zk.im.y = lane ? own_a.im.y : own_b.im.y;
-            const cx sup = v[perm32(j)];
-            zn.re.x = __shfl_sync(0xffffffffu, sup.re.x, partner);
-            zn.re.y = __shfl_sync(0xffffffffu, sup.re.y, partner);
-            zn.im.x = __shfl_sync(0xffffffffu, sup.im.x, partner);
-            zn.im.y = __shfl_sync(0xffffffffu, sup.im.y, partner);
-            const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
-            const float2 w = sm.tw2[j * 32 + lane];
-            const f2 wr = pfma(di, bc(-w.y), pmul(dr, bc(w.x))), wi = pfma(dr, bc(w.y), pmul(di, bc(w.x)));
-            const f2 ar = padd(er, wi), ai = psub(ei, wr), br = psub(er, wi), bi = padd(ei, wr);
-            const f2 sa = pfma(ar, ar, pmul(ai, ai)), sb = pfma(br, br, pmul(bi, bi));
-            smax.x = fmaxf(smax.x, fmaxf(sa.x, sb.x));
-            smax.y = fmaxf(smax.y, fmaxf(sa.y, sb.y));
-            const int k_own = lane32 + 32 * (31 - j), k_par = 1024 - k_own;
-            if (MEL) {
-                mag[k_own] = make_float2(sqrt_ftz(sa.x), sqrt_ftz(sa.y));
-                mag[k_par] = make_float2(sqrt_ftz(sb.x), sqrt_ftz(sb.y));
-            } else {
-                const f2 a = pmul(make_float2(lg2_ftz(sa.x), lg2_ftz(sa.y)), bc(kDbPerLog2Pow));
-                const f2 b = pmul(make_float2(lg2_ftz(sb.x), lg2_ftz(sb.y)), bc(kDbPerLog2Pow));
-                orow_a[k_own] = a.x;
-                orow_a[k_par] = b.x;
-                orow_b[k_own] = a.y;
-                orow_b[k_par] = b.y;
-                fmx.x = fmaxf(fmx.x, fmaxf(a.x, b.x));
-                fmx.y = fmaxf(fmx.y, fmaxf(a.y, b.y));
-                fnm.x = fmaxf(fnm.x, fmaxf(-a.x, -b.x));
-                fnm.y = fmaxf(fnm.y, fmaxf(-a.y, -b.y));
-            }
-        }
-        if (lane == 0) {  // k = 512 pairs with itself: X[512] = conj(2 Z'[512])
-            const cx z = v[perm32(16)];
-            const f2 s5 = pmul(pfma(z.re, z.re, pmul(z.im, z.im)), bc(4.0f));
-            smax.x = fmaxf(smax.x, s5.x);
-            smax.y = fmaxf(smax.y, s5.y);
-            if (MEL) {
-                mag[512] = make_float2(sqrt_ftz(s5.x), sqrt_ftz(s5.y));
-            } else {
-                const f2 a = pmul(make_float2(lg2_ftz(s5.x), lg2_ftz(s5.y)), bc(kDbPerLog2Pow));
-                orow_a[512] = a.x;
-                orow_b[512] = a.y;
-                fmx.x = fmaxf(fmx.x, a.x);
-                fmx.y = fmaxf(fmx.y, a.y);
-                fnm.x = fmaxf(fnm.x, -a.x);
-                fnm.y = fmaxf(fnm.y, -a.y);
-            }
-        }
-        // A frame whose largest |X|^2 is outside [2^-80, 2^100] (f32 audio hundreds of dB from full scale) loses
-        // bins to under/overflow of the square: its tile is put on the rescue list and redone by the scalar
-        // kernel, which rescales such frames exactly (thb_stft_fast.cu); nothing of it enters the min/max here.
-        const float mx_a = warp_max(smax.x), mx_b = warp_max(smax.y);
-        const bool pair_ok = !((mx_a < kPowTiny && mx_a > 0.0f) || mx_a > kPowHuge || (mx_b < kPowTiny && mx_b > 0.0f) ||
-                               mx_b > kPowHuge);
-        if (!pair_ok && lane == 0) tile_flag = 1;
-        if (!MEL && pair_ok) {
-            lmax = fmaxf(lmax, fmaxf(fmx.x, fmx.y));
-            lnmin = fmaxf(lnmin, fmaxf(fnm.x, fnm.y));
-        }
-        if (MEL) {
-            __syncwarp();
-            const uint32_t *T = sm.ms, *woff = sm.ms + p.mp_groups;
-            const int32_t *start = reinterpret_cast<const int32_t *>(sm.ms + 2 * p.mp_groups);
-            for (int g = 0; g < p.mp_groups; g++) {
-                // weights: float2 (steps t, t+1) per lane, [t/2][lane]; magnitudes: two bins x two frames
-                const float2 *wq = reinterpret_cast<const float2 *>(sm.ms + woff[g]) + lane;
-                const float4 *mq = reinterpret_cast<const float4 *>(mag + start[g * 32 + lane]);
-                const int steps2 = static_cast<int>(T[g]) >> 1;
-                f2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 2
-                for (int t = 0; t < steps2; t++) {
-                    const float2 w = wq[32 * t];
-                    const float4 m = mq[t];
-                    acc = pfma(make_float2(m.x, m.y), bc(w.x), acc);
-                    acc = pfma(make_float2(m.z, m.w), bc(w.y), acc);
+            for (int k1 = 0; k1 < 32; k1++) {
+                if (k1) {
+                    const float2 w = sm.tw1[(k1 - 1) * 32 + lane];
+                    v[perm32(k1)] = cmul_s(v[perm32(k1)], w.x, w.y);
                 }
-                const int m = g * 32 + lane;
-                if (m < p.n_mel) {
+                tile[k1 * kRow + lane] = v[perm32(k1)].re;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++) v[n2].re = tile[lane * kRow + n2];
+            __syncwarp();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; k1++) tile[k1 * kRow + lane] = v[perm32(k1)].im;
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++) v[n2].im = tile[lane * kRow + n2];
+            __syncwarp();
+            // ---- pass 2: DFT over n2 -> Z[lane + 32 k2] in v[perm32(k2)] ----
+            dft32p(v);
+            // ---- real split: 16 (k, 1024 - k) pairs per lane; |X| or dB ----
+            float *orow_a = d.out + fa * p.n_bins, *orow_b = d.out + fb * p.n_bins;
+            f2 smax = make_float2(0.0f, 0.0f);
+            f2 fmx = make_float2(-CUDART_INF_F, -CUDART_INF_F), fnm = fmx;  // this pair's own max / -min (linear)
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const cx own_a = v[perm32(31 - j)], own_b = v[perm32((32 - j) & 31)];
+                cx zk, zn;
+                zk.re.x = lane ? own_a.re.x : own_b.re.x;
+                zk.re.y = lane ? own_a.re.y : own_b.re.y;
+                zk.im.x = lane ? own_a.im.x : own_b.im.x;
+                zk.im.y = lane ? own_a.im.y : own_b.im.y;
+                const cx sup = v[perm32(j)];
+                zn.re.x = __shfl_sync(0xffffffffu, sup.re.x, partner);
+                zn.re.y = __shfl_sync(0xffffffffu, sup.re.y, partner);
+                zn.im.x = __shfl_sync(0xffffffffu, sup.im.x, partner);
+                zn.im.y = __shfl_sync(0xffffffffu, sup.im.y, partner);
+                const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
+                const float2 w = sm.tw2[j * 32 + lane];
+                const f2 wr = pfma(di, bc(-w.y), pmul(dr, bc(w.x))), wi = pfma(dr, bc(w.y), pmul(di, bc(w.x)));
+                const f2 ar = padd(er, wi), ai = psub(ei, wr), br = psub(er, wi), bi = padd(ei, wr);
+                const f2 sa = pfma(ar, ar, pmul(ai, ai)), sb = pfma(br, br, pmul(bi, bi));
+                smax.x = fmaxf(smax.x, fmaxf(sa.x, sb.x));
+                smax.y = fmaxf(smax.y, fmaxf(sa.y, sb.y));
+                const int k_own = lane32 + 32 * (31 - j), k_par = 1024 - k_own;
+                if (MEL) {
+                    mag[k_own] = make_float2(sqrt_ftz(sa.x), sqrt_ftz(sa.y));
+                    mag[k_par] = make_float2(sqrt_ftz(sb.x), sqrt_ftz(sb.y));
+                } else {
+                    const f2 a = pmul(make_float2(lg2_ftz(sa.x), lg2_ftz(sa.y)), bc(kDbPerLog2Pow));
+                    const f2 b = pmul(make_float2(lg2_ftz(sb.x), lg2_ftz(sb.y)), bc(kDbPerLog2Pow));
+                    orow_a[k_own] = a.x;
+                    orow_a[k_par] = b.x;
+                    orow_b[k_own] = a.y;
+                    orow_b[k_par] = b.y;
+                    fmx.x = fmaxf(fmx.x, fmaxf(a.x, b.x));
+                    fmx.y = fmaxf(fmx.y, fmaxf(a.y, b.y));
+                    fnm.x = fmaxf(fnm.x, fmaxf(-a.x, -b.x));
+                    fnm.y = fmaxf(fnm.y, fmaxf(-a.y, -b.y));
+                }
+            }
+            if (lane == 0) {  // k = 512 pairs with itself: X[512] = conj(2 Z'[512])
+                const cx z = v[perm32(16)];
+                const f2 s5 = pmul(pfma(z.re, z.re, pmul(z.im, z.im)), bc(4.0f));
+                smax.x = fmaxf(smax.x, s5.x);
+                smax.y = fmaxf(smax.y, s5.y);
+                if (MEL) {
+                    mag[512] = make_float2(sqrt_ftz(s5.x), sqrt_ftz(s5.y));
+                } else {
+                    const f2 a = pmul(make_float2(lg2_ftz(s5.x), lg2_ftz(s5.y)), bc(kDbPerLog2Pow));
+                    orow_a[512] = a.x;
+                    orow_b[512] = a.y;
+                    fmx.x = fmaxf(fmx.x, a.x);
+                    fmx.y = fmaxf(fmx.y, a.y);
+                    fnm.x = fmaxf(fnm.x, -a.x);
+                    fnm.y = fmaxf(fnm.y, -a.y);
+                }
+            }
+            // frames outside the exact range of the f32 square: the tile goes on the rescue list, and nothing of
+            // this pair enters the min/max here (the scalar kernel redoes the whole tile, bit-identically for
+            // the frames that were fine)
+            const float mx_a = warp_max(smax.x), mx_b = warp_max(smax.y);
+            const bool pair_ok = !((mx_a < kPowTiny && mx_a > 0.0f) || mx_a > kPowHuge || (mx_b < kPowTiny && mx_b > 0.0f) ||
+                                   mx_b > kPowHuge);
+            flagged |= !pair_ok;
+            if (!MEL && pair_ok) {
+                lmax = fmaxf(lmax, fmaxf(fmx.x, fmx.y));
+                lnmin = fmaxf(lnmin, fmaxf(fnm.x, fnm.y));
+            }
+            if (MEL) {
+                __syncwarp();
+                const MelView mv(sm.ms);
+                for (int g = 0; g < mv.n_groups; g++) {
+                    const float2 *wq = reinterpret_cast<const float2 *>(mv.base + mv.woff[g]) + lane;
+                    const float2 *mq = mag + mv.start[g * 32 + lane];
+                    const int steps2 = static_cast<int>(mv.T[g]) >> 1;
+                    f2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+                    for (int t = 0; t < steps2; t++) {
+                        const float2 w = wq[32 * t];
+                        acc = pfma(mq[2 * t], bc(w.x), acc);
+                        acc = pfma(mq[2 * t + 1], bc(w.y), acc);
+                    }
+                    part[g * 32 + lane] = acc;
+                }
+                __syncwarp();
+                for (int m = lane; m < mv.n_mel; m += 32) {
+                    const uint32_t p0 = mv.pptr[m], p1 = mv.pptr[m + 1];
+                    f2 acc = part[mv.pids[p0]];
+                    for (uint32_t i = p0 + 1; i < p1; i++) acc = padd(acc, part[mv.pids[i]]);
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
                     orow_b[m] = db.y;
@@ -342,38 +303,28 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                         lnmin = fmaxf(lnmin, fmaxf(-db.x, -db.y));
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
-    }
-    // ---- per-channel {max, -min}: warp shuffle -> shared -> one atomic pair per CTA ----
-    lmax = warp_max(lmax);
-    lnmin = warp_max(lnmin);
-    if (lane == 0) {
-        red_max[warp] = lmax;
-        red_nmin[warp] = lnmin;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        float a = lane < NW ? red_max[lane] : -CUDART_INF_F;
-        float b = lane < NW ? red_nmin[lane] : -CUDART_INF_F;
-        a = warp_max(a);
-        b = warp_max(b);
+        // ---- per-channel {max, -min}: one atomic pair per warp and work item ----
+        lmax = warp_max(lmax);
+        lnmin = warp_max(lnmin);
         if (lane == 0) {
-            if (!tile_flag) {  // a rescued tile contributes through the scalar kernel only
-                atomic_max_float(&d.minmax[0], a);
-                atomic_max_float(&d.minmax[1], b);
-            } else {
+            if (lmax > -CUDART_INF_F || lnmin > -CUDART_INF_F) {
+                atomic_max_float(&d.minmax[0], lmax);
+                atomic_max_float(&d.minmax[1], lnmin);
+            }
+            if (flagged && atomicExch(&rescue.flags[item], 1u) == 0u) {
                 const unsigned slot = atomicAdd(rescue.count, 1u);
-                if (slot < rescue.capacity) rescue.items[slot] = make_uint2(blockIdx.y + rescue.track_base, blockIdx.x);
+                if (slot < rescue.capacity) rescue.items[slot] = make_uint2(static_cast<unsigned>(track), static_cast<unsigned>(tile_idx));
             }
         }
     }
 }
 
 size_t pair_smem_bytes(const PlanDev &p, int nw) {
-    return sizeof(float) * 2048 + sizeof(float2) * (31 * 32 + 16 * 32) + sizeof(float2) * nw * kTileFloat2 +
-           sizeof(uint32_t) * static_cast<size_t>(p.n_mel ? p.mp_words : 0);
+    return sizeof(float) * 2048 + sizeof(float2) * (31 * 32 + 16 * 32) + sizeof(float2) * nw * tile_elems(p) +
+           sizeof(uint32_t) * static_cast<size_t>(p.n_mel ? p.mi_words : 0);
 }
 
 int pair_warps() {
@@ -384,45 +335,41 @@ int pair_warps() {
 }
 
 template <bool MEL, int NW>
-cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
-                      RescueList rescue, cudaStream_t st) {
+cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
+                      cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
     auto kern = stft2048_pair_kernel<MEL, NW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const long long tiles = (max_frames + kTileFrames - 1) / kTileFrames;
-    for (int t0 = 0; t0 < n_tracks; t0 += 65535) {
-        const int nt = min(65535, n_tracks - t0);
-        dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(nt));
-        RescueList r = rescue;
-        r.track_base = static_cast<unsigned>(t0);
-        kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks + t0, r);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
+    const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
+    kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks, n_items, rescue);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
+int stft_pair_tile_frames() { return 8 * pair_warps(); }
+
 bool stft_pair_supported(const PlanDev &p) {
     if (p.n_fft != 2048 || !p.fast_wpad || !p.fast_tw) return false;
-    if (p.n_mel && (!p.mp_blob || kMagBase + p.mp_max_reach + 2 > kTileFloat2)) return false;
-    return pair_smem_bytes(p, pair_warps()) <= 200 * 1024;
+    if (p.n_mel && (!p.mi_blob || p.mi_min_start < -(kMagBase - 1))) return false;
+    return pair_smem_bytes(p, pair_warps()) <= 220 * 1024;
 }
 
-cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
-                             RescueList rescue, cudaStream_t st) {
-    if (n_tracks <= 0 || max_frames <= 0) return cudaSuccess;
+// rescue.tile_frames must be stft_pair_tile_frames() and rescue.tiles_per_track = ceil(max n_frames / tile_frames)
+cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
+                             int sm_count, cudaStream_t st) {
+    if (n_tracks <= 0 || rescue.tiles_per_track == 0) return cudaSuccess;
     const int nw = pair_warps();
     if (plan.n_mel) {
-        if (nw == 8) return launch_nw<true, 8>(plan, d_tracks, n_tracks, max_frames, rescue, st);
-        if (nw == 10) return launch_nw<true, 10>(plan, d_tracks, n_tracks, max_frames, rescue, st);
-        return launch_nw<true, 12>(plan, d_tracks, n_tracks, max_frames, rescue, st);
+        if (nw == 8) return launch_nw<true, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        if (nw == 10) return launch_nw<true, 10>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<true, 12>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
-    if (nw == 8) return launch_nw<false, 8>(plan, d_tracks, n_tracks, max_frames, rescue, st);
-    if (nw == 10) return launch_nw<false, 10>(plan, d_tracks, n_tracks, max_frames, rescue, st);
-    return launch_nw<false, 12>(plan, d_tracks, n_tracks, max_frames, rescue, st);
+    if (nw == 8) return launch_nw<false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    if (nw == 10) return launch_nw<false, 10>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    return launch_nw<false, 12>(plan, d_tracks, n_tracks, rescue, sm_count, st);
 }
 
 }  // namespace thb

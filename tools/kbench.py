@@ -60,7 +60,7 @@ def main():
         ctx.synchronize()
         ms, launches = ctx.profile_get(kname)
         ctx.profile_enable(False)
-        ms /= max(launches, 1)
+        ms /= a.reps  # the scope covers every launch of one spec_batch call
         out = ctx.spec_read(0, 0)
         if ref is None:
             ref = out
