@@ -250,7 +250,8 @@ def run_b200(args) -> None:
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count()
-    k_ms, k_launches = ctx.profile_get("stft_mel_db")
+    k_ms, k_launches = ctx.profile_get("stft_mel_db")          # the frame-pair STFT kernel alone
+    edge_ms, edge_launches = ctx.profile_get("stft_mel_db_edges")  # scalar kernel: file edges + rescue list
     img_ms, img_launches = ctx.profile_get("spec_to_img")
     red_ms, _ = ctx.profile_get("minmax_reduce")
     ctx.profile_enable(False)
@@ -282,6 +283,8 @@ def run_b200(args) -> None:
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
         "achieved_fp32_tflops": alg_flops / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0,
         "share_of_step": (k_ms / ms_total) if ms_total > 0 else None,
+        "launches_per_step": k_launches / max(args.steps, 1),
+        "edge_kernels_ms_per_step": edge_ms / max(args.steps, 1),
         "spec_to_img_avg_ms": img_ms / max(img_launches, 1),
         "spec_to_img_gbs": (n_ch_total * (4 * T * N_MEL + 2 * T * N_MEL)) / (img_ms / max(img_launches, 1) * 1e-3) / 1e9
         if img_ms > 0 else None,

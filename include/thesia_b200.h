@@ -194,8 +194,9 @@ int thb_comm_destroy(thb_ctx *ctx);
 
 /* ---- measurement support --------------------------------------------------------------------
  * Per-kernel CUDA-event timing on the ctx stream and a launch counter (bench.py's roofline /
- * gpu_launches).  Kernel names: "stft_mel_db", "stft_lin_db", "minmax_reduce", "spec_to_img",
- * "envelope". */
+ * gpu_launches).  Kernel names: "stft_mel_db", "stft_lin_db" (the main STFT kernel of a batch),
+ * "stft_mel_db_edges", "stft_lin_db_edges" (file-edge frames and rescued tiles, when the main kernel
+ * leaves them to the scalar one), "minmax_reduce", "minmax_array", "spec_to_img", "envelope". */
 int thb_profile_enable(thb_ctx *ctx, int on);
 int thb_profile_reset(thb_ctx *ctx);
 int thb_profile_get(thb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *launches);

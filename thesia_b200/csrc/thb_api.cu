@@ -820,18 +820,27 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         const int chunks = (l.count + 65534) / 65535;
         cudaError_t e = cudaSuccess;
         if (l.n_pair || l.n_edge) {
-            ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", (l.n_pair ? 2 : 0) + (l.n_edge ? 1 : 0));
+            const char *kname = pd.n_mel ? "stft_mel_db" : "stft_lin_db";
+            const char *ename = pd.n_mel ? "stft_mel_db_edges" : "stft_lin_db_edges";
             if (l.n_pair) {
                 const unsigned tf = static_cast<unsigned>(thb::stft_pair_tile_frames());
                 const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
                                          static_cast<unsigned>(ctx->rescue_cap), tf,
                                          static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf)};
                 CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
-                e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, ctx->sm_count, ctx->stream);
-                if (e == cudaSuccess) e = thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
+                {
+                    ProfScope ps(ctx, kname, 1);  // the frame-pair kernel alone: this is the roofline kernel
+                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, ctx->sm_count, ctx->stream);
+                }
+                if (e == cudaSuccess) {
+                    ProfScope ps(ctx, ename, 1);
+                    e = thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
+                }
             }
-            if (e == cudaSuccess && l.n_edge)
+            if (e == cudaSuccess && l.n_edge) {
+                ProfScope ps(ctx, ename, (l.n_edge + 65534) / 65535);
                 e = thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream);
+            }
         } else {
             ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", chunks);
             if (want_fast && thb::stft_fast_supported(pd))

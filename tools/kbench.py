@@ -59,6 +59,7 @@ def main():
             ctx.spec_batch(tracks, setting)
         ctx.synchronize()
         ms, launches = ctx.profile_get(kname)
+        ms += ctx.profile_get(kname + "_edges")[0]
         ctx.profile_enable(False)
         ms /= a.reps  # the scope covers every launch of one spec_batch call
         out = ctx.spec_read(0, 0)
