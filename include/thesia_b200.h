@@ -41,7 +41,8 @@ typedef enum thb_status {
     THB_ERR_NOMEM = -4,
     THB_ERR_NOT_FOUND = -5,    /* unknown (id, ch) */
     THB_ERR_NCCL = -6,
-    THB_ERR_SMALL_BUFFER = -7  /* caller buffer too small; *written / dims tell the need */
+    THB_ERR_SMALL_BUFFER = -7, /* caller buffer too small; *written / dims tell the need */
+    THB_ERR_INTERNAL = -8      /* a self-check of the library failed (a bug) */
 } thb_status;
 
 typedef struct thb_ctx thb_ctx;
@@ -118,6 +119,11 @@ int thb_hann_window(uint64_t win, uint64_t n_fft, float *out);
  * out is (n_fft/2+1, n_mel) row-major; n_mel == 0 -> default rule; *n_mel_out gets the count.
  * out may be NULL to query n_mel only. */
 int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t *n_mel_out);
+/* Diagnostic: replays the warp schedule the n_fft == 2048 kernels follow for the sparse mel product (the same
+ * contraction as spectrogram.rs:207, zeros skipped) on the host and writes the (n_fft/2+1, n_mel) matrix it
+ * amounts to -- it must equal thb_mel_fb's.  stats[0..3] = {schedule valid, groups, steps per frame, shared-memory
+ * wavefronts lost to bank conflicts per frame pair}.  Returns THB_ERR_UNSUPPORTED when there is no schedule. */
+int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t stats[4]);
 /* FreqScale::hz_range_to_idx (src-common/src/lib.rs:144-159) */
 int thb_hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uint64_t n_bins,
                         uint64_t *i0, uint64_t *i1);

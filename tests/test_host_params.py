@@ -109,3 +109,20 @@ def test_synth_twin_is_deterministic_and_pcm_like():
     c0 = synth_pcm(4800, 48000, 5, 0, 0)
     assert np.all(c1[:7] == 0) and np.abs(c1[7:] - 0.8 * c0[:-7]).max() < 2 / 32768
     assert np.abs(synth_pcm(4800, 48000, 2, 0, LOUD)).max() > 1.0
+
+
+@pytest.mark.parametrize("sr,n_mel", [(48000, 128), (48000, 0), (44100, 128), (44100, 0), (48000, 8), (48000, 40),
+                                      (16000, 64), (96000, 256), (48000, 1025), (8000, 0), (24000, 80)])
+def test_mel_warp_schedule_is_the_filterbank(sr, n_mel):
+    """The bin-major warp schedule of the n_fft 2048 kernels (MelItems, thb_host.cpp) applies every non-zero
+    weight of calc_mel_fb exactly once, to the right band, with the reference's f32 value."""
+    fb = thb.calc_mel_fb(sr, 2048, n_mel) if n_mel else thb.calc_mel_fb_default(sr, 2048)
+    out = np.zeros_like(fb)
+    stats = (C.c_uint32 * 4)()
+    rc = _lib.lib().thb_mel_schedule_replay(sr, 2048, n_mel, out.ctypes.data_as(C.POINTER(C.c_float)), stats)
+    assert rc == 0 and stats[0] == 1
+    assert np.array_equal(out, fb)
+    # every bin is walked once: steps per frame stay within 2x of the 1025 / 32 lower bound
+    assert stats[2] <= (64 if fb.shape[1] <= 512 else 80)
+    if n_mel in (0, 128):
+        assert stats[3] <= 8  # (almost) bank-conflict free for the headline configurations

@@ -64,6 +64,7 @@ SIGNATURES = {
     "thb_n_bins": (_i, [_P(Setting), _u32, _P(_u32)]),
     "thb_hann_window": (_i, [_u64, _u64, _P(_f32)]),
     "thb_mel_fb": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
+    "thb_mel_schedule_replay": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
     "thb_hz_range_to_idx": (_i, [_u32, _f32, _f32, _u32, _u64, _P(_u64), _P(_u64)]),
     "thb_spec_batch": (_i, [_vp, _P(Track), C.c_size_t, _P(Setting), _P(SpecOut)]),
     "thb_spec_put": (_i, [_vp, _u64, _u32, _u32, _u32, _vp, _u64, _u32]),

@@ -327,7 +327,10 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     std::vector<uint32_t> mi_blob;
     if (d.n_mel && d.n_fft == 2048) {
         const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
-        mi_blob = mi.blob();
+        if (mi.valid) mi_blob = mi.blob();
+    }
+    if (!mi_blob.empty()) {
+        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
         d.mi_words = static_cast<int>(mi_blob.size());
         d.mi_groups = static_cast<int>(mi.n_groups);
         d.mi_min_start = mi.min_start;
@@ -598,6 +601,53 @@ int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t
     if (out) {
         const std::vector<float> d = mb.dense();
         memcpy(out, d.data(), sizeof(float) * d.size());
+    }
+    return THB_OK;
+}
+
+int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t stats[4]) {
+    if (!out || !stats || n_fft < 4) return THB_ERR_INVALID;
+    const thb::MelBank mb = thb::mel_bank(sr, n_fft, n_mel);
+    const thb::MelItems mi = thb::mel_items(mb);
+    stats[0] = mi.valid ? 1u : 0u;
+    stats[1] = mi.n_groups;
+    stats[2] = stats[3] = 0;
+    if (!mi.valid) return THB_ERR_UNSUPPORTED;
+    const size_t F = mb.n_freq, M = mb.n_mel, n_slots = static_cast<size_t>(mi.n_groups) * 32;
+    std::fill(out, out + F * M, 0.0f);
+    // band of every slot
+    std::vector<int64_t> band_of(2 * n_slots, -1);
+    for (size_t r = 0; r < mi.gk.size(); r++)
+        for (uint32_t j = 0; j < mi.gk[r]; j++)
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t pid = mi.goff[(static_cast<size_t>(mi.gbase[r]) + j) * 32 + l];
+                if (pid == mi.zero_slot) continue;
+                if (pid >= 2 * n_slots || 32 * r + l >= M || band_of[pid] >= 0) return THB_ERR_INTERNAL;  // a slot feeds one band only
+                band_of[pid] = static_cast<int64_t>(32 * r + l);
+            }
+    for (uint32_t g = 0; g < mi.n_groups; g++) {
+        stats[2] += mi.T[g];
+        for (uint32_t t = 0; t < mi.T[g]; t++) {
+            for (uint32_t h = 0; h < 2; h++) {
+                uint32_t cnt[16] = {}, worst = 0;
+                for (uint32_t l = 16 * h; l < 16 * h + 16; l++) {
+                    const int64_t k = static_cast<int64_t>(mi.start[g * 32 + l]) + t;
+                    worst = std::max(worst, ++cnt[((k % 16) + 16) % 16]);
+                }
+                stats[3] += worst - 1;
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                const int64_t k = static_cast<int64_t>(mi.start[g * 32 + l]) + t;
+                for (uint32_t side = 0; side < 2; side++) {
+                    const float w = mi.w[mi.w_index(g, t, l) + side];
+                    if (w == 0.0f) continue;
+                    const int64_t m = band_of[side * n_slots + g * 32 + l];
+                    if (m < 0 || k < 0 || k >= static_cast<int64_t>(F)) return THB_ERR_INTERNAL;  // weight that reaches no band
+                    if (out[static_cast<size_t>(k) * M + m] != 0.0f) return THB_ERR_INTERNAL;       // weight applied twice
+                    out[static_cast<size_t>(k) * M + m] = w;
+                }
+            }
+        }
     }
     return THB_OK;
 }

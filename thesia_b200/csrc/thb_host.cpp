@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 
 namespace thb {
 
@@ -168,23 +169,65 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
 MelItems mel_items(const MelBank &b) {
     MelItems it;
     it.n_mel = b.n_mel;
-    struct Piece {
-        uint32_t band, k, len, wofs;
-    };
-    std::vector<Piece> pieces;
-    std::vector<std::vector<uint32_t>> of_band(b.n_mel);
-    for (uint32_t m = 0; m < b.n_mel; m++) {
-        const uint32_t len = b.ptr[m + 1] - b.ptr[m];
-        const uint32_t np = std::max<uint32_t>(1, (len + kMelPieceMax - 1) / kMelPieceMax);
-        const uint32_t base = len / np, rem = len % np;
-        uint32_t pos = 0;
-        for (uint32_t i = 0; i < np; i++) {
-            const uint32_t li = base + (i < rem ? 1 : 0);
-            of_band[m].push_back(static_cast<uint32_t>(pieces.size()));
-            pieces.push_back({m, b.k0[m] + pos, li, b.ptr[m] + pos});
-            pos += li;
+    const uint32_t F = b.n_freq, M = b.n_mel;
+    // ---- per bin: segment id and its two weights (rise of band seg, fall of band seg - 1) ----
+    std::vector<int32_t> seg(F, -1);
+    std::vector<float> wr(F, 0.0f), wf(F, 0.0f);
+    // A bin between the peaks of bands m - 1 and m ("segment" m) carries the falling weight of band m - 1 and the
+    // rising weight of band m; a bin inside a single band joins the segment of the bin before it when it can.
+    std::vector<int32_t> band_lo(F, -1), band_hi(F, -1);
+    std::vector<float> w_lo(F, 0.0f), w_hi(F, 0.0f);
+    for (uint32_t m = 0; m < M; m++)
+        for (uint32_t i = b.ptr[m]; i < b.ptr[m + 1]; i++) {
+            const uint32_t k = b.k0[m] + (i - b.ptr[m]);
+            if (k >= F) return it;
+            if (band_lo[k] < 0) {
+                band_lo[k] = static_cast<int32_t>(m);
+                w_lo[k] = b.w[i];
+            } else if (band_hi[k] < 0 && band_lo[k] + 1 == static_cast<int32_t>(m)) {
+                band_hi[k] = static_cast<int32_t>(m);
+                w_hi[k] = b.w[i];
+            } else {
+                return it;  // not a chain of overlapping triangles: no schedule (the generic kernel handles it)
+            }
+        }
+    for (uint32_t k = 0; k < F; k++) {
+        if (band_lo[k] < 0) continue;
+        if (band_hi[k] >= 0) {
+            seg[k] = band_hi[k];
+            wf[k] = w_lo[k];
+            wr[k] = w_hi[k];
+        } else if (k > 0 && seg[k - 1] == band_lo[k] + 1) {
+            seg[k] = band_lo[k] + 1;
+            wf[k] = w_lo[k];
+        } else {
+            seg[k] = band_lo[k];
+            wr[k] = w_lo[k];
         }
     }
+    // ---- pieces: runs of one segment cut to at most kMelPieceMax bins ----
+    struct Piece {
+        uint32_t seg, k, len;
+    };
+    std::vector<Piece> pieces;
+    for (uint32_t k = 0; k < F;) {
+        if (seg[k] < 0) {
+            k++;
+            continue;
+        }
+        uint32_t e = k;
+        while (e < F && seg[e] == seg[k]) e++;
+        const uint32_t len = e - k, np = (len + kMelPieceMax - 1) / kMelPieceMax;
+        const uint32_t base = len / np, rem = len % np;
+        uint32_t pos = k;
+        for (uint32_t i = 0; i < np; i++) {
+            const uint32_t li = base + (i < rem ? 1 : 0);
+            pieces.push_back({static_cast<uint32_t>(seg[k]), pos, li});
+            pos += li;
+        }
+        k = e;
+    }
+    if (pieces.empty()) return it;
     std::vector<uint32_t> order(pieces.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return pieces[x].len > pieces[y].len; });
@@ -194,69 +237,168 @@ MelItems mel_items(const MelBank &b) {
     it.start.assign(static_cast<size_t>(it.n_groups) * 32, 0);
     std::vector<uint32_t> slot_of(pieces.size());
     for (uint32_t g = 0; g < it.n_groups; g++) {
-        uint32_t lead[32] = {}, T = 2;
-        int used[2][16] = {};
-        for (uint32_t l = 0; l < 32; l++) {
-            const size_t oi = static_cast<size_t>(g) * 32 + l;
-            if (oi >= order.size()) {
-                it.start[oi] = static_cast<int32_t>(l);  // idle lane: zero weights, harmless address
-                continue;
+        const uint32_t n = static_cast<uint32_t>(std::min<size_t>(32, order.size() - static_cast<size_t>(g) * 32));
+        const uint32_t *ids = &order[static_cast<size_t>(g) * 32];
+        uint32_t maxL = 1;
+        for (uint32_t i = 0; i < n; i++) maxL = std::max(maxL, pieces[ids[i]].len);
+        // Bank assignment.  A float2 load of a half warp is conflict-free when its 16 lanes hit 16 different
+        // 8-byte bank pairs, i.e. when their start bins differ mod 16.  A piece shorter than the group's step
+        // count may start up to (T - len) bins early on zero weights, which gives it a choice of residues:
+        // match pieces to (half warp, residue) slots (Kuhn's augmenting paths), growing T by at most kSlack.
+        constexpr uint32_t kSlack = 3;
+        int owner[32];      // slot (16 h + r) -> piece index in ids, or -1
+        int slot_sel[32];   // piece -> slot
+        uint32_t T = maxL;
+        bool matched = false;
+        for (uint32_t e = 0; e <= kSlack && !matched; e++) {
+            T = (maxL + e + 1) & ~1u;  // even: the walk takes two steps per float4 of weights
+            std::fill(owner, owner + 32, -1);
+            bool seen[32];
+            std::function<bool(int)> aug = [&](int i) -> bool {
+                const Piece &pc = pieces[ids[i]];
+                const uint32_t omax = std::min<uint32_t>(15, T - pc.len);
+                for (uint32_t o = 0; o <= omax; o++) {
+                    const uint32_t r = (pc.k + 16 * 16 - o) % 16;
+                    for (uint32_t h = 0; h < 2; h++) {
+                        const uint32_t sl = 16 * h + r;
+                        if (seen[sl]) continue;
+                        seen[sl] = true;
+                        if (owner[sl] < 0 || aug(owner[sl])) {
+                            owner[sl] = i;
+                            return true;
+                        }
+                    }
+                }
+                return false;
+            };
+            matched = true;
+            for (uint32_t i = 0; i < n && matched; i++) {
+                std::fill(seen, seen + 32, false);
+                matched = aug(static_cast<int>(i));
             }
-            const Piece &pc = pieces[order[oi]];
-            uint32_t o = 0;
-            auto res = [&](uint32_t oo) { return ((static_cast<int64_t>(pc.k) - oo) % 16 + 16) % 16; };
-            while (o < 15 && used[l / 16][res(o)] >= 2) o++;
-            used[l / 16][res(o)]++;
-            lead[l] = o;
-            it.start[oi] = static_cast<int32_t>(pc.k) - static_cast<int32_t>(o);
-            slot_of[order[oi]] = static_cast<uint32_t>(oi);
-            T = std::max(T, o + pc.len);
         }
-        T = (T + 1) & ~1u;
+        if (matched) {
+            for (int sl = 0; sl < 32; sl++)
+                if (owner[sl] >= 0) slot_sel[owner[sl]] = sl;
+        } else {  // give up on conflict freedom for this group: no lead, halves in order
+            T = (maxL + 1) & ~1u;
+            for (uint32_t i = 0; i < n; i++) slot_sel[i] = -1;
+        }
+        // Lane inside the half warp: the lane whose index equals the segment id mod 16 when it is free, so that
+        // the gather of consecutive bands reads consecutive bank pairs.
+        int lane_of[32];
+        bool lane_used[32] = {};
+        uint32_t lead[32] = {};
+        for (int pass = 0; pass < 2; pass++)
+            for (uint32_t i = 0; i < n; i++) {
+                const Piece &pc = pieces[ids[i]];
+                const int h = matched ? slot_sel[i] / 16 : static_cast<int>(i / 16);
+                const int want = 16 * h + static_cast<int>(pc.seg % 16);
+                if (pass == 0) {
+                    lane_of[i] = -1;
+                    if (!lane_used[want]) {
+                        lane_of[i] = want;
+                        lane_used[want] = true;
+                    }
+                } else if (lane_of[i] < 0) {
+                    int l = 16 * h;
+                    while (lane_used[l]) l++;
+                    lane_of[i] = l;
+                    lane_used[l] = true;
+                }
+            }
+        for (uint32_t i = 0; i < n; i++) {
+            const Piece &pc = pieces[ids[i]];
+            if (matched) lead[i] = (pc.k + 16 * 16 - static_cast<uint32_t>(slot_sel[i] % 16)) % 16;
+        }
         it.T[g] = T;
         it.woff[g] = static_cast<uint32_t>(it.w.size());
-        it.w.resize(it.w.size() + static_cast<size_t>(T) * 32, 0.0f);
+        it.w.resize(it.w.size() + static_cast<size_t>(T) * 64, 0.0f);
+        for (uint32_t l = 0; l < 32; l++) it.start[static_cast<size_t>(g) * 32 + l] = static_cast<int32_t>(l);  // idle lanes
+        for (uint32_t i = 0; i < n; i++) {
+            const Piece &pc = pieces[ids[i]];
+            const size_t oi = static_cast<size_t>(g) * 32 + static_cast<size_t>(lane_of[i]);
+            it.start[oi] = static_cast<int32_t>(pc.k) - static_cast<int32_t>(lead[i]);
+            slot_of[ids[i]] = static_cast<uint32_t>(oi);
+            for (uint32_t j = 0; j < pc.len; j++) {
+                const size_t at = it.w_index(g, lead[i] + j, static_cast<uint32_t>(lane_of[i]));
+                it.w[at] = wr[pc.k + j];
+                it.w[at + 1] = wf[pc.k + j];
+            }
+        }
         for (uint32_t l = 0; l < 32; l++) {
             const size_t oi = static_cast<size_t>(g) * 32 + l;
             it.min_start = std::min(it.min_start, it.start[oi]);
             const int64_t reach = static_cast<int64_t>(it.start[oi]) + T - 1;
             if (reach > static_cast<int64_t>(it.max_reach)) it.max_reach = static_cast<uint32_t>(reach);
-            if (oi >= order.size()) continue;
-            const Piece &pc = pieces[order[oi]];
-            for (uint32_t i = 0; i < pc.len; i++)
-                {
-                const uint32_t t = lead[l] + i;  // float2 steps: (t even, t odd) side by side per lane
-                it.w[it.woff[g] + static_cast<size_t>(t / 2) * 64 + 2 * l + (t & 1)] = b.w[pc.wofs + i];
-            }
         }
     }
-    it.piece_ptr.assign(b.n_mel + 1, 0);
-    for (uint32_t m = 0; m < b.n_mel; m++) {
-        for (uint32_t pi : of_band[m]) it.piece_ids.push_back(slot_of[pi]);
+    // ---- gather lists: band m = rise sums of segment m's pieces, then fall sums of segment m + 1's ----
+    const uint32_t n_slots = it.n_groups * 32;
+    it.piece_ptr.assign(M + 1, 0);
+    for (uint32_t m = 0; m < M; m++) {
+        for (uint32_t pi = 0; pi < pieces.size(); pi++)
+            if (pieces[pi].seg == m) it.piece_ids.push_back(slot_of[pi]);
+        for (uint32_t pi = 0; pi < pieces.size(); pi++)
+            if (pieces[pi].seg == m + 1) it.piece_ids.push_back(n_slots + slot_of[pi]);
         it.piece_ptr[m + 1] = static_cast<uint32_t>(it.piece_ids.size());
     }
+    // ---- the same lists in the shape the kernels read: per round of 32 bands a uniform count K and K rows of 32
+    //      slot ids (u16), short lists padded with a slot that always holds zero ----
+    it.zero_slot = 2 * n_slots;
+    const uint32_t n_rounds = (M + 31) / 32;
+    it.gk.assign(n_rounds, 0);
+    it.gbase.assign(n_rounds, 0);
+    uint32_t rows = 0;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        uint32_t K = 0;
+        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) K = std::max(K, it.piece_ptr[m + 1] - it.piece_ptr[m]);
+        it.gk[r] = K;
+        it.gbase[r] = rows;
+        rows += K;
+    }
+    if (it.zero_slot > 0xffffu) return it;
+    it.goff.assign(static_cast<size_t>(rows) * 32, static_cast<uint16_t>(it.zero_slot));
+    for (uint32_t m = 0; m < M; m++)
+        for (uint32_t i = it.piece_ptr[m]; i < it.piece_ptr[m + 1]; i++)
+            it.goff[(static_cast<size_t>(it.gbase[m / 32]) + (i - it.piece_ptr[m])) * 32 + m % 32] = static_cast<uint16_t>(it.piece_ids[i]);
+    it.valid = true;
     return it;
 }
 
 std::vector<uint32_t> MelItems::blob() const {
     std::vector<uint32_t> o(8, 0);
-    auto put = [&](size_t hdr, const void *data, size_t words) {
-        o[hdr] = static_cast<uint32_t>(o.size());
-        const uint32_t *p = static_cast<const uint32_t *>(data);
-        o.insert(o.end(), p, p + words);
+    auto align4 = [&]() {
+        while (o.size() & 3) o.push_back(0);
     };
     o[0] = n_groups;
     o[1] = n_mel;
-    put(2, T.data(), T.size());
-    const size_t woff_at = o.size();
-    put(3, woff.data(), woff.size());
-    put(4, start.data(), start.size());
-    put(5, piece_ptr.data(), piece_ptr.size());
-    put(6, piece_ids.data(), piece_ids.size());
-    while (o.size() & 3) o.push_back(0);
-    put(7, w.data(), w.size());
-    for (size_t g = 0; g < woff.size(); g++) o[woff_at + g] += o[7];
-    while (o.size() & 3) o.push_back(0);
+    o[6] = zero_slot;
+    o[2] = static_cast<uint32_t>(o.size());  // {T, absolute word offset of the group's weights}
+    const size_t grp_at = o.size();
+    for (uint32_t g = 0; g < n_groups; g++) {
+        o.push_back(T[g]);
+        o.push_back(woff[g]);
+    }
+    align4();
+    o[3] = static_cast<uint32_t>(o.size());
+    for (int32_t v : start) o.push_back(static_cast<uint32_t>(v));
+    align4();
+    o[4] = static_cast<uint32_t>(o.size());  // {K, first row} per round of 32 bands
+    for (size_t r = 0; r < gk.size(); r++) {
+        o.push_back(gk[r]);
+        o.push_back(gbase[r]);
+    }
+    align4();
+    o[5] = static_cast<uint32_t>(o.size());
+    for (size_t i = 0; i + 1 < goff.size() + 1; i += 2)
+        o.push_back(static_cast<uint32_t>(goff[i]) | (static_cast<uint32_t>(i + 1 < goff.size() ? goff[i + 1] : 0) << 16));
+    align4();
+    o[7] = static_cast<uint32_t>(o.size());
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(w.data());
+    o.insert(o.end(), wp, wp + w.size());
+    for (uint32_t g = 0; g < n_groups; g++) o[grp_at + 2 * g + 1] += o[7];
+    align4();
     return o;
 }
 

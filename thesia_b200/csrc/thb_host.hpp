@@ -36,26 +36,41 @@ struct MelBank {
     std::vector<float> dense() const;  // (n_freq, n_mel) row-major
 };
 // Warp schedule of the sparse mel product, shared by the two n_fft == 2048 kernels (they must add in the same
-// order to agree bit for bit).  Every band is cut into pieces of at most kMelPieceMax consecutive bins; the pieces
-// ("items") are sorted by length and dealt 32 at a time to the lanes of a warp ("groups"), so that a group costs
-// max-length steps and the sum over groups stays close to nnz / 32.  Lane l of group g walks T[g] bins from
-// start[g*32+l] with weights w[woff[g] + 64 (t/2) + 2 l + (t&1)] (zero outside the piece) and leaves a partial sum in slot
-// g*32+l; band m is the sum of its slots piece_ids[piece_ptr[m] .. piece_ptr[m+1]) in ascending-bin order.
-// `start` is pulled back by a few bins (zero weights) so that the 16 lanes of each half warp hit every 8-byte
-// shared-memory bank pair at most twice; it can be negative (>= -15).
-constexpr uint32_t kMelPieceMax = 16;
+// order to agree bit for bit).  The bins are walked ONCE: bin k between the peaks of bands s - 1 and s ("segment" s)
+// carries two weights, the rising one of band s and the falling one of band s - 1.  Every segment is cut into
+// pieces of at most kMelPieceMax consecutive bins; the pieces are sorted by length and dealt 32 at a time to the
+// lanes of a warp ("groups"), so that a group costs max-length steps.  Lane l of group g walks T[g] bins from
+// start[g*32+l]; at step t it multiplies the bin by the weight pair w[w_index(g, t, l) + {0: rise, 1: fall}]
+// (zero outside the piece) into two accumulators, which end up in slots g*32+l (rise) and n_slots + g*32+l (fall),
+// n_slots = 32 n_groups.  Band m is the sum of the slots piece_ids[piece_ptr[m] .. piece_ptr[m+1]): the rise sums of
+// segment m's pieces, then the fall sums of segment m+1's, each in ascending-bin order.  The kernels read those
+// lists as a table: round r (bands 32 r ..) has gk[r] rows starting at row gbase[r]; row j holds one slot id per
+// lane (goff[(gbase[r] + j) * 32 + lane]), lists shorter than gk[r] are padded with zero_slot, a slot nobody writes.
+// Shared-memory banks: `start` is pulled back by up to 15 bins (zero weights) so that the 16 lanes of each half
+// warp start on 16 different residues mod 16 -- their float2 loads then hit 16 different 8-byte bank pairs at every
+// step -- and a piece of segment s sits in a lane congruent to s mod 16 when that lane is free, which spreads the
+// gather of consecutive bands over the banks.  `valid` is false when the bank is not a chain of overlapping
+// triangles (at most two adjacent bands per bin); such banks run on the generic kernel.
+constexpr uint32_t kMelPieceMax = 15;
 struct MelItems {
+    bool valid = false;
     uint32_t n_groups = 0, n_mel = 0;
     std::vector<uint32_t> T;          // [n_groups], even
     std::vector<uint32_t> woff;       // [n_groups], offset into w
     std::vector<int32_t> start;       // [n_groups * 32]
-    std::vector<float> w;             // interleaved weights
+    std::vector<float> w;             // float4 per lane and two steps: {rise, fall} of step 2i, then of step 2i+1
     std::vector<uint32_t> piece_ptr;  // [n_mel + 1]
-    std::vector<uint32_t> piece_ids;  // slots, ascending bins within a band
+    std::vector<uint32_t> piece_ids;  // slots
+    std::vector<uint32_t> gk, gbase;  // [ceil(n_mel / 32)]
+    std::vector<uint16_t> goff;       // [sum(gk) * 32]
+    uint32_t zero_slot = 0;
+    size_t w_index(uint32_t g, uint32_t t, uint32_t lane) const {
+        return woff[g] + static_cast<size_t>(t / 2) * 128 + 4 * static_cast<size_t>(lane) + 2 * (t & 1);
+    }
     int32_t min_start = 0;
     uint32_t max_reach = 0;           // largest bin index any lane reads
-    // one blob of 32-bit words for the device: header {n_groups, n_mel, off_T, off_woff, off_start, off_pptr,
-    // off_pids, off_w} then the arrays; woff entries are made absolute word offsets into the blob
+    // one blob of 32-bit words for the device: header {n_groups, n_mel, off_groups, off_start, off_rounds,
+    // off_goff, zero_slot, off_w} then the arrays (see blob())
     std::vector<uint32_t> blob() const;
 };
 MelItems mel_items(const MelBank &b);

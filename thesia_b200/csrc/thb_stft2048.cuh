@@ -55,26 +55,81 @@ constexpr float kRescueDown = 8.6736174e-19f;  // 2^-60
 struct MelView {
     const uint32_t *base;
     int n_groups, n_mel;
-    const uint32_t *T, *woff, *pptr, *pids;
-    const int32_t *start;
+    const uint2 *grp;      // {T, word offset of the group's weights}
+    const int32_t *start;  // [n_groups * 32]
+    const uint2 *rounds;   // {K, first row} per 32 bands
+    const uint16_t *goff;  // rows of 32 slot ids
     __device__ __forceinline__ explicit MelView(const uint32_t *b) : base(b) {
         n_groups = static_cast<int>(b[0]);
         n_mel = static_cast<int>(b[1]);
-        T = b + b[2];
-        woff = b + b[3];
-        start = reinterpret_cast<const int32_t *>(b + b[4]);
-        pptr = b + b[5];
-        pids = b + b[6];
+        grp = reinterpret_cast<const uint2 *>(b + b[2]);
+        start = reinterpret_cast<const int32_t *>(b + b[3]);
+        rounds = reinterpret_cast<const uint2 *>(b + b[4]);
+        goff = reinterpret_cast<const uint16_t *>(b + b[5]);
     }
 };
 
 // elements (float for the scalar kernel, float2 for the pair kernel) of one warp's tile: the transpose tile,
-// later the magnitudes [kMagBase + bin] with the mel walk's lead / reach, then one partial sum per mel slot
+// later the magnitudes [kMagBase + bin] with the mel walk's lead / reach, then two partial sums (rise, fall) per
+// mel slot: part[slot] and part[n_slots + slot]
 __host__ __device__ inline int part_base(const PlanDev &p) { return (kMagBase + (p.n_mel ? p.mi_max_reach : 1024) + 2) & ~1; }
 __host__ __device__ inline int tile_elems(const PlanDev &p) {
-    const int need = part_base(p) + (p.n_mel ? p.mi_groups * 32 : 0);
+    const int need = part_base(p) + (p.n_mel ? 2 * p.mi_groups * 32 + 1 : 0);  // + the always-zero slot
     const int t = need > 32 * kRow ? need : 32 * kRow;
     return (t + 3) & ~3;
+}
+
+// The sparse mel product of one frame (V = float) or one frame pair (V = float2) from the warp's magnitudes,
+// following the MelItems schedule (thb_host.hpp).  Leaves the band sums in part[...]: the caller gathers them.
+template <typename V>
+struct MelOps;
+template <>
+struct MelOps<float> {
+    static __device__ __forceinline__ float zero() { return 0.0f; }
+    static __device__ __forceinline__ float fma(float m, float w, float acc) { return fmaf(m, w, acc); }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+};
+template <>
+struct MelOps<float2> {
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.0f, 0.0f); }
+    static __device__ __forceinline__ float2 fma(float2 m, float w, float2 acc) { return __ffma2_rn(m, make_float2(w, w), acc); }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+};
+
+template <typename V>
+__device__ __forceinline__ void mel_walk(const MelView &mv, const V *mag, V *part, int lane) {
+    using O = MelOps<V>;
+    const int n_slots = mv.n_groups * 32;
+    for (int g = 0; g < mv.n_groups; g++) {
+        const uint2 gh = mv.grp[g];
+        const float4 *wq = reinterpret_cast<const float4 *>(mv.base + gh.y) + lane;
+        const V *mq = mag + mv.start[g * 32 + lane];
+        const int T2 = static_cast<int>(gh.x) >> 1;
+        V rise = O::zero(), fall = O::zero();
+#pragma unroll 2
+        for (int t = 0; t < T2; t++) {
+            const float4 w = wq[32 * t];
+            const V m0 = mq[2 * t], m1 = mq[2 * t + 1];
+            rise = O::fma(m0, w.x, rise);
+            fall = O::fma(m0, w.y, fall);
+            rise = O::fma(m1, w.z, rise);
+            fall = O::fma(m1, w.w, fall);
+        }
+        part[g * 32 + lane] = rise;
+        part[n_slots + g * 32 + lane] = fall;
+    }
+    if (lane == 0) part[2 * n_slots] = O::zero();  // the padding slot of the gather (the tile is reused by the transposes)
+}
+
+// band 32 r + lane: sum of its partial sums in the schedule's order (the padding rows add the always-zero slot)
+template <typename V>
+__device__ __forceinline__ V mel_band(const MelView &mv, const V *part, int r, int lane) {
+    using O = MelOps<V>;
+    const uint2 rd = mv.rounds[r];
+    const uint16_t *row = mv.goff + rd.y * 32 + lane;
+    V acc = O::zero();
+    for (uint32_t j = 0; j < rd.x; j++) acc = O::add(acc, part[row[32 * j]]);
+    return acc;
 }
 
 }  // namespace k2048

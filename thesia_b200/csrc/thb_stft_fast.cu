@@ -272,24 +272,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                for (int g = 0; g < mv.n_groups; g++) {
-                    const float2 *wq = reinterpret_cast<const float2 *>(mv.base + mv.woff[g]) + lane;
-                    const float *mq = mag + mv.start[g * 32 + lane];
-                    const int steps2 = static_cast<int>(mv.T[g]) >> 1;
-                    float acc = 0.0f;
-#pragma unroll 2
-                    for (int t = 0; t < steps2; t++) {
-                        const float2 w = wq[32 * t];
-                        acc = fmaf(mq[2 * t], w.x, acc);
-                        acc = fmaf(mq[2 * t + 1], w.y, acc);
-                    }
-                    part[g * 32 + lane] = acc;
-                }
+                mel_walk<float>(mv, mag, part, lane);
                 __syncwarp();
-                for (int m = lane; m < mv.n_mel; m += 32) {
-                    const uint32_t p0 = mv.pptr[m], p1 = mv.pptr[m + 1];
-                    float acc = part[mv.pids[p0]];
-                    for (uint32_t i = p0 + 1; i < p1; i++) acc += part[mv.pids[i]];
+                for (int r = 0; 32 * r < mv.n_mel; r++) {
+                    const int m = 32 * r + lane;
+                    const float acc = mel_band<float>(mv, part, r, lane);
+                    if (m >= mv.n_mel) continue;
                     // exact zero stays -inf; db_off only shifts finite values
                     const float db = fmaf(kDbPerLog2Amp, lg2_ftz(acc), db_off);
                     orow[m] = db;

@@ -277,24 +277,12 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                for (int g = 0; g < mv.n_groups; g++) {
-                    const float2 *wq = reinterpret_cast<const float2 *>(mv.base + mv.woff[g]) + lane;
-                    const float2 *mq = mag + mv.start[g * 32 + lane];
-                    const int steps2 = static_cast<int>(mv.T[g]) >> 1;
-                    f2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 2
-                    for (int t = 0; t < steps2; t++) {
-                        const float2 w = wq[32 * t];
-                        acc = pfma(mq[2 * t], bc(w.x), acc);
-                        acc = pfma(mq[2 * t + 1], bc(w.y), acc);
-                    }
-                    part[g * 32 + lane] = acc;
-                }
+                mel_walk<float2>(mv, mag, part, lane);
                 __syncwarp();
-                for (int m = lane; m < mv.n_mel; m += 32) {
-                    const uint32_t p0 = mv.pptr[m], p1 = mv.pptr[m + 1];
-                    f2 acc = part[mv.pids[p0]];
-                    for (uint32_t i = p0 + 1; i < p1; i++) acc = padd(acc, part[mv.pids[i]]);
+                for (int r = 0; 32 * r < mv.n_mel; r++) {
+                    const int m = 32 * r + lane;
+                    const f2 acc = mel_band<float2>(mv, part, r, lane);
+                    if (m >= mv.n_mel) continue;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
                     orow_b[m] = db.y;
