@@ -119,6 +119,30 @@ def test_spectrogram_to_img_kat_through_gpu(ctx):
     ctx.release(900, 0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,rows", [((300, 128), (0, 128)), ((517, 347), (0, 347)), ((517, 347), (8, 400)),
+                                        ((129, 128), (4, 100)), ((1, 5), (0, 5)), ((260, 1025), (3, 1025)),
+                                        ((64, 132), (128, 140))])
+@pytest.mark.parametrize("tile_mode", ["0", "1", "2"])
+def test_spec_to_img_kernels_agree_with_oracle(ctx, orc, monkeypatch, shape, rows, tile_mode):
+    """drawing.rs:4-33 through all three image kernels (THB_IMG_TILE caps the kernel choice): ragged tiles, rows
+    above the last bin, -inf / NaN / out-of-range values -- bit-exact given the dB input."""
+    monkeypatch.setenv("THB_IMG_TILE", tile_mode)
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    spec = rng.uniform(-130.0, 12.0, size=shape).astype(np.float32)
+    spec.flat[:: 37] = -np.inf
+    spec.flat[5 :: 211] = np.nan
+    spec.flat[3 :: 97] = np.float32(-100.0)
+    spec.flat[7 :: 89] = np.float32(0.0)
+    ctx.spec_put(901, 0, 48000, thb.FreqScale.Linear, spec)
+    for rng_dB, cmap in (((-100.0, 0.0), 258), ((-63.25, -1.5), 4), ((-np.inf, -np.inf), 258)):
+        img = ctx.spec_to_img(901, 0, rows, rng_dB, cmap)
+        want = orc.spec_to_img(spec, rows, rng_dB, cmap)
+        assert img.shape == want.shape
+        assert np.array_equal(img, want), (shape, rows, tile_mode, rng_dB)
+    ctx.release(901, 0)
+
+
 def _tile_fields(b):
     rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
     return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)

@@ -1042,6 +1042,17 @@ int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB
     return THB_OK;
 }
 
+// which spec_to_img kernel a batch of descriptors may use (thb_kernels.cuh); THB_IMG_TILE=0|1|2 caps it (A/B runs)
+static int img_tile_mode(const thb::ImgDesc *h, size_t n) {
+    int mode = 2;
+    for (size_t i = 0; i < n; i++) {
+        if ((h[i].pitch & 1) || (reinterpret_cast<uintptr_t>(h[i].img) & 3)) return 0;
+        if ((h[i].B & 3) || (h[i].i0 & 3) || (reinterpret_cast<uintptr_t>(h[i].spec) & 15)) mode = 1;
+    }
+    if (const char *e = getenv("THB_IMG_TILE")) mode = std::min(mode, atoi(e));
+    return mode < 0 ? 0 : mode;
+}
+
 static int img_prepare(thb_ctx *ctx, Spec &sp, uint64_t H) {
     const uint64_t pitch = (sp.T + 63) & ~uint64_t(63);
     const size_t need = static_cast<size_t>(H) * pitch;
@@ -1083,7 +1094,7 @@ int thb_spec_to_img(thb_ctx *ctx, uint64_t id, uint32_t ch, uint64_t i0, uint64_
     if ((rc = arena_commit(ctx))) return rc;
     {
         ProfScope ps(ctx, "spec_to_img");
-        cudaError_t e = thb::launch_spec_to_img(d_desc, 1, h->T, h->H, d_rng, colormap_length, ctx->stream);
+        cudaError_t e = thb::launch_spec_to_img(d_desc, 1, h->T, h->H, d_rng, colormap_length, img_tile_mode(h, 1), ctx->stream);
         if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spec_to_img: %s", cudaGetErrorString(e));
     }
     CK(cudaMemcpy2DAsync(out, sizeof(uint16_t) * sp->T, d_tmp, sizeof(uint16_t) * pitch, sizeof(uint16_t) * sp->T, H,
@@ -1136,7 +1147,8 @@ int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length,
     if ((rc = global_minmax_on_stream(ctx, dB_range))) return rc;
     if (j) {
         ProfScope ps(ctx, "spec_to_img", static_cast<int>((j + 65534) / 65535));
-        cudaError_t e = thb::launch_spec_to_img(d_desc, static_cast<int>(j), max_T, max_H, ctx->d_range, colormap_length, ctx->stream);
+        cudaError_t e = thb::launch_spec_to_img(d_desc, static_cast<int>(j), max_T, max_H, ctx->d_range, colormap_length,
+                                                img_tile_mode(h, j), ctx->stream);
         if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spec_to_img: %s", cudaGetErrorString(e));
     }
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_range, sizeof(float) * 2, cudaMemcpyDeviceToHost, ctx->stream));

@@ -118,6 +118,85 @@ __global__ void __launch_bounds__(256) spec_to_img_kernel(const ImgDesc *__restr
     }
 }
 
+// The quantiser of drawing.rs:22-31, operation for operation (no contraction).
+__device__ __forceinline__ uint32_t quantise_dB(float v, float dB_min, float span, float u16_span, float min_value_f) {
+    const float zero_to_one = __fdiv_rn(__fsub_rn(v, dB_min), span);
+    const float scaled = __fadd_rn(__fmul_rn(zero_to_one, u16_span), min_value_f);
+    const float r = roundf(scaled);  // f32::round: half away from zero
+    return (r != r) ? 0u : static_cast<uint32_t>(fminf(fmaxf(r, 0.0f), 65535.0f));  // clamp, `as u16`; NaN -> 0
+}
+
+// 128 (bins) x 128 (frames) tiles: a thread quantises 4 consecutive bins of 2 consecutive frames at a time (two
+// 16-byte loads when VEC), packs the two frames of a bin into one 32-bit word and parks it in a shared tile whose
+// columns are XOR-swizzled by the lane, so both the transposing stores and the row reads are conflict-free; image
+// rows leave as 128-byte warp stores.
+constexpr int kBigT = 128, kBigB = 128;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) spec_to_img_tile_kernel(const ImgDesc *__restrict__ descs,
+                                                                const float *__restrict__ range, float min_value_f,
+                                                                float u16_span) {
+    __shared__ uint32_t tile[kBigB][kBigT / 2];
+    const ImgDesc d = descs[blockIdx.z];
+    const long long t0 = static_cast<long long>(blockIdx.x) * kBigT;
+    const int r0 = blockIdx.y * kBigB;
+    if (t0 >= d.T || r0 >= d.H) return;
+    const float dB_min = range[0], dB_max = range[1];
+    const bool all_zero = (dB_min == dB_max) && (dB_max == -CUDART_INF_F);
+    const float span = __fsub_rn(dB_max, dB_min);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = r0 + 4 * lane;      // first image row of this lane's 4 bins
+    const int bin = d.i0 + row;
+#pragma unroll 2
+    for (int i = 0; i < kBigT / 16; i++) {
+        const int fp = warp + 8 * i;    // frame pair inside the tile
+        const long long t = t0 + 2 * fp;
+        float v[2][4];
+        bool ok[2][4];
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            const bool t_ok = (t + f) < d.T && !all_zero;
+            const float *src = d.spec + (t + f) * d.B + bin;
+            if (VEC && t_ok && row + 3 < d.H && bin + 3 < d.B) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+                v[f][0] = q.x; v[f][1] = q.y; v[f][2] = q.z; v[f][3] = q.w;
+                ok[f][0] = ok[f][1] = ok[f][2] = ok[f][3] = true;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    ok[f][j] = t_ok && (row + j) < d.H && (bin + j) < d.B;
+                    v[f][j] = ok[f][j] ? __ldg(src + j) : 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t a = ok[0][j] ? quantise_dB(v[0][j], dB_min, span, u16_span, min_value_f) : 0u;
+            const uint32_t b = ok[1][j] ? quantise_dB(v[1][j], dB_min, span, u16_span, min_value_f) : 0u;
+            tile[4 * lane + j][fp ^ lane] = a | (b << 16);
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < kBigB / 8; i++) {
+        const int rr = warp + 8 * i;
+        if (r0 + rr >= d.H) break;
+        const int g = (rr >> 2) & 31;
+        uint16_t *orow = d.img + static_cast<long long>(r0 + rr) * d.pitch + t0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int c = lane + 32 * h;
+            const uint32_t w = tile[rr][c ^ g];
+            const long long t = t0 + 2 * c;
+            if (t + 1 < d.pitch) {
+                *reinterpret_cast<uint32_t *>(orow + 2 * c) = w;   // columns >= T inside the pitch get zeros
+            } else if (t < d.T) {
+                orow[2 * c] = static_cast<uint16_t>(w & 0xffffu);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_minmax_init(float *d_slots, int n, cudaStream_t st) {
@@ -152,7 +231,7 @@ cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d
 }
 
 cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, int max_H,
-                               const float *d_range, uint32_t colormap_length, cudaStream_t st) {
+                               const float *d_range, uint32_t colormap_length, int tile_mode, cudaStream_t st) {
     if (n <= 0 || max_T <= 0 || max_H <= 0) return cudaSuccess;
     // min_value = max(1, round(65535 / colormap_length) as u16)   (drawing.rs:20-21)
     double r = colormap_length ? std::round(65535.0 / static_cast<double>(colormap_length)) : 65535.0;
@@ -160,12 +239,18 @@ cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, i
     uint32_t min_value = static_cast<uint32_t>(r);
     if (min_value < 1) min_value = 1;
     const float u16_span = static_cast<float>(65535u - min_value);
-    const unsigned gx = static_cast<unsigned>((max_T + kTileT - 1) / kTileT);
-    const unsigned gy = static_cast<unsigned>((max_H + kTileB - 1) / kTileB);
+    // tile_mode: 0 = small tiles (any layout), 1 = big tiles, 2 = big tiles with 16-byte loads
+    const unsigned gx = static_cast<unsigned>(tile_mode ? (max_T + kBigT - 1) / kBigT : (max_T + kTileT - 1) / kTileT);
+    const unsigned gy = static_cast<unsigned>(tile_mode ? (max_H + kBigB - 1) / kBigB : (max_H + kTileB - 1) / kTileB);
     for (int t0 = 0; t0 < n; t0 += 65535) {
         const int nt = n - t0 < 65535 ? n - t0 : 65535;
         dim3 grid(gx, gy, static_cast<unsigned>(nt));
-        spec_to_img_kernel<<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        if (tile_mode == 2)
+            spec_to_img_tile_kernel<true><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        else if (tile_mode == 1)
+            spec_to_img_tile_kernel<false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        else
+            spec_to_img_kernel<<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

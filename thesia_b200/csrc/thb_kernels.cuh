@@ -97,8 +97,10 @@ cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_sen
 // d_range = {min_dB, max_dB} after the clamp rules of mod.rs:179-180
 cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d_range, cudaStream_t st);
 
+// tile_mode 0: 32 x 64 tiles, any layout.  1: 128 x 128 tiles (image pitch even, 4-byte aligned rows).
+// 2: as 1 with 16-byte loads (every descriptor: spec 16-byte aligned, B % 4 == 0, i0 % 4 == 0).
 cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, int max_H,
-                               const float *d_range, uint32_t colormap_length, cudaStream_t st);
+                               const float *d_range, uint32_t colormap_length, int tile_mode, cudaStream_t st);
 
 // tiles [tile_begin, tile_begin + tile_count) of every channel; tile_count == 0 -> to the end
 cudaError_t launch_envelope(const EnvDesc *d_descs, int n, long long max_len, uint32_t level,
