@@ -241,6 +241,7 @@ def run_b200(args) -> None:
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
     e0.record(stream)
     for _ in range(args.steps):
         mn, mx = step_resident()
@@ -249,7 +250,7 @@ def run_b200(args) -> None:
     clocks = sampler.stop()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count()
+    launches = ctx.launch_count() - launches0  # kernels of this library launched inside the timed region
     k_ms, k_launches = ctx.profile_get("stft_mel_db")          # the frame-pair STFT kernel alone
     edge_ms, edge_launches = ctx.profile_get("stft_mel_db_edges")  # scalar kernel: file edges + rescue list
     img_ms, img_launches = ctx.profile_get("spec_to_img")
@@ -293,45 +294,80 @@ def run_b200(args) -> None:
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
+    e2e_i16 = None
     if not args.no_e2e:
-        h2d_bytes = n_ch_total * n * 4
         img_bytes = n_ch_total * N_MEL * T * 2
-        host_pcm_p, host_img_p = C.c_void_p(), C.c_void_p()
-        _lib.check(_lib.lib().thb_host_alloc(h2d_bytes, C.byref(host_pcm_p)))
+        img_stride = N_MEL * T
+        host_img_p = C.c_void_p()
         _lib.check(_lib.lib().thb_host_alloc(img_bytes, C.byref(host_img_p)))
-        host_pcm = np.ctypeslib.as_array(C.cast(host_pcm_p, C.POINTER(C.c_float)), shape=(n_ch_total, n))
-        host_pcm_t = torch.from_numpy(host_pcm)
-        host_pcm_t.copy_(pcm[:, :n])  # fill the pinned input once (outside the timed region)
+
+        def pinned(nbytes, dtype, shape):
+            ptr = C.c_void_p()
+            _lib.check(_lib.lib().thb_host_alloc(nbytes, C.byref(ptr)))
+            ctype = C.c_float if dtype == np.float32 else C.c_int16
+            return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape)
+
+        def time_e2e(tracks_host):
+            def step_e2e():
+                ctx.spec_batch(tracks_host, setting)
+                r = ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
+                for c in range(n_ch_total):
+                    ctx.img_read_into(c // N_CH, c % N_CH, host_img_p.value + 2 * c * img_stride, img_stride)
+                return r
+
+            e2e_steps = max(1, min(args.steps, args.e2e_steps))
+            step_e2e()  # warm-up (staging pool growth)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                mn_e, mx_e = step_e2e()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            dt = float(t_e.item())
+            assert (mn_e, mx_e) == (mn, mx), "host-buffer and device-resident runs disagree on the dB range"
+            return hours_per_step * e2e_steps / dt, e2e_steps, 1000.0 * dt / e2e_steps
+
+        # (1) the reference's own host layout: f32 channels (Audio.wavs rows)
+        h2d_bytes = n_ch_total * n * 4
+        host_pcm_p, host_pcm = pinned(h2d_bytes, np.float32, (n_ch_total, n))
+        torch.from_numpy(host_pcm).copy_(pcm[:, :n])  # fill the pinned input once (outside the timed region)
         torch.cuda.synchronize()
         tracks_host = [dict(pcm=host_pcm[c], id=c // N_CH, ch=c % N_CH, sr=SR) for c in range(n_ch_total)]
-        img_stride = N_MEL * T
+        v, k, ms = time_e2e(tracks_host)
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": img_bytes + 8, "steps": k,
+               "ms_per_step": ms, "host_memory": "pinned (thb_host_alloc)", "pcm_format": "f32",
+               "pipeline": "H2D in 256 MB stages on a copy stream, overlapped with the STFT kernels"}
+        imgs_f32 = np.ctypeslib.as_array(C.cast(host_img_p, C.POINTER(C.c_uint16)), shape=(img_bytes // 2,)).copy() \
+            if args.scale < 1.0 else None
 
-        def step_e2e():
-            ctx.spec_batch(tracks_host, setting)
-            r = ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
-            for c in range(n_ch_total):
-                ctx.img_read_into(c // N_CH, c % N_CH, host_img_p.value + 2 * c * img_stride, img_stride)
-            return r
-
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        step_e2e()  # warm-up (staging pool growth)
+        # (2) SURVEY.md 8 f1: 16-bit PCM handed over as i16 (the >0 dBFS test track cannot be 16-bit and stays f32)
+        is16 = [track_flags(c // N_CH) & 1 == 0 for c in range(n_ch_total)]
+        n16 = sum(is16)
+        host_i16_p, host_i16 = pinned(max(n16, 1) * n * 2, np.int16, (max(n16, 1), n))
+        row16 = {}
+        for c in range(n_ch_total):
+            if is16[c]:
+                row16[c] = len(row16)
+                q = torch.round(pcm[c, :n] * 32768.0).to(torch.int16)
+                torch.from_numpy(host_i16[row16[c]]).copy_(q)
         torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            mn_e, mx_e = step_e2e()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        dt = float(t_e.item())
-        assert (mn_e, mx_e) == (mn, mx), "host-buffer and device-resident runs disagree on the dB range"
-        e2e = {"value": hours_per_step * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": img_bytes + 8, "steps": e2e_steps, "ms_per_step": 1000.0 * dt / e2e_steps,
-               "host_memory": "pinned (thb_host_alloc)"}
+        tracks_i16 = [dict(pcm=host_i16[row16[c]] if is16[c] else host_pcm[c], id=c // N_CH, ch=c % N_CH, sr=SR)
+                      for c in range(n_ch_total)]
+        v, k, ms = time_e2e(tracks_i16)
+        if imgs_f32 is not None:
+            got = np.ctypeslib.as_array(C.cast(host_img_p, C.POINTER(C.c_uint16)), shape=(img_bytes // 2,))
+            assert np.array_equal(got, imgs_f32), "i16 ingest changed the images"
+        e2e_i16 = {"value": v, "unit": UNIT, "h2d_bytes_per_step": n16 * n * 2 + (n_ch_total - n16) * n * 4,
+                   "d2h_bytes_per_step": img_bytes + 8, "steps": k, "ms_per_step": ms, "pcm_format": "i16",
+                   "note": f"{n16} of {n_ch_total} channels as 16-bit PCM (sample = s / 32768, exact): same dB range and "
+                           "images as the f32 run; the reference-side decoder would hand over i16 instead of f32"}
         _lib.lib().thb_host_free(host_pcm_p)
+        _lib.lib().thb_host_free(host_i16_p)
         _lib.lib().thb_host_free(host_img_p)
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample ----
@@ -353,7 +389,8 @@ def run_b200(args) -> None:
                        "parallelism": f"channels sharded, {world} rank(s), one 2-float NCCL max all-reduce",
                        "l2": "inputs (14.75 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "dB_range": [mn, mx]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_i16": e2e_i16, "clocks": clocks,
+            "gpu_launches": int(launches),
         }
         print(json.dumps(line), flush=True)
     ctx.close()

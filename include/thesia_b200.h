@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define THB_ABI_VERSION 1
+#define THB_ABI_VERSION 2
 
 typedef enum thb_status {
     THB_OK = 0,
@@ -63,12 +63,12 @@ typedef struct thb_setting {
 } thb_setting;
 
 /* One (id, ch) channel = `tracklist[id].channel(ch)` (src-tauri/src/core/track.rs:92-94) with its
- * sample rate.  The last four fields shard a long file by FRAME RANGE across GPUs: `pcm` then
+ * sample rate.  full_len .. frame_count shard a long file by FRAME RANGE across GPUs: `pcm` then
  * points at sample `pcm_offset` of a file of `full_len` samples and only frames
  * [frame_begin, frame_begin + frame_count) are computed; reflect padding is applied against the
  * true file ends.  All four zero = the whole channel. */
 typedef struct thb_track {
-    const float *pcm; /* host or device */
+    const void *pcm;  /* host or device; f32 samples, or i16 when pcm_format == THB_PCM_I16 */
     uint64_t len;     /* samples available at pcm */
     uint64_t id;
     uint32_t ch;
@@ -77,7 +77,16 @@ typedef struct thb_track {
     uint64_t pcm_offset;
     uint64_t frame_begin;
     uint64_t frame_count; /* 0 = all frames from frame_begin */
+    uint32_t pcm_format;  /* THB_PCM_F32 (0, what Audio.wavs holds, audio.rs:24-30) | THB_PCM_I16 */
+    uint32_t reserved;    /* 0 */
 } thb_track;
+
+/* PCM ingest formats.  THB_PCM_I16 hands over 16-bit PCM as the decoder produced it: the kernels convert on
+ * the fly with the decoder's own rule, sample / 32768 (audio.rs:262-439 via symphonia's i16 -> f32; exact in
+ * f32), so the results equal those of the f32 channel bit for bit while the host->device copy and the HBM read
+ * are half the size. */
+#define THB_PCM_F32 0u
+#define THB_PCM_I16 1u
 
 /* Per-channel result of thb_spec_batch: Array2<f32> (T, B) of calc_spec
  * (spectrogram.rs:187-212).  spec_host, when non-NULL on input, receives the dB values

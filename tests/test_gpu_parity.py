@@ -143,6 +143,56 @@ def test_spec_to_img_kernels_agree_with_oracle(ctx, orc, monkeypatch, shape, row
     ctx.release(901, 0)
 
 
+@pytest.mark.parametrize("setting,n", [
+    (thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128), 48000 * 3 + 17),
+    (thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Linear), 48000 + 1),
+    (thb.SpecSetting(40.0, 4, 1, thb.FreqScale.Mel, 0), 30011),          # win 1920 in n_fft 2048, default mel
+    (thb.SpecSetting(8192 / 48.0, 4, 1, thb.FreqScale.Mel, 64), 70000),  # generic kernel (n_fft 8192)
+    (thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128), 700),   # shorter than one window: edges only
+])
+def test_i16_ingest_is_bit_identical_to_f32(ctx, setting, n):
+    """16-bit PCM handed over as i16 (sample = s / 32768, the decoder's own rule, exact in f32) gives
+    the dB spectrogram of the f32 channel bit for bit, on every kernel (frame pairs, file edges, generic), for host
+    and for device-resident samples, also from an odd (2-byte aligned) start."""
+    import torch
+    rng = np.random.default_rng(n)
+    s16 = rng.integers(-32768, 32768, size=n + 1, dtype=np.int16)
+    s16[n // 3: n // 3 + 4000] = 0   # exact-zero frames (-inf rows) must survive too
+    for off in (0, 1):
+        q = s16[off: off + n]
+        f32 = q.astype(np.float32) / np.float32(32768.0)
+        want = ctx.calc_spec(f32, 48000, setting)
+        got_host = ctx.calc_spec(np.ascontiguousarray(q), 48000, setting)
+        assert got_host.shape == want.shape
+        assert np.array_equal(got_host, want, equal_nan=True), (off, "host")
+        dev = torch.from_numpy(s16.copy()).cuda()[off: off + n]
+        got_dev = ctx.spec_batch([dict(pcm=dev, id=5, ch=0, sr=48000)], setting, want_host=True)[0][2]
+        assert np.array_equal(got_dev, want, equal_nan=True), (off, "device")
+        ctx.release(5, 0)
+
+
+def test_host_pcm_pipeline_equals_device_resident(ctx):
+    """Host channels travel in H2D stages that overlap the kernels of the previous stage (thb_spec_batch); the result
+    must not depend on where the samples were or on how the batch was cut into stages."""
+    import torch
+    setting = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    n = 48000 * 30
+    wavs = [synth_pcm(n + 1000 * c, 48000, c, 0, ZERO_GAP if c == 2 else 0) for c in range(6)]
+    # mixed batch: host f32, host i16, device f32 -- several stages x formats in one call
+    q16 = [np.round(w * 32768.0).astype(np.int16) for w in wavs]
+    assert all(np.array_equal(q.astype(np.float32) / np.float32(32768.0), w) for q, w in zip(q16, wavs))
+    tracks = []
+    for c, w in enumerate(wavs):
+        pcm = w if c % 3 == 0 else (q16[c] if c % 3 == 1 else torch.from_numpy(w).cuda())
+        tracks.append(dict(pcm=pcm, id=c, ch=0, sr=48000))
+    ctx.spec_batch(tracks, setting)
+    mixed = [ctx.spec_read(c, 0) for c in range(6)]
+    ctx.spec_batch([dict(pcm=torch.from_numpy(w).cuda(), id=c, ch=0, sr=48000) for c, w in enumerate(wavs)], setting)
+    for c in range(6):
+        assert np.array_equal(ctx.spec_read(c, 0), mixed[c]), c
+        ctx.release(c, 0)
+
+
 def _tile_fields(b):
     rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
     return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)

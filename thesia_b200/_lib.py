@@ -36,7 +36,11 @@ class Setting(C.Structure):
 class Track(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("len", C.c_uint64), ("id", C.c_uint64), ("ch", C.c_uint32),
                 ("sr", C.c_uint32), ("full_len", C.c_uint64), ("pcm_offset", C.c_uint64),
-                ("frame_begin", C.c_uint64), ("frame_count", C.c_uint64)]
+                ("frame_begin", C.c_uint64), ("frame_count", C.c_uint64), ("pcm_format", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+PCM_F32, PCM_I16 = 0, 1
 
 
 class SpecOut(C.Structure):
@@ -116,7 +120,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.thb_abi_version() != 1:
+        if l.thb_abi_version() != 2:
             raise RuntimeError("libthesia_b200.so ABI version mismatch")
         _lib = l
     return _lib

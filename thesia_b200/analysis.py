@@ -22,7 +22,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import Setting, SpecOut, Track, check, lib
+from ._lib import PCM_F32, PCM_I16, Setting, SpecOut, Track, check, lib
 
 IdCh = Tuple[int, int]
 
@@ -104,6 +104,19 @@ def hz_range_to_idx(freq_scale: int, hz_range: Tuple[float, float], sr: int, n_b
     return a.value, b.value
 
 
+def _ptr_len_fmt(x) -> Tuple[int, int, object, int]:
+    """(address, n_samples, keep-alive, pcm_format) of a 1-D PCM array: int16 arrays / tensors are handed over as
+    THB_PCM_I16 (sample = s / 32768), everything else as float32."""
+    if isinstance(x, np.ndarray) and x.dtype == np.int16:
+        x = np.ascontiguousarray(x).reshape(-1)
+        return x.ctypes.data, x.size, x, PCM_I16
+    if hasattr(x, "data_ptr") and str(x.dtype) == "torch.int16":
+        if not x.is_contiguous() or x.dim() != 1:
+            raise ValueError("PCM tensors must be 1-D contiguous")
+        return x.data_ptr(), x.numel(), x, PCM_I16
+    return _ptr_len(x) + (PCM_F32,)
+
+
 def _ptr_len(x) -> Tuple[int, int, object]:
     """(address, n_samples, keep-alive) of a 1-D float32 numpy array or torch tensor."""
     if isinstance(x, np.ndarray):
@@ -166,10 +179,10 @@ class Context:
         outs = (SpecOut * n)()
         s = setting._c()
         for i, t in enumerate(tracks):
-            addr, ln, k = _ptr_len(t["pcm"])
+            addr, ln, k, fmt = _ptr_len_fmt(t["pcm"])
             keep.append(k)
             arr[i] = Track(addr, ln, int(t["id"]), int(t.get("ch", 0)), int(t["sr"]), int(t.get("full_len", 0)),
-                           int(t.get("pcm_offset", 0)), int(t.get("frame_begin", 0)), int(t.get("frame_count", 0)))
+                           int(t.get("pcm_offset", 0)), int(t.get("frame_begin", 0)), int(t.get("frame_count", 0)), fmt, 0)
         host = []
         if want_host:
             hop, win, n_fft = None, None, None

@@ -132,6 +132,7 @@ struct thb_ctx {
     size_t arena_cap = 0, arena_used = 0;
     cudaEvent_t arena_ev = nullptr;
     cudaEvent_t h2d_ev = nullptr;
+    std::vector<cudaEvent_t> stage_ev;  // one per H2D pipeline stage of thb_spec_batch
 
     // tiles the frame-pair STFT kernel hands back to the scalar kernel (thb_kernels.cuh RescueList)
     uint2 *d_rescue_items = nullptr;
@@ -520,6 +521,7 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     if (ctx->arena_ev) cudaEventDestroy(ctx->arena_ev);
     if (ctx->h2d_ev) cudaEventDestroy(ctx->h2d_ev);
+    for (cudaEvent_t ev : ctx->stage_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -673,13 +675,18 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         uint64_t total_T, f_begin, f_count, full_len;
         const float *d_pcm;
         void *staging;
+        int chunk;       // H2D pipeline stage this channel's samples arrive with (0 for device-resident PCM)
+        bool i16;
     };
     std::vector<Item> items(n);
-    std::map<const Plan *, std::vector<size_t>> groups;
+    // a launch group = one analyzer plan x one PCM format x one H2D pipeline stage
+    using GroupKey = std::tuple<int, const Plan *, bool>;
+    std::map<GroupKey, std::vector<size_t>> groups;
     // ---- validate everything before touching device state ----
     for (size_t i = 0; i < n; i++) {
         const thb_track &t = tracks[i];
         if (!t.pcm) return fail(ctx, THB_ERR_INVALID, "track %zu: pcm is NULL", i);
+        if (t.pcm_format > THB_PCM_I16) return fail(ctx, THB_ERR_INVALID, "track %zu: pcm_format = %u", i, t.pcm_format);
         const uint64_t full_len = t.full_len ? t.full_len : t.len;
         if (full_len < 2) return fail(ctx, THB_ERR_INVALID, "track %zu: %llu samples (need >= 2; the reference's reflect pad is undefined below that)", i, (unsigned long long)full_len);
         if (t.pcm_offset + t.len > full_len) return fail(ctx, THB_ERR_INVALID, "track %zu: slice exceeds the file", i);
@@ -710,13 +717,40 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         }
         it.d_pcm = nullptr;
         it.staging = nullptr;
-        groups[pl].push_back(i);
+        it.i16 = t.pcm_format == THB_PCM_I16;
+        it.chunk = 0;
+    }
+    // H2D pipeline: host channels are cut, in call order, into stages of about kStageBytes; stage c is copied on
+    // the copy stream while the kernels of stage c - 1 run, so only the last stage's compute is exposed.
+    constexpr size_t kStageBytes = size_t(256) << 20;
+    constexpr int kMaxStages = 64;
+    int n_stages = 0;
+    {
+        size_t acc = 0;
+        bool open = false;
+        for (size_t i = 0; i < n; i++) {
+            Item &it = items[i];
+            if (is_device_ptr(tracks[i].pcm)) continue;
+            if (!open || (acc >= kStageBytes && n_stages < kMaxStages)) {
+                n_stages++;
+                acc = 0;
+                open = true;
+            }
+            it.chunk = n_stages;  // stages are numbered from 1; 0 = no copy to wait for
+            acc += tracks[i].len * (it.i16 ? 2 : 4);
+        }
+    }
+    for (size_t i = 0; i < n; i++) groups[GroupKey{items[i].chunk, items[i].plan, items[i].i16}].push_back(i);
+    while (ctx->stage_ev.size() < static_cast<size_t>(n_stages)) {
+        cudaEvent_t ev = nullptr;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->stage_ev.push_back(ev);
     }
     int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * 4 * n + 4096);
     if (rc) return rc;
 
     // ---- device buffers; host PCM goes through stream-ordered staging ----
-    bool any_host = false;
+    const bool any_host = n_stages > 0;
     for (size_t i = 0; i < n; i++) {
         const thb_track &t = tracks[i];
         Item &it = items[i];
@@ -737,16 +771,26 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             CK(cudaMallocAsync(reinterpret_cast<void **>(&sp.d_spec), sizeof(float) * (need ? need : 1), ctx->stream));
             sp.spec_cap = need;
         }
-        if (is_device_ptr(t.pcm)) {
-            it.d_pcm = t.pcm;
+        if (it.chunk == 0) {
+            it.d_pcm = static_cast<const float *>(t.pcm);
         } else {
-            any_host = true;
-            CK(cudaMallocAsync(&it.staging, sizeof(float) * t.len + 64, ctx->stream));
-            CK(cudaMemcpyAsync(it.staging, t.pcm, sizeof(float) * t.len, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMallocAsync(&it.staging, (it.i16 ? 2 : 4) * t.len + 64, ctx->stream));
             it.d_pcm = static_cast<const float *>(it.staging);
         }
     }
-    if (any_host) CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
+    if (any_host) {
+        // the staging buffers exist once ctx->stream reaches this point; the copies then run stage by stage on the
+        // copy stream, each stage followed by its event
+        CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->h2d_ev, 0));
+        for (int c = 1; c <= n_stages; c++) {
+            for (size_t i = 0; i < n; i++)
+                if (items[i].chunk == c)
+                    CK(cudaMemcpyAsync(items[i].staging, tracks[i].pcm, (items[i].i16 ? 2 : 4) * tracks[i].len,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->stage_ev[c - 1], ctx->copy_stream));
+        }
+    }
 
     // ---- descriptors, one array per plan group ----
     // THB_STFT_KERNEL = generic | fast | pair pins one implementation (A/B measurements); default: best
@@ -763,13 +807,17 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         int n_pair = 0, n_edge = 0;
         long long max_pair_frames = 0, max_edge_frames = 0;
         size_t pair_tiles = 0;
+        int stage = 0;
+        bool i16 = false;
     };
     std::vector<Launch> launches;
     size_t max_pair_tiles = 0;
     for (auto &g : groups) {
         thb::TrackDesc *d_desc = nullptr;
         thb::TrackDesc *h = arena_push<thb::TrackDesc>(ctx, g.second.size(), &d_desc);
-        Launch L{g.first, d_desc, static_cast<int>(g.second.size()), 0};
+        Launch L{std::get<1>(g.first), d_desc, static_cast<int>(g.second.size()), 0};
+        L.stage = std::get<0>(g.first);
+        L.i16 = std::get<2>(g.first);
         for (size_t j = 0; j < g.second.size(); j++) {
             const size_t i = g.second[j];
             const thb_track &t = tracks[i];
@@ -783,9 +831,11 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             h[j].n_frames = static_cast<long long>(it.f_count);
             h[j].out = sp.d_spec;
             h[j].minmax = ctx->d_slots + 2 * sp.slot;
+            h[j].pcm_i16 = it.i16 ? 1 : 0;
+            h[j].pad_ = 0;
             L.max_frames = std::max(L.max_frames, h[j].n_frames);
         }
-        const thb::PlanDev &pd = g.first->dev;
+        const thb::PlanDev &pd = L.plan->dev;
         if (want_pair && thb::stft_pair_supported(pd) && thb::stft_fast_supported(pd)) {
             std::vector<thb::TrackDesc> pairs, edges;
             const long long W = pd.win, H = pd.hop, half = W / 2, padl = pd.pad_left;
@@ -798,9 +848,11 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 const long long c2 = f.full_len - W + half, c4 = f.pcm_offset + f.slice_len - 2048 + half + padl;
                 hi = (c2 < 0 || c4 < 0) ? -1 : std::min({hi, c2 / H, c4 / H});
                 long long cnt = hi >= lo ? hi - lo + 1 : 0;
+                // the frame-pair kernel loads sample pairs: 8-byte aligned float2, or 4-byte aligned i16 pairs
                 const uintptr_t addr = reinterpret_cast<uintptr_t>(f.pcm);
-                const bool aligned = (addr & 3) == 0 && (H & 1) == 0 &&
-                                     ((static_cast<long long>(addr >> 2) + lo * H - half - padl - f.pcm_offset) & 1) == 0;
+                const int esz = L.i16 ? 2 : 4;
+                const bool aligned = (addr & (esz - 1)) == 0 && (H & 1) == 0 &&
+                                     ((static_cast<long long>(addr / esz) + lo * H - half - padl - f.pcm_offset) & 1) == 0;
                 cnt = aligned ? (cnt & ~1ll) : 0;
                 if (cnt < 2) {
                     if (f.n_frames) edges.push_back(f);
@@ -864,9 +916,14 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         ctx->launch_count += 1;
     }
 
-    // ---- K1/K2/K3: per (sr, win, n_fft) group ----
+    // ---- K1/K2/K3: per (stage, plan, format) group, in stage order (std::map order) ----
+    int waited = 0;
     for (const Launch &l : launches) {
         const thb::PlanDev &pd = l.plan->dev;
+        if (l.stage > waited) {  // the samples of this stage must have landed
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->stage_ev[l.stage - 1], 0));
+            waited = l.stage;
+        }
         const int chunks = (l.count + 65534) / 65535;
         cudaError_t e = cudaSuccess;
         if (l.n_pair || l.n_edge) {
@@ -880,7 +937,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
                 {
                     ProfScope ps(ctx, kname, 1);  // the frame-pair kernel alone: this is the roofline kernel
-                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, ctx->sm_count, ctx->stream);
+                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, ctx->sm_count, ctx->stream);
                 }
                 if (e == cudaSuccess) {
                     ProfScope ps(ctx, ename, 1);
@@ -926,7 +983,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     }
     // Host buffers belong to the caller again when we return.
     if (any_host_out) CK(cudaStreamSynchronize(ctx->stream));
-    else if (any_host) CK(cudaEventSynchronize(ctx->h2d_ev));
+    else if (any_host) CK(cudaEventSynchronize(ctx->stage_ev[n_stages - 1]));
     return THB_OK;
 }
 
@@ -1212,10 +1269,11 @@ int thb_waveform_level_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, ui
     for (size_t i = 0; i < n; i++) {
         const thb_track &t = tracks[i];
         if (!t.pcm && t.len) return fail(ctx, THB_ERR_INVALID, "track %zu: pcm is NULL", i);
+        if (t.pcm_format != THB_PCM_F32) return fail(ctx, THB_ERR_UNSUPPORTED, "track %zu: waveform tiles take f32 PCM", i);
         bytes[i] = level_bytes(t.len, level);
         if (host_out && host_out[i] && caps && caps[i] < bytes[i])
             return fail(ctx, THB_ERR_SMALL_BUFFER, "track %zu: need %llu bytes", i, (unsigned long long)bytes[i]);
-        const float *d_pcm = t.pcm;
+        const float *d_pcm = static_cast<const float *>(t.pcm);
         if (t.len && !is_device_ptr(t.pcm)) {
             CK(cudaMallocAsync(&staging[i], sizeof(float) * t.len + 64, ctx->stream));
             CK(cudaMemcpyAsync(staging[i], t.pcm, sizeof(float) * t.len, cudaMemcpyHostToDevice, ctx->stream));

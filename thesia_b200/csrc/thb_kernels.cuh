@@ -8,7 +8,7 @@ namespace thb {
 
 // One channel (or one frame-range shard of a channel) as the STFT kernels see it.
 struct TrackDesc {
-    const float *pcm;        // device; pcm[0] is sample `pcm_offset` of the file
+    const float *pcm;        // device; pcm[0] is sample `pcm_offset` of the file (int16_t samples when pcm_i16)
     long long pcm_offset;
     long long slice_len;     // samples available at pcm
     long long full_len;      // samples in the whole file (reflect happens at 0 and full_len-1)
@@ -16,6 +16,8 @@ struct TrackDesc {
     long long n_frames;      // frames to compute
     float *out;              // (n_frames, n_bins) row-major dB
     float *minmax;           // 2 floats: {max, -min} of this channel (atomic-max accumulated)
+    int pcm_i16;             // 1: 16-bit PCM, sample value = s / 32768 (exact)
+    int pad_;
 };
 
 // Everything that depends only on (sr, win, n_fft, n_mel): uploaded once per SrWinNfft key.
@@ -68,6 +70,12 @@ struct EnvDesc {
     uint8_t *out;        // device, tiles of this level concatenated in wire format
 };
 
+// sample `idx` of a channel's slice as f32: 16-bit PCM converts as s / 32768 (exact)
+__device__ __forceinline__ float pcm_sample(const TrackDesc &d, long long idx) {
+    if (d.pcm_i16) return static_cast<float>(__ldg(reinterpret_cast<const short *>(d.pcm) + idx)) * 3.0517578125e-05f;
+    return __ldg(d.pcm + idx);
+}
+
 // ---- launchers (all asynchronous on `st`) ----
 // generic shared-memory path, any power-of-two n_fft in [4, 32768]
 cudaError_t launch_stft_generic(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
@@ -79,8 +87,9 @@ cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int
 
 // two frames per warp in packed f32x2 arithmetic, n_fft == 2048
 bool stft_pair_supported(const PlanDev &plan);
+// (every descriptor of one launch holds the same PCM format: pcm_i16 says which)
 cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
-                             int sm_count, cudaStream_t st);
+                             bool pcm_i16, int sm_count, cudaStream_t st);
 // frames per work item of the frame-pair kernel (a multiple of twice its warps per CTA)
 int stft_pair_tile_frames();
 // the scalar kernel over the tiles on a rescue list (persistent grid; a no-op when the list is empty)

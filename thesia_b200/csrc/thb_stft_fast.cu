@@ -162,7 +162,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
                                   first + 2048 <= d.pcm_offset + d.slice_len;
             if (interior) {
                 const float *src = d.pcm + (first - d.pcm_offset) + 2 * lane;
-                if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+                if (d.pcm_i16) {
+                    const long long at = (first - d.pcm_offset) + 2 * lane;
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; n1++)
+                        v[n1] = make_float2(pcm_sample(d, at + 64 * n1), pcm_sample(d, at + 64 * n1 + 1));
+                } else if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
 #pragma unroll
                     for (int n1 = 0; n1 < 32; n1++) v[n1] = __ldg(reinterpret_cast<const float2 *>(src + 64 * n1));
                 } else {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
                     float x = 0.0f;
                     if (a >= 0 && a < p.win) {
                         const long long s = reflect_index(tap0 + a, d.full_len);
-                        x = __ldg(&d.pcm[s - d.pcm_offset]) * sm.wpad[pos];
+                        x = pcm_sample(d, s - d.pcm_offset) * sm.wpad[pos];
                     }
                     stage[pos] = x;
                 }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(1024) stft_generic_kernel(const PlanDev p,
                 if (a >= 0 && a < p.win) {
                     long long s = s0 + a;
                     if (!interior) s = reflect_index(s, d.full_len);
-                    x = __ldg(&d.pcm[s - d.pcm_offset]) * __ldg(&p.window[a]);
+                    x = pcm_sample(d, s - d.pcm_offset) * __ldg(&p.window[a]);
                 }
                 v[e] = x;
             }

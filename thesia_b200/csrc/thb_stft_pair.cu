@@ -129,7 +129,11 @@ __device__ __forceinline__ PairSmem carve(unsigned char *raw, int tile_f2) {
 // Contract (the launcher guarantees it, thb_api.cu): every frame of every descriptor is interior (no reflect
 // padding, the whole n_fft span inside the slice), 8-byte aligned, and n_frames is even.  Edge frames, odd
 // leftovers and unaligned channels go through the scalar kernel.
-template <bool MEL, int NW>
+// I16: the channels hold 16-bit PCM.  A 32-bit load brings a sample pair; each half is sign-extended and
+// converted (I2F, exact), and the 2^-15 of "s / 32768" rides on the window table, so every product equals the f32
+// channel's bit for bit.  (Not the 1.5 * 2^23 exponent-pasting trick: the compiler distributes the window over its
+// subtraction, (x - M) w -> fma(x, w, -M w), which is no longer exact.)
+template <bool MEL, int NW, bool I16>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
                                                                         long long n_items, RescueList rescue) {
@@ -138,8 +142,14 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
 
     const int tile_f2 = tile_elems(p);
     const PairSmem sm = carve<NW>(smem_raw, tile_f2);
-    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
-        reinterpret_cast<float4 *>(sm.wpad)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_wpad) + i);
+    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) {
+        float4 w = __ldg(reinterpret_cast<const float4 *>(p.fast_wpad) + i);
+        if (I16) {
+            const float k = 3.0517578125e-05f;  // 2^-15, exact
+            w = make_float4(w.x * k, w.y * k, w.z * k, w.w * k);
+        }
+        reinterpret_cast<float4 *>(sm.wpad)[i] = w;
+    }
     for (int i = threadIdx.x; i < (31 * 32 + 16 * 32) / 2; i += blockDim.x)
         reinterpret_cast<float4 *>(sm.tw1)[i] = __ldg(reinterpret_cast<const float4 *>(p.fast_tw) + i);
     for (int i = threadIdx.x; i < NW * tile_f2 / 2; i += blockDim.x)
@@ -173,15 +183,33 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             cx v[32];
             // ---- load + window: v[n1] = z[32 n1 + lane] of both frames ----
             const long long first_a = (d.frame_begin + fa) * p.hop - half - p.pad_left;  // file index of FFT position 0
-            const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
-            const float *src_b = src_a + p.hop;
+            if constexpr (I16) {
+                const uint32_t *src_a = reinterpret_cast<const uint32_t *>(reinterpret_cast<const short *>(d.pcm) +
+                                                                           (first_a - d.pcm_offset) + 2 * lane);
+                const uint32_t *src_b = src_a + (p.hop >> 1);
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1));
-                const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 64 * n1));
-                const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
-                v[n1].re = make_float2(xa.x * w.x, xb.x * w.x);
-                v[n1].im = make_float2(xa.y * w.y, xb.y * w.y);
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const uint32_t wa = __ldg(src_a + 32 * n1), wb = __ldg(src_b + 32 * n1);
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    // sign-extend each half (low: 16-bit cast, high: arithmetic shift), I2F converts it (exact)
+                    const float a_re = static_cast<float>(static_cast<int>(static_cast<short>(wa & 0xffffu)));
+                    const float a_im = static_cast<float>(static_cast<int>(wa) >> 16);
+                    const float b_re = static_cast<float>(static_cast<int>(static_cast<short>(wb & 0xffffu)));
+                    const float b_im = static_cast<float>(static_cast<int>(wb) >> 16);
+                    v[n1].re = make_float2(a_re * w.x, b_re * w.x);
+                    v[n1].im = make_float2(a_im * w.y, b_im * w.y);
+                }
+            } else {
+                const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
+                const float *src_b = src_a + p.hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1));
+                    const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 64 * n1));
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    v[n1].re = make_float2(xa.x * w.x, xb.x * w.x);
+                    v[n1].im = make_float2(xa.y * w.y, xb.y * w.y);
+                }
             }
             // ---- pass 1: DFT over n1, twiddle, transpose (real plane, then imaginary plane) ----
             dft32p(v);
@@ -322,11 +350,11 @@ int pair_warps() {
     return (w == 8 || w == 10 || w == 12) ? w : 12;
 }
 
-template <bool MEL, int NW>
+template <bool MEL, int NW, bool I16>
 cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
                       cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
-    auto kern = stft2048_pair_kernel<MEL, NW>;
+    auto kern = stft2048_pair_kernel<MEL, NW, I16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
@@ -347,17 +375,21 @@ bool stft_pair_supported(const PlanDev &p) {
 
 // rescue.tile_frames must be stft_pair_tile_frames() and rescue.tiles_per_track = ceil(max n_frames / tile_frames)
 cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
-                             int sm_count, cudaStream_t st) {
+                             bool pcm_i16, int sm_count, cudaStream_t st) {
     if (n_tracks <= 0 || rescue.tiles_per_track == 0) return cudaSuccess;
     const int nw = pair_warps();
-    if (plan.n_mel) {
-        if (nw == 8) return launch_nw<true, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-        if (nw == 10) return launch_nw<true, 10>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-        return launch_nw<true, 12>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    if (pcm_i16) {  // the ingest variant exists for the tuned warp count only
+        if (plan.n_mel) return launch_nw<true, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<false, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
-    if (nw == 8) return launch_nw<false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-    if (nw == 10) return launch_nw<false, 10>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-    return launch_nw<false, 12>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    if (plan.n_mel) {
+        if (nw == 8) return launch_nw<true, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        if (nw == 10) return launch_nw<true, 10, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<true, 12, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
+    if (nw == 8) return launch_nw<false, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    if (nw == 10) return launch_nw<false, 10, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    return launch_nw<false, 12, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
 }
 
 }  // namespace thb
