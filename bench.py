@@ -311,8 +311,9 @@ def run_b200(args) -> None:
             def step_e2e():
                 ctx.spec_batch(tracks_host, setting)
                 r = ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
-                for c in range(n_ch_total):
-                    ctx.img_read_into(c // N_CH, c % N_CH, host_img_p.value + 2 * c * img_stride, img_stride)
+                ctx.img_read_batch_into([(c // N_CH, c % N_CH) for c in range(n_ch_total)],
+                                        [host_img_p.value + 2 * c * img_stride for c in range(n_ch_total)],
+                                        [img_stride] * n_ch_total)
                 return r
 
             e2e_steps = max(1, min(args.steps, args.e2e_steps))

@@ -181,6 +181,10 @@ int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length,
 /* TrackManager::get_spectrogram (mod.rs:133-135): copy image (H, W = T) to the host */
 int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t cap,
                  uint64_t *height, uint64_t *width);
+/* the images of n (id, ch) in one go: every copy is queued before the one wait (what a redraw of all tracks asks
+ * for; TrackManager.spec_imgs as a whole).  outs[i] is HOST memory for (H_i, T_i) u16, caps[i] its size in pixels. */
+int thb_img_read_batch(thb_ctx *ctx, size_t n, const uint64_t *ids, const uint32_t *chs, uint16_t *const *outs,
+                       const uint64_t *caps);
 /* device view of a retained image: rows are `pitch` u16 apart */
 int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr,
                        uint64_t *height, uint64_t *width, uint64_t *pitch);

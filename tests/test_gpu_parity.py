@@ -367,6 +367,15 @@ def test_global_minmax_and_images_batch(ctx, orc):
         diff = np.abs(img.astype(np.int32) - o_imgs[j].astype(np.int32))
         assert diff.max() <= 1, (k, diff.max())
         assert (img == 0).any() == (o_imgs[j] == 0).any()
+    # all images in one batched read == the per-image reads
+    keys = sorted(wavs)
+    bufs = [np.zeros((128, specs[k].shape[0]), np.uint16) for k in keys]
+    ctx.img_read_batch_into(keys, [b.ctypes.data for b in bufs], [b.size for b in bufs])
+    for k, b in zip(keys, bufs):
+        assert np.array_equal(b, ctx.img_read(*k)), k
+    with pytest.raises(thb.ThbError) as e:
+        ctx.img_read_batch_into(keys[:2], [bufs[0].ctypes.data, bufs[1].ctypes.data], [bufs[0].size, 5])
+    assert e.value.code == _lib.THB_ERR_SMALL_BUFFER
     # set_dB_range only re-quantises (mod.rs:123-126)
     mn2, mx2 = ctx.update_spec_imgs(40.0, 258)
     assert (mn2, mx2) == (-40.0, 0.0)

@@ -81,6 +81,7 @@ SIGNATURES = {
     "thb_spec_to_img": (_i, [_vp, _u64, _u32, _u64, _u64, _f32, _f32, _u32, _vp, _u64]),
     "thb_update_spec_imgs": (_i, [_vp, _f32, _u32, _u32, _P(_u64), C.c_size_t, _P(_f32), _P(_f32)]),
     "thb_img_read": (_i, [_vp, _u64, _u32, _vp, _u64, _P(_u64), _P(_u64)]),
+    "thb_img_read_batch": (_i, [_vp, C.c_size_t, _P(_u64), _P(_u32), _P(_vp), _P(_u64)]),
     "thb_img_device_ptr": (_i, [_vp, _u64, _u32, _P(_vp), _P(_u64), _P(_u64), _P(_u64)]),
     "thb_waveform_tile": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),
     "thb_waveform_level": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),

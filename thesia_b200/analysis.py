@@ -268,6 +268,15 @@ class Context:
         check(lib().thb_img_read(self._h, id, ch, out.ctypes.data, out.size, None, None), self._h)
         return out
 
+    def img_read_batch_into(self, id_chs: Sequence[IdCh], addrs: Sequence[int], caps: Sequence[int]) -> None:
+        """thb_img_read_batch: all copies queued, one wait."""
+        n = len(id_chs)
+        ids = (C.c_uint64 * n)(*[int(i) for i, _ in id_chs])
+        chs = (C.c_uint32 * n)(*[int(c) for _, c in id_chs])
+        outs = (C.c_void_p * n)(*[int(a) for a in addrs])
+        cps = (C.c_uint64 * n)(*[int(c) for c in caps])
+        check(lib().thb_img_read_batch(self._h, n, ids, chs, outs, cps), self._h)
+
     def img_read_into(self, id: int, ch: int, addr: int, cap: int) -> Tuple[int, int]:
         h, w = C.c_uint64(), C.c_uint64()
         check(lib().thb_img_read(self._h, id, ch, addr, cap, C.byref(h), C.byref(w)), self._h)

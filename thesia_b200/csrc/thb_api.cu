@@ -1232,6 +1232,29 @@ int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t
     return THB_OK;
 }
 
+int thb_img_read_batch(thb_ctx *ctx, size_t n, const uint64_t *ids, const uint32_t *chs, uint16_t *const *outs,
+                       const uint64_t *caps) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return THB_OK;
+    if (!ids || !chs || !outs || !caps) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; i++) {  // validate everything before the first copy
+        const Spec *sp = find_spec(ctx, ids[i], chs[i]);
+        if (!sp || !sp->d_img) return fail(ctx, THB_ERR_NOT_FOUND, "no image for (%llu, %u)", (unsigned long long)ids[i], chs[i]);
+        if (!outs[i] || caps[i] < sp->img_H * sp->T)
+            return fail(ctx, THB_ERR_SMALL_BUFFER, "image %zu: need %llu pixels", i, (unsigned long long)(sp->img_H * sp->T));
+    }
+    for (size_t i = 0; i < n; i++) {
+        const Spec *sp = find_spec(ctx, ids[i], chs[i]);
+        if (sp->img_H && sp->T)
+            CK(cudaMemcpy2DAsync(outs[i], sizeof(uint16_t) * sp->T, sp->d_img, sizeof(uint16_t) * sp->img_pitch,
+                                 sizeof(uint16_t) * sp->T, sp->img_H, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
 int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr, uint64_t *height, uint64_t *width,
                        uint64_t *pitch) {
     if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");

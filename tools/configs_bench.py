@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Kernel timings of BASELINE.json's five configurations on one GPU (device-resident synthetic PCM, CUDA events
+through the library's per-kernel profile hooks).  Not the bench line (bench.py is, on C3): the survey table behind
+DESIGN.md's per-config numbers.  One JSON object per line on stdout and in gpurun_out/configs.jsonl.
+
+    python tools/configs_bench.py [--only C1,C2,C4L,C4M,C5] [--reps 3]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import torch  # noqa: E402
+
+import thesia_b200 as thb  # noqa: E402
+
+HBM_GBS = 6552.3
+try:
+    HBM_GBS = float(json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:
+    pass
+
+
+def synth(ctx, n_ch, n, sr):
+    row = (n + 63) // 64 * 64
+    pcm = torch.empty((n_ch, row), dtype=torch.float32, device="cuda")
+    for c in range(n_ch):
+        ctx.synth_pcm(pcm[c, :n], sr, c // 2, c % 2, 0)
+    ctx.synchronize()
+    return pcm
+
+
+def stft_case(ctx, name, n_ch, seconds, sr, win_ms, t_overlap, scale, n_mel, reps, out):
+    n = int(sr * seconds)
+    setting = thb.SpecSetting(win_ms, t_overlap, 1, scale, n_mel)
+    hop, win, n_fft = setting.calc_framing_params(sr)
+    T = thb.n_frames(n, win, hop)
+    B = setting.n_bins(sr)
+    pcm = synth(ctx, n_ch, n, sr)
+    tracks = [dict(pcm=pcm[c, :n], id=c, ch=0, sr=sr) for c in range(n_ch)]
+    kname = "stft_mel_db" if scale == thb.FreqScale.Mel else "stft_lin_db"
+    ctx.spec_batch(tracks, setting)  # warm-up
+    ctx.synchronize()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    for _ in range(reps):
+        ctx.spec_batch(tracks, setting)
+    ctx.synchronize()
+    ms = (ctx.profile_get(kname)[0] + ctx.profile_get(kname + "_edges")[0]) / reps
+    ctx.profile_enable(False)
+    alg = n_ch * (4 * n + 4 * T * B)
+    flops = n_ch * T * (2.5 * n_fft * (n_fft.bit_length() - 1) + 4 * (n_fft // 2 + 1) + 4 * (n_fft // 2 + 1) + B)
+    rec = {"config": name, "channels": n_ch, "seconds": seconds, "sr": sr, "win": win, "hop": hop, "n_fft": n_fft, "bins": B,
+           "frames": n_ch * T, "stft_ms": ms, "audio_hours_per_s": n_ch * seconds / 3600.0 / (ms * 1e-3),
+           "Mframes_per_s": n_ch * T / ms / 1e3, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
+           "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS, "fp32_tflops": flops / (ms * 1e-3) / 1e12}
+    ctx.release_all()
+    del pcm
+    torch.cuda.empty_cache()
+    out(rec)
+
+
+def envelope_case(ctx, n_ch, seconds, sr, reps, out):
+    n = int(sr * seconds)
+    pcm = synth(ctx, n_ch, n, sr)
+    wavs = [pcm[c, :n] for c in range(n_ch)]
+    for level in range(9, 16):
+        ctx.waveform_level_batch(wavs, 1, level, want_host=False)
+        ctx.synchronize()
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        for _ in range(reps):
+            ctx.waveform_level_batch(wavs, 1, level, want_host=False)
+        ctx.synchronize()
+        ms = ctx.profile_get("envelope")[0] / reps
+        ctx.profile_enable(False)
+        bins = -(-n // (1 << level))
+        tiles = -(-bins // 1024)
+        alg = n_ch * (4 * n + 12 * bins + 24 * tiles)
+        out({"config": "C5", "level": level, "columns_per_channel": bins, "channels": n_ch, "samples_per_channel": n,
+             "envelope_ms": ms, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS,
+             "audio_hours_per_s": n_ch * seconds / 3600.0 / (ms * 1e-3)})
+    del pcm
+    torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="C1,C2,C2D,C3D,C4L,C4M,C5")
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    only = set(a.only.split(","))
+    stream = torch.cuda.current_stream()
+    ctx = thb.Context(0, stream.cuda_stream)
+    outdir = Path("gpurun_out")
+    outdir.mkdir(exist_ok=True)
+    fh = open(outdir / "configs.jsonl", "a")
+
+    def out(rec):
+        line = json.dumps(rec)
+        print(line, flush=True)
+        fh.write(line + "\n")
+        fh.flush()
+
+    Mel, Lin = thb.FreqScale.Mel, thb.FreqScale.Linear
+    if "C1" in only:   # one 44 s mono file, win 2048 hop 512, linear dB
+        stft_case(ctx, "C1 linear 2048/512, 2 113 529 samples mono", 1, 2113529 / 48000.0, 48000, 2048 / 48.0, 4, Lin, 0, a.reps, out)
+    if "C2" in only:   # one 1-hour mono track, hop 256, mel 128
+        stft_case(ctx, "C2 mel128 2048/256, 1 h mono", 1, 3600, 48000, 2048 / 48.0, 8, Mel, 128, a.reps, out)
+    if "C2D" in only:  # same with the reference's default mel size (347 bands)
+        stft_case(ctx, "C2 mel-default(347) 2048/256, 1 h mono", 1, 3600, 48000, 2048 / 48.0, 8, Mel, 0, a.reps, out)
+    if "C3D" in only:  # the reference's default setting (40 ms / 4 -> win 1920 hop 480, default mel) on 32 x 10 min
+        stft_case(ctx, "C3' default setting 40 ms/4 (1920/480/2048, mel 347), 32 ch x 10 min", 32, 600, 48000, 40.0, 4, Mel, 0, a.reps, out)
+    if "C4M" in only:  # large FFT, default mel (1621 bands), 2 of the 8 one-hour 96 kHz tracks
+        stft_case(ctx, "C4 mel-default 16384/1024 @96 kHz, 2 x 1 h", 2, 3600, 96000, 16384 / 96.0, 16, Mel, 0, max(1, a.reps - 1), out)
+    if "C4L" in only:  # large FFT, linear (8193 bins: 11 GB of f32 per track), 1 track
+        stft_case(ctx, "C4 linear 16384/1024 @96 kHz, 1 x 1 h", 1, 3600, 96000, 16384 / 96.0, 16, Lin, 0, max(1, a.reps - 1), out)
+    if "C5" in only:
+        envelope_case(ctx, 128, 600, 48000, a.reps, out)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
