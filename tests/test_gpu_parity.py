@@ -319,6 +319,36 @@ def test_frame_range_shards_equal_whole(ctx):
     assert e.value.code == _lib.THB_ERR_INVALID
 
 
+@pytest.mark.parametrize("scale,n_mel", [(thb.FreqScale.Linear, 0), (thb.FreqScale.Mel, 0), (thb.FreqScale.Mel, 128)])
+def test_large_fft_kernel_shards_edges_and_i16(ctx, orc, scale, n_mel):
+    """n_fft 16384 (config C4) runs on the two-frame large-FFT kernel, which handles every frame itself: file edges,
+    odd frame counts, frame-range shards (bit-equal to the whole file) and 16-bit PCM (bit-equal to f32)."""
+    from thesia_b200.sharding import split_frames
+    sr = 96000
+    s = thb.SpecSetting(16384 / 96.0, 16, 1, scale, n_mel)
+    hop, win, n_fft = s.calc_framing_params(sr)
+    assert (hop, win, n_fft) == (1024, 16384, 16384)
+    x = synth_pcm(100003, sr, 5, 0, ZERO_GAP)
+    whole = ctx.calc_spec(x, sr, s, id=30)
+    assert whole.shape[0] == orc.n_frames(x.size, win, hop) and whole.shape[0] % 2 == 0  # 98 frames
+    check_spec(orc, whole, x, sr, s, "big-whole")
+    odd = ctx.calc_spec(x[:100003 - 1024], sr, s, id=31)  # 97 frames: the last one is paired with itself
+    assert odd.shape[0] == whole.shape[0] - 1
+    check_spec(orc, odd, x[:100003 - 1024], sr, s, "big-odd")
+    for parts in (2, 3, 5):
+        units = split_frames(32, 0, sr, x.size, win, hop, parts)
+        pieces = []
+        for k, u in enumerate(units):
+            tr = dict(pcm=x[u.pcm_lo:u.pcm_hi].copy(), id=200 + k, ch=0, sr=sr, full_len=x.size, pcm_offset=u.pcm_lo,
+                      frame_begin=u.frame_begin, frame_count=u.frame_count)
+            pieces.append(ctx.spec_batch([tr], s, want_host=True)[0][2])
+        assert np.array_equal(np.concatenate(pieces, axis=0), whole, equal_nan=True), parts
+    q = np.round(x * 32768.0).astype(np.int16)
+    assert np.array_equal(q.astype(np.float32) / np.float32(32768.0), x)
+    assert np.array_equal(ctx.calc_spec(q, sr, s, id=33), whole, equal_nan=True)
+    ctx.release_all()
+
+
 def test_error_behaviour(ctx):
     with pytest.raises(thb.ThbError) as e:
         ctx.calc_spec(np.zeros(1, np.float32), 48000, thb.SpecSetting())

@@ -338,6 +338,73 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         d.mi_max_reach = static_cast<int>(mi.max_reach);
         if ((rc = upload(ctx, pl.get(), mi_blob, &d.mi_blob))) return rc;
     }
+    d.big_wpad = nullptr;
+    d.big_tw = nullptr;
+    d.big_pieces = nullptr;
+    d.big_w = nullptr;
+    d.big_pptr = nullptr;
+    d.big_n_pieces = 0;
+    std::vector<float> bwpad, btw;
+    std::vector<uint32_t> bpieces, bpptr;
+    std::vector<float> bgw;
+    if (d.n_fft == 16384) {
+        // tables of the two-frame large-FFT kernel (thb_stft_big.cu)
+        bwpad.assign(16384, 0.0f);
+        for (int a = 0; a < d.win; a++) bwpad[a + d.pad_left] = 0.5f * win[a];
+        // [31][16] W_512^(n2 k1), k1 = 1..31; [32][16] W_8192^(n3 k1); [16][16] W_256^(n3 k2)
+        btw.resize(2 * (31 * 16 + 32 * 16 + 16 * 16));
+        const double tau = 6.283185307179586476925286766559;
+        auto put_tw = [&](size_t at, long long num, long long den) {
+            const double a = -tau * static_cast<double>(num % den) / static_cast<double>(den);
+            btw[2 * at] = static_cast<float>(std::cos(a));
+            btw[2 * at + 1] = static_cast<float>(std::sin(a));
+        };
+        for (int k1 = 1; k1 < 32; k1++)
+            for (int n2 = 0; n2 < 16; n2++) put_tw((k1 - 1) * 16 + n2, n2 * k1, 512);
+        for (int k1 = 0; k1 < 32; k1++)
+            for (int n3 = 0; n3 < 16; n3++) put_tw(31 * 16 + k1 * 16 + n3, n3 * k1, 8192);
+        for (int k2 = 0; k2 < 16; k2++)
+            for (int n3 = 0; n3 < 16; n3++) put_tw(31 * 16 + 32 * 16 + k2 * 16 + n3, n3 * k2, 256);
+        if ((rc = upload(ctx, pl.get(), bwpad, &d.big_wpad))) return rc;
+        const float *btwp = nullptr;
+        if ((rc = upload(ctx, pl.get(), btw, &btwp))) return rc;
+        d.big_tw = reinterpret_cast<const float2 *>(btwp);
+        if (d.n_mel) {
+            // Band-major pieces of <= 32 bins.  32 consecutive pieces form a group that one warp walks in lock step:
+            // the group's weights are stored step-major ([step][lane], zero padded to the longest piece), so every
+            // step is one coalesced 128-byte load.
+            const thb::MelBank mb = thb::mel_bank(sr, f.n_fft, s.n_mel);
+            bpptr.assign(mb.n_mel + 1, 0);
+            std::vector<uint32_t> p_start, p_len, p_wofs;
+            for (uint32_t m = 0; m < mb.n_mel; m++) {
+                const uint32_t len = mb.ptr[m + 1] - mb.ptr[m];
+                for (uint32_t o = 0; o < len; o += 32) {
+                    p_start.push_back(mb.k0[m] + o);
+                    p_len.push_back(std::min<uint32_t>(32, len - o));
+                    p_wofs.push_back(mb.ptr[m] + o);
+                }
+                bpptr[m + 1] = static_cast<uint32_t>(p_start.size());
+            }
+            const size_t n_pieces = p_start.size(), n_groups = (n_pieces + 31) / 32;
+            d.big_n_pieces = static_cast<int>(n_pieces);
+            bpieces.assign(n_groups * 32 + 2 * n_groups, 0);  // [piece] first bin, then per group {steps, weight offset}
+            for (size_t g = 0; g < n_groups; g++) {
+                uint32_t T = 0;
+                for (size_t q = 32 * g; q < std::min(n_pieces, 32 * g + 32); q++) T = std::max(T, p_len[q]);
+                bpieces[n_groups * 32 + 2 * g] = T;
+                bpieces[n_groups * 32 + 2 * g + 1] = static_cast<uint32_t>(bgw.size());
+                bgw.resize(bgw.size() + static_cast<size_t>(T) * 32, 0.0f);
+                for (size_t q = 32 * g; q < std::min(n_pieces, 32 * g + 32); q++) {
+                    bpieces[q] = p_start[q];
+                    for (uint32_t i = 0; i < p_len[q]; i++)
+                        bgw[bpieces[n_groups * 32 + 2 * g + 1] + static_cast<size_t>(i) * 32 + (q - 32 * g)] = mb.w[p_wofs[q] + i];
+                }
+            }
+            if ((rc = upload(ctx, pl.get(), bpieces, &d.big_pieces))) return rc;
+            if ((rc = upload(ctx, pl.get(), bgw, &d.big_w))) return rc;
+            if ((rc = upload(ctx, pl.get(), bpptr, &d.big_pptr))) return rc;
+        }
+    }
     d.fast_wpad = nullptr;
     d.fast_tw = nullptr;
     std::vector<float> wpad, ftw;
@@ -796,6 +863,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     // THB_STFT_KERNEL = generic | fast | pair pins one implementation (A/B measurements); default: best
     const char *force = getenv("THB_STFT_KERNEL");
     const bool want_pair = !force || !strcmp(force, "pair"), want_fast = want_pair || !strcmp(force, "fast");
+    const bool want_big = !force || !strcmp(force, "big");
     struct Launch {
         const Plan *plan;
         thb::TrackDesc *d_desc;  // every channel of the group, whole frame range
@@ -950,7 +1018,9 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             }
         } else {
             ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", chunks);
-            if (want_fast && thb::stft_fast_supported(pd))
+            if (want_big && thb::stft_big_supported(pd))
+                e = thb::launch_stft_big(pd, l.d_desc, l.count, l.max_frames, ctx->sm_count, ctx->stream);
+            else if (want_fast && thb::stft_fast_supported(pd))
                 e = thb::launch_stft_fast(pd, l.d_desc, l.count, l.max_frames, ctx->sm_count, ctx->stream);
             else
                 e = thb::launch_stft_generic(pd, l.d_desc, l.count, l.max_frames, ctx->stream);

@@ -41,6 +41,14 @@ struct PlanDev {
     int mi_words;                     // size of mi_blob in 32-bit words
     int mi_groups, mi_min_start, mi_max_reach;
     const uint32_t *mi_blob;
+    // n_fft == 16384 two-frame path (thb_stft_big.cu); null otherwise
+    const float *big_wpad;            // [16384] 0.5 * window centred in the FFT buffer, zeros outside
+    const float2 *big_tw;             // [31][16] W_512^(n2 k1); [32][16] W_8192^(n3 k1); [16][16] W_256^(n3 k2)
+    // mel: band-major pieces of <= 32 bins, 32 consecutive pieces = one warp-wide group
+    const uint32_t *big_pieces;       // [32 G] first bin of every piece, then [G] {steps, offset into big_w}
+    const float *big_w;               // per group [steps][32 lanes], zero padded
+    const uint32_t *big_pptr;         // [n_mel + 1] pieces of band m: big_pptr[m] .. big_pptr[m + 1]
+    int big_n_pieces;
 };
 
 // Tiles (tile_frames consecutive frames of one descriptor) that the frame-pair kernel could not finish
@@ -84,6 +92,11 @@ cudaError_t launch_stft_generic(const PlanDev &plan, const TrackDesc *d_tracks, 
 bool stft_fast_supported(const PlanDev &plan);
 cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks,
                              long long max_frames, int sm_count, cudaStream_t st);
+
+// two frames per CTA in packed f32x2 arithmetic, n_fft == 16384 (handles every frame itself: edges, 16-bit PCM)
+bool stft_big_supported(const PlanDev &plan);
+cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
+                            int sm_count, cudaStream_t st);
 
 // two frames per warp in packed f32x2 arithmetic, n_fft == 2048
 bool stft_pair_supported(const PlanDev &plan);

@@ -1,0 +1,335 @@
+// thb_stft_big.cu -- K1/K2/K3 for n_fft == 16384 (BASELINE config 4: win 16384, hop 1024, 96 kHz): the large-FFT
+// shared-memory path.  One CTA of 256 threads transforms TWO consecutive frames at once in packed f32x2 arithmetic
+// (thb_packed.cuh: .x = frame A, .y = frame B).
+//
+// The frame is packed as 8192 complex z[m] = x[2m] + i x[2m+1]; 8192 = 32 x 16 x 16:
+//   step 1  thread t holds z[256 n1 + t], n1 = 0..31 (coalesced 8-byte loads straight from the PCM, window folded in):
+//           32-point DFT in registers, twiddle W_512^(n2 k1), 16-byte stores to shared memory
+//   step 2  thread (k1, n3) x 2: 16-point DFT over n2, twiddle W_8192^(n3 (k1 + 32 k2)) as the product of two small
+//           shared-memory tables, stored back in place
+//   step 3  thread (k1, k2) x 2: 16-point DFT over n3 -> Z[k1 + 32 k2 + 512 k3]; after a barrier the spectrum is laid
+//           out in natural order (one pad element every 32) so that the real split reads Z[k] and Z[8192 - k]
+//           conflict-free and the dB rows leave as coalesced stores
+//   split   X[k], X[8192 - k] from Z[k], Z[8192 - k] (k = 0 pairs with itself and yields bins 0 and 8192),
+//           |X|^2 -> dB (linear) or |X| -> back into the FFT buffer, in place (mel)
+//   mel     band-major pieces of <= 32 bins, 32 pieces per warp in lock step (coalesced step-major weights), partial
+//           sums added per band in ascending-bin order
+// Every 16-byte shared-memory element is {re.A, re.B, im.A, im.B}; rows of 16 elements are padded to 17, which keeps
+// the 128-bit accesses of all three steps on distinct bank groups.  Every frame of a channel goes through this one
+// kernel (file edges take a reflect-indexed load, utils.rs:111-137, an odd last frame is paired with itself), so a
+// frame's result does not depend on how a file is sharded.
+//
+//   perform_stft (stft.rs:16-149), Complex::norm (spectrogram.rs:200), linspec.dot(mel_fb) (spectrogram.rs:207),
+//   dB_from_amp (decibel.rs:198-202), find_min_max (mod.rs:169-178).
+#include "thb_packed.cuh"
+
+#include <type_traits>
+
+namespace thb {
+
+namespace {
+
+using namespace packed;
+
+constexpr int kNC = 8192;        // complex points
+constexpr int kThreads = 256;
+constexpr int kRow17 = 17;       // padded row of 16 elements
+constexpr int kPairsPerItem = 8; // frame pairs a CTA takes at a time
+// element index of A[k1][x][y] (steps 1-3) and of Z[k] (natural order)
+__device__ __forceinline__ int idx3(int k1, int x, int y) { return k1 * (16 * kRow17) + x * kRow17 + y; }
+__device__ __forceinline__ int idxn(int k) { return k + (k >> 5); }
+constexpr int kBufElems = 32 * 16 * kRow17;  // 8704 elements of 16 bytes = 136 KB
+static_assert(kBufElems >= kNC + kNC / 32, "the natural-order layout (8448 elements) fits the same buffer");
+
+struct alignas(16) Elem {
+    float2 re, im;
+};
+
+__device__ __forceinline__ Elem to_elem(const cx &c) { return Elem{c.re, c.im}; }
+__device__ __forceinline__ cx to_cx(const Elem &e) { return cx{e.re, e.im}; }
+
+__device__ __forceinline__ float mag_of(float s, float re, float im) {
+    return (s > kPowTiny && s < kPowHuge) ? sqrt_ftz(s) : hypotf(re, im);
+}
+// 10 log10(re^2 + im^2) = 20 log10 |X|; the square is only trusted inside [2^-80, 2^100]
+__device__ __forceinline__ float db_of(float s, float re, float im) {
+    if (s > kPowTiny && s < kPowHuge) return kDbPerLog2Pow * lg2_ftz(s);
+    return amp_to_db(hypotf(re, im));
+}
+
+template <bool MEL>
+__global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
+                                                               long long n_items, long long items_per_track) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Elem *buf = reinterpret_cast<Elem *>(smem_raw);                         // [kBufElems]
+    float2 *tw_a = reinterpret_cast<float2 *>(buf + kBufElems);   // [31][16] W_512^(n2 k1)
+    float2 *tw_b = tw_a + 31 * 16;                                          // [32][16] W_8192^(n3 k1)
+    float2 *tw_c = tw_b + 32 * 16;                                          // [16][16] W_256^(n3 k2)
+    __shared__ float red_max[kThreads / 32], red_nmin[kThreads / 32];
+    // After the real split the FFT buffer is reused in place: |X[k]| of both frames replaces the first 8 bytes of
+    // element idxn(k) (each element is read by exactly one thread before it is overwritten), and the mel partial
+    // sums go to the second 8 bytes of elements 0, 1, 2, ...
+    auto mag_at = [&](int k) -> float2 & { return buf[idxn(k)].re; };
+    auto part_at = [&](int q) -> float2 & { return buf[q].im; };
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 31 * 16 + 32 * 16 + 16 * 16; i += kThreads) tw_a[i] = __ldg(&p.big_tw[i]);
+    // (the mel walk reads up to 31 bins past a piece with weight 0: idxn(8192 + 31) = 8479 is inside the buffer, and
+    // what it finds there is left-over FFT data, finite whenever the frame is)
+    __syncthreads();
+    const int half = p.win / 2;
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const long long track = item / items_per_track, chunk = item - track * items_per_track;
+        const TrackDesc d = tracks[track];
+        const long long f_begin = chunk * (2 * kPairsPerItem);
+        if (f_begin >= d.n_frames) continue;
+        const long long f_end = min(f_begin + 2 * kPairsPerItem, d.n_frames);
+        float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
+
+        for (long long fa = f_begin; fa < f_end; fa += 2) {
+            const bool has_b = fa + 1 < f_end;
+            const long long fb = has_b ? fa + 1 : fa;  // an odd last frame is computed twice, stored once
+            cx v[32];
+            // ---- step 1: load + window, 32-point DFT over n1 ----
+            {
+                const long long tap0[2] = {(d.frame_begin + fa) * p.hop - half, (d.frame_begin + fb) * p.hop - half};
+                const float *wsrc = p.big_wpad + 2 * t;
+                bool interior[2];
+#pragma unroll
+                for (int f = 0; f < 2; f++) {
+                    const long long first = tap0[f] - p.pad_left;  // file index of FFT position 0
+                    interior[f] = !d.pcm_i16 && tap0[f] >= 0 && tap0[f] + p.win <= d.full_len && first >= d.pcm_offset &&
+                                  first + 2 * kNC <= d.pcm_offset + d.slice_len &&
+                                  ((reinterpret_cast<uintptr_t>(d.pcm + (first - d.pcm_offset))) & 7) == 0;
+                }
+                if (interior[0] && interior[1] && has_b && p.hop == 1024) {
+                    // frame B starts hop = 1024 samples = 2 rows of 256 complex later: 34 loads serve both frames
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * t;
+                    float2 r[34];
+#pragma unroll
+                    for (int n1 = 0; n1 < 34; n1++) r[n1] = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; n1++) {
+                        const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
+                        v[n1].re = make_float2(r[n1].x * w.x, r[n1 + 2].x * w.x);
+                        v[n1].im = make_float2(r[n1].y * w.y, r[n1 + 2].y * w.y);
+                    }
+                } else if (interior[0] && interior[1]) {
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * t;
+                    const float *src_b = d.pcm + (tap0[1] - p.pad_left - d.pcm_offset) + 2 * t;
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; n1++) {
+                        const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
+                        const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 512 * n1));
+                        const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
+                        v[n1].re = make_float2(xa.x * w.x, xb.x * w.x);
+                        v[n1].im = make_float2(xa.y * w.y, xb.y * w.y);
+                    }
+                } else {
+                    // file edges (numpy-style reflect, utils.rs:111-137), 16-bit PCM, unaligned channels
+                    auto tap = [&](int f, int pos) -> float {
+                        const int a = pos - p.pad_left;
+                        if (a < 0 || a >= p.win) return 0.0f;
+                        return pcm_sample(d, reflect_index(tap0[f] + a, d.full_len) - d.pcm_offset);
+                    };
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; n1++) {
+                        const int pos = 512 * n1 + 2 * t;
+                        const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
+                        v[n1].re = make_float2(tap(0, pos) * w.x, tap(1, pos) * w.x);
+                        v[n1].im = make_float2(tap(0, pos + 1) * w.y, tap(1, pos + 1) * w.y);
+                    }
+                }
+            }
+            dft32p(v);
+            {
+                const int n2 = t >> 4, n3 = t & 15;
+#pragma unroll
+                for (int k1 = 0; k1 < 32; k1++) {
+                    cx o = v[perm32(k1)];
+                    if (k1) {
+                        const float2 w = tw_a[(k1 - 1) * 16 + n2];
+                        o = cmul_s(o, w.x, w.y);
+                    }
+                    buf[idx3(k1, n2, n3)] = to_elem(o);
+                }
+            }
+            __syncthreads();
+            // ---- step 2: 16-point DFT over n2, twiddle W_8192^(n3 (k1 + 32 k2)) ----
+#pragma unroll 1
+            for (int pr = 0; pr < 2; pr++) {
+                const int k1 = (t >> 4) + 16 * pr, n3 = t & 15;
+                cx u[16];
+#pragma unroll
+                for (int n2 = 0; n2 < 16; n2++) u[n2] = to_cx(buf[idx3(k1, n2, n3)]);
+                dft16p(u);
+                // W_8192^(n3 (k1 + 32 k2)) = W_8192^(n3 k1) * W_256^(n3 k2): two small shared-memory tables instead of
+                // a 64 KB one in L2 (the product is computed once for both frames)
+                const float2 wb = tw_b[k1 * 16 + n3];
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    const float2 wc = tw_c[k2 * 16 + n3];
+                    const float c = fmaf(-wb.y, wc.y, wb.x * wc.x), sn = fmaf(wb.x, wc.y, wb.y * wc.x);
+                    buf[idx3(k1, k2, n3)] = to_elem(cmul_s(u[perm16(k2)], c, sn));
+                }
+            }
+            __syncthreads();
+            // ---- step 3: 16-point DFT over n3 -> Z[k1 + 32 k2 + 512 k3], then natural order ----
+            {
+                cx u0[16], u1[16];
+                const int k2 = t & 15, k1a = t >> 4, k1b = k1a + 16;
+#pragma unroll
+                for (int n3 = 0; n3 < 16; n3++) {
+                    u0[n3] = to_cx(buf[idx3(k1a, k2, n3)]);
+                    u1[n3] = to_cx(buf[idx3(k1b, k2, n3)]);
+                }
+                dft16p(u0);
+                dft16p(u1);
+                __syncthreads();
+#pragma unroll
+                for (int k3 = 0; k3 < 16; k3++) {
+                    buf[idxn(k1a + 32 * k2 + 512 * k3)] = to_elem(u0[perm16(k3)]);
+                    buf[idxn(k1b + 32 * k2 + 512 * k3)] = to_elem(u1[perm16(k3)]);
+                }
+            }
+            __syncthreads();
+            // ---- real split: pairs (k, 8192 - k), k = t + 256 j; |X|^2 -> dB, or |X| -> mag[] ----
+            float *orow_a = d.out + fa * p.n_bins, *orow_b = d.out + fb * p.n_bins;
+#pragma unroll 4
+            for (int j = 0; j <= 16; j++) {
+                const int k = t + 256 * j;
+                if (j == 16 && t != 0) break;  // k = 4096 pairs with itself: one thread
+                const int kp = (kNC - k) & (kNC - 1);
+                const cx zk = to_cx(buf[idxn(k)]), zn = to_cx(buf[idxn(kp)]);
+                const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
+                const float2 w = __ldg(&p.twiddle[k]);
+                const f2 wr = pfma(di, bc(-w.y), pmul(dr, bc(w.x))), wi = pfma(dr, bc(w.y), pmul(di, bc(w.x)));
+                const f2 ar = padd(er, wi), ai = psub(ei, wr), br = psub(er, wi), bi = padd(ei, wr);
+                const f2 sa = pfma(ar, ar, pmul(ai, ai)), sb = pfma(br, br, pmul(bi, bi));
+                const int k_hi = kNC - k;  // bin of the partner: 8192 for k = 0, 4096 for k = 4096 (same bin)
+                if (MEL) {
+                    mag_at(k) = make_float2(mag_of(sa.x, ar.x, ai.x), mag_of(sa.y, ar.y, ai.y));
+                    if (k_hi != k) mag_at(k_hi) = make_float2(mag_of(sb.x, br.x, bi.x), mag_of(sb.y, br.y, bi.y));
+                } else {
+                    const float a0 = db_of(sa.x, ar.x, ai.x), a1 = db_of(sa.y, ar.y, ai.y);
+                    orow_a[k] = a0;
+                    lmax = fmaxf(lmax, a0);
+                    lnmin = fmaxf(lnmin, -a0);
+                    if (has_b) {
+                        orow_b[k] = a1;
+                        lmax = fmaxf(lmax, a1);
+                        lnmin = fmaxf(lnmin, -a1);
+                    }
+                    if (k_hi != k) {
+                        const float b0 = db_of(sb.x, br.x, bi.x), b1 = db_of(sb.y, br.y, bi.y);
+                        orow_a[k_hi] = b0;
+                        lmax = fmaxf(lmax, b0);
+                        lnmin = fmaxf(lnmin, -b0);
+                        if (has_b) {
+                            orow_b[k_hi] = b1;
+                            lmax = fmaxf(lmax, b1);
+                            lnmin = fmaxf(lnmin, -b1);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (MEL) {
+                // ---- sparse mel: a warp walks 32 pieces (<= 32 consecutive bins of one band each) in lock step ----
+                // ---- sparse mel: a warp walks 32 pieces (<= 32 consecutive bins of one band each) in lock step ----
+                const int n_groups = (p.big_n_pieces + 31) >> 5;
+                for (int g = warp; g < n_groups; g += kThreads / 32) {
+                    const int q = 32 * g + lane;
+                    const uint2 gh = __ldg(reinterpret_cast<const uint2 *>(p.big_pieces + 32 * n_groups) + g);  // {steps, offset}
+                    const int k0 = static_cast<int>(__ldg(&p.big_pieces[q]));
+                    const float *w = p.big_w + gh.y + lane;
+                    // the weight table (150 KB for 1621 bands) lives in L2: all loads of a group are issued before the
+                    // first use, so a group costs one L2 round trip, not one per step
+                    f2 acc = make_float2(0.0f, 0.0f);
+                    const int T = static_cast<int>(gh.x);
+                    auto walk = [&](auto nmax) {  // unrolled for groups of up to nmax steps (padding lanes: weight 0)
+                        constexpr int N = decltype(nmax)::value;
+                        float wv[N];
+#pragma unroll
+                        for (int i = 0; i < N; i++) wv[i] = i < T ? __ldg(w + 32 * i) : 0.0f;
+#pragma unroll
+                        for (int i = 0; i < N; i++)
+                            if (i < T) acc = pfma(mag_at(k0 + i), bc(wv[i]), acc);
+                    };
+                    if (T <= 8) walk(std::integral_constant<int, 8>{});
+                    else if (T <= 16) walk(std::integral_constant<int, 16>{});
+                    else walk(std::integral_constant<int, 32>{});
+                    if (q < p.big_n_pieces) part_at(q) = acc;
+                }
+                __syncthreads();
+                for (int m = t; m < p.n_mel; m += kThreads) {
+                    const uint32_t q0 = __ldg(&p.big_pptr[m]), q1 = __ldg(&p.big_pptr[m + 1]);
+                    f2 acc = make_float2(0.0f, 0.0f);
+                    for (uint32_t q = q0; q < q1; q++) acc = padd(acc, part_at(q));
+                    const float a0 = kDbPerLog2Amp * lg2_ftz(acc.x), a1 = kDbPerLog2Amp * lg2_ftz(acc.y);
+                    orow_a[m] = a0;
+                    lmax = fmaxf(lmax, a0);
+                    lnmin = fmaxf(lnmin, -a0);
+                    if (has_b) {
+                        orow_b[m] = a1;
+                        lmax = fmaxf(lmax, a1);
+                        lnmin = fmaxf(lnmin, -a1);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- per-channel {max, -min}: warp shuffle -> shared -> one atomic pair per CTA and item ----
+        lmax = warp_max(lmax);
+        lnmin = warp_max(lnmin);
+        if (lane == 0) {
+            red_max[warp] = lmax;
+            red_nmin[warp] = lnmin;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float a = lane < kThreads / 32 ? red_max[lane] : -CUDART_INF_F;
+            float b = lane < kThreads / 32 ? red_nmin[lane] : -CUDART_INF_F;
+            a = warp_max(a);
+            b = warp_max(b);
+            if (lane == 0) {
+                atomic_max_float(&d.minmax[0], a);
+                atomic_max_float(&d.minmax[1], b);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t big_smem_bytes(const PlanDev &) { return sizeof(Elem) * (kBufElems) + sizeof(float2) * (31 * 16 + 32 * 16 + 16 * 16); }
+
+}  // namespace
+
+bool stft_big_supported(const PlanDev &p) {
+    if (p.n_fft != 2 * kNC || !p.big_wpad || !p.big_tw) return false;
+    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > kBufElems)) return false;
+    return big_smem_bytes(p) <= 226 * 1024;
+}
+
+cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
+                            int sm_count, cudaStream_t st) {
+    if (n_tracks <= 0 || max_frames <= 0) return cudaSuccess;
+    const size_t smem = big_smem_bytes(plan);
+    const long long items_per_track = (max_frames + 2 * kPairsPerItem - 1) / (2 * kPairsPerItem);
+    const long long n_items = items_per_track * n_tracks;
+    const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
+    cudaError_t e;
+    if (plan.n_mel) {
+        e = cudaFuncSetAttribute(stft16384_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        stft16384_kernel<true><<<grid, kThreads, smem, st>>>(plan, d_tracks, n_items, items_per_track);
+    } else {
+        e = cudaFuncSetAttribute(stft16384_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        stft16384_kernel<false><<<grid, kThreads, smem, st>>>(plan, d_tracks, n_items, items_per_track);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace thb
