@@ -204,6 +204,23 @@ int thb_waveform_level_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, ui
                              const uint8_t **dev_out);
 uint64_t thb_waveform_level_bytes(uint64_t len, uint32_t level);
 
+/* ---- StatCalculator::calc, level part (src-tauri/src/core/dynamics/stats.rs:56-85) ----
+ * thb_channel_stats: for each of n channels (thb_track: pcm, len, pcm_format; host or device) the two reductions the
+ * reference runs over the PCM: sum_squares (simd.rs:113-134,820-832) and abs_max (simd.rs:161-183,935-937).
+ * thb_audio_stats: the scalar arithmetic on top for ONE track of n_ch channels: mean_squared = sum of the channels'
+ * sums / n_elem, rms_dB = 10 log10 (0 -> -inf), max_peak, max_peak_dB = 20 log10 (host code, no device needed).
+ * The loudness leg (EBU R128, a sequential filter) is not part of this library. */
+typedef struct thb_audio_stats_t {
+    float mean_squared;
+    float rms_dB;
+    float max_peak;
+    float max_peak_dB;
+} thb_audio_stats_t;
+int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *sum_squares /* [n] */,
+                      float *abs_max /* [n] */);
+int thb_audio_stats(const float *sum_squares, const float *abs_max, const uint64_t *lens, size_t n_ch,
+                    thb_audio_stats_t *out);
+
 /* ---- multi-GPU: one process per GPU, one communicator per box ---------
  * NCCL is dlopen'ed ("libnccl.so.2") on first use.  Rank 0 creates the id, the host program
  * distributes the 128 bytes (torch.distributed / MPI / a file), every rank calls thb_comm_init. */

@@ -65,6 +65,9 @@ def _load() -> C.CDLL:
         "orc_dB_scalar_f32": (_f32, [_f32, _f32, _f32, _f32]),
         "orc_dB_from_amp_inplace_f32": (None, [_pf32, _u64, _f32, _f32]),
         "orc_find_min_max_f32": (None, [_pf32, _u64, _pf32, _pf32]),
+        "orc_sum_squares_f32": (C.c_float, [_pf32, _u64]),
+        "orc_abs_max_f32": (C.c_float, [_pf32, _u64]),
+        "orc_audio_stats_f32": (None, [_pf32, _u64, _u64, _pf32]),
         "orc_sum_simd_order_f32": (_f32, [_pf32, _u64, _u32]),
         "orc_encode_waveform_tile": (_u64, [_pf32, _u64, _u64, _u32, _u32, _pu8]),
         "orc_spec_to_img": (None, [_pf32, _u64, _u64, _u64, _u64, _f32, _f32, _int, _u32, _pu16]),
@@ -225,6 +228,28 @@ def find_min_max(x):
     a, b = _f32(), _f32()
     lib().orc_find_min_max_f32(_p(x, _pf32), x.size, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def sum_squares(x) -> float:
+    """sum_squares_scalar (simd.rs:820-832)."""
+    x = _f32c(x).ravel()
+    return lib().orc_sum_squares_f32(_p(x, _pf32), x.size)
+
+
+def abs_max(x) -> float:
+    """abs_max_scalar (simd.rs:935-937)."""
+    x = _f32c(x).ravel()
+    return lib().orc_abs_max_f32(_p(x, _pf32), x.size)
+
+
+def audio_stats(wavs):
+    """StatCalculator::calc without global_lufs (stats.rs:56-85): (mean_squared, rms_dB, max_peak, max_peak_dB)."""
+    w = _f32c(wavs)
+    if w.ndim == 1:
+        w = w[None, :]
+    out = (C.c_float * 4)()
+    lib().orc_audio_stats_f32(_p(w, _pf32), w.shape[0], w.shape[1], out)
+    return tuple(out)
 
 
 def sum_simd_order(x, align_elems: int = 0) -> float:

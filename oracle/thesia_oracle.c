@@ -377,6 +377,48 @@ ORC_API void orc_find_min_max_f32(const float *x, uint64_t n, float *mn, float *
     *mn = a; *mx = b;
 }
 
+/* sum_squares_scalar (simd.rs:820-832): Kahan-compensated sum of x*x in f32.  The reference's SIMD legs keep one
+   compensated accumulator per lane (alignment dependent), so only the scalar leg is restated; tests compare within
+   f32 rounding. */
+ORC_API float orc_sum_squares_f32(const float *x, uint64_t n) {
+    volatile float sum = 0.0f, c = 0.0f;  /* volatile: keeps the compiler from simplifying the compensation away */
+    for (uint64_t i = 0; i < n; i++) {
+        volatile float y = x[i] * x[i] - c;
+        volatile float t = sum + y;
+        c = (t - sum) - y;
+        sum = t;
+    }
+    return sum;
+}
+
+/* abs_max_scalar (simd.rs:935-937): fold(0, max) over |x| (empty -> 0) */
+ORC_API float orc_abs_max_f32(const float *x, uint64_t n) {
+    float m = 0.0f;
+    for (uint64_t i = 0; i < n; i++) {
+        const float a = fabsf(x[i]);
+        if (a > m) m = a;
+    }
+    return m;
+}
+
+/* StatCalculator::calc without the loudness leg (dynamics/stats.rs:56-85): wavs is (n_ch, n) row-major.
+   mean_squared = sum over channels of sum_squares(channel) / n_elem (f32), rms_dB = 10 log10 (dB_from_power_default,
+   decibel.rs:95-107: 0 -> -inf), max_peak = abs_max over everything, max_peak_dB = 20 log10.  out = {mean_squared,
+   rms_dB, max_peak, max_peak_dB}. */
+ORC_API void orc_audio_stats_f32(const float *wavs, uint64_t n_ch, uint64_t n, float out[4]) {
+    float total = 0.0f, peak = 0.0f;
+    for (uint64_t c = 0; c < n_ch; c++) {
+        total += orc_sum_squares_f32(wavs + c * n, n);
+        const float m = orc_abs_max_f32(wavs + c * n, n);
+        if (m > peak) peak = m;
+    }
+    const float ms = total / (float)(n_ch * n);
+    out[0] = ms;
+    out[1] = 10.0f * log10f(ms);
+    out[2] = peak;
+    out[3] = 20.0f * log10f(peak);
+}
+
 /* sum_avx2 order (simd.rs:594-619): scalar prefix up to 32-byte alignment, 8 lane
    accumulators over the aligned middle, lanes reduced, scalar suffix. `align_elems` = number of
    prefix elements (0..7) -- the reference derives it from the slice ADDRESS, so the sum is

@@ -184,6 +184,18 @@ static void test_gpu_flow() {
         const auto il = tm.get_spectrogram({0, 0});
         EXPECT(il && il->height == 1025 && il->width == n_frames(48000, 2048, 512));
     }
+    // ---- level statistics (dynamics/stats.rs:56-85): a full-scale square wave has 0 dB RMS and 0 dB peak ----
+    {
+        Audio a;
+        a.sr = 48000; a.len = 100000; a.n_ch = 2;
+        a.wavs.resize(200000);
+        for (size_t i = 0; i < a.wavs.size(); i++) a.wavs[i] = (i & 1) ? 1.0f : -1.0f;
+        AudioStats st = calc_stats(ctx, a);
+        EXPECT(st.rms_dB == 0.0f && st.max_peak == 1.0f && st.max_peak_dB == 0.0f);
+        for (float &v : a.wavs) v *= 0.5f;
+        st = calc_stats(ctx, a);
+        EXPECT(std::fabs(st.rms_dB - 20.0f * std::log10(0.5f)) < 1e-5f && st.max_peak == 0.5f);
+    }
     // ---- waveform tile KATs (render_tiles.rs:408-433) ----
     {
         const float wav[8] = {-1.0f, 0.5f, 0.25f, -0.75f, 0.1f, 0.2f, -0.3f, 0.9f};

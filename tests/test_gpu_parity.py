@@ -193,6 +193,44 @@ def test_host_pcm_pipeline_equals_device_resident(ctx):
         ctx.release(c, 0)
 
 
+def test_channel_stats_parity(ctx, orc):
+    """SURVEY.md 8 f3: sum_squares / abs_max / rms_dB / max_peak_dB of StatCalculator::calc (stats.rs:56-85).
+    abs_max is exact; the sum (f64 accumulation on the device, Kahan f32 in the reference) within f32 rounding."""
+    import torch
+    for data, ss, mx in (([1.0, 2.0, 3.0, 4.0], 30.0, 4.0), ([-1.0, -2.0, -3.0], 14.0, 3.0), ([0.0, 0.0, 0.0], 0.0, 0.0),
+                         ([-1.0], 1.0, 1.0)):  # simd.rs:1253-1273, 1358-1380
+        g_ss, g_mx = ctx.channel_stats([np.array(data, np.float32)])
+        assert g_ss[0] == ss and g_mx[0] == mx
+    rng = np.random.default_rng(11)
+    lens = [1, 7, 1 << 18, (1 << 18) + 1, 3 * (1 << 18) + 12345, 48000 * 25 + 3]
+    wavs = [(rng.standard_normal(n) * 0.2).astype(np.float32) for n in lens]
+    wavs[2][17] = -3.5   # a peak only one thread sees
+    g_ss, g_mx = ctx.channel_stats(wavs)
+    d_ss, d_mx = ctx.channel_stats([torch.from_numpy(w).cuda() for w in wavs])
+    assert np.array_equal(g_ss, d_ss) and np.array_equal(g_mx, d_mx)   # host and device-resident PCM agree
+    for w, a, b in zip(wavs, g_ss, g_mx):
+        exact = float(np.sum(w.astype(np.float64) ** 2))
+        assert abs(a - exact) <= 1.2e-7 * exact                       # correctly rounded f64 sum
+        assert abs(a - orc.sum_squares(w)) <= 4e-7 * exact            # the reference's Kahan f32 sum
+        assert b == orc.abs_max(w)
+    # odd start (4-byte aligned only) and 16-bit PCM
+    off = wavs[4][1:]
+    a, b = ctx.channel_stats([torch.from_numpy(wavs[4]).cuda()[1:]])
+    assert abs(a[0] - float(np.sum(off.astype(np.float64) ** 2))) <= 1.2e-7 * a[0] and b[0] == orc.abs_max(off)
+    q = rng.integers(-32768, 32768, 300001, dtype=np.int16)
+    f = q.astype(np.float32) / np.float32(32768.0)
+    a16, b16 = ctx.channel_stats([q])
+    a32, b32 = ctx.channel_stats([f])
+    assert a16[0] == a32[0] and b16[0] == b32[0] == orc.abs_max(f)
+    # one stereo track through StatCalculator::calc's arithmetic
+    st = ctx.calc_stats([wavs[5], wavs[5] * np.float32(0.5)])
+    ms, rms_dB, peak, peak_dB = orc.audio_stats(np.stack([wavs[5], wavs[5] * np.float32(0.5)]))
+    assert abs(st["mean_squared"] - ms) <= 4e-7 * ms and abs(st["rms_dB"] - rms_dB) <= 1e-5
+    assert st["max_peak"] == peak and abs(st["max_peak_dB"] - peak_dB) <= 1e-5
+    z = ctx.calc_stats([np.zeros(1000, np.float32)])
+    assert z["rms_dB"] == -math.inf and z["max_peak_dB"] == -math.inf
+
+
 def _tile_fields(b):
     rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
     return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)

@@ -264,3 +264,27 @@ def test_synth_c_twin_matches_numpy_twin(orc):
     for (n, sr, tr, ch, fl) in [(100003, 48000, 0, 0, 0), (150000, 48000, 63, 1, 2), (50000, 96000, 9, 0, 1),
                                 (300000, 44100, 17, 1, 3)]:
         assert np.array_equal(orc.synth_pcm(n, sr, tr, ch, fl, n_threads=4), synth_pcm(n, sr, tr, ch, fl))
+
+
+# simd.rs:1253-1273 test_sum_squares, simd.rs:1358-1380 test_abs_max -- the reference's own cases and tolerance
+def test_sum_squares_and_abs_max(orc):
+    for data, want in (([1.0, 2.0, 3.0, 4.0], 30.0), ([-1.0, -2.0, -3.0], 14.0), ([0.0, 0.0, 0.0], 0.0), ([1.0], 1.0), ([], 0.0)):
+        assert abs(orc.sum_squares(np.array(data, np.float32)) - want) < 1e-5
+    for data, want in (([1.0, -2.0, 3.0, -4.0], 4.0), ([-1.0, -2.0, -3.0], 3.0), ([0.0, 0.0, 0.0], 0.0), ([1.0], 1.0), ([-1.0], 1.0),
+                       ([], 0.0)):
+        assert abs(orc.abs_max(np.array(data, np.float32)) - want) < 1e-5
+    # Kahan keeps a long f32 sum within an ulp or two of the exact value
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 1 << 20).astype(np.float32)
+    exact = float(np.sum(x.astype(np.float64) ** 2))
+    assert abs(orc.sum_squares(x) - exact) <= 2e-7 * exact
+
+
+# dynamics/stats.rs:56-85 (level part): mean square over all channels, 10 log10 / 20 log10, -inf for silence
+def test_audio_stats(orc):
+    w = np.array([[0.5, -0.5, 0.0, 0.25], [1.0, 0.0, 0.0, -0.125]], np.float32)
+    ms, rms_dB, peak, peak_dB = orc.audio_stats(w)
+    assert ms == np.float32((0.25 + 0.25 + 0.0625 + 1.0 + 0.015625) / 8)
+    assert abs(rms_dB - 10 * math.log10(ms)) < 1e-5 and peak == 1.0 and peak_dB == 0.0
+    ms, rms_dB, peak, peak_dB = orc.audio_stats(np.zeros((2, 16), np.float32))
+    assert ms == 0.0 and rms_dB == -math.inf and peak == 0.0 and peak_dB == -math.inf

@@ -49,6 +49,10 @@ class SpecOut(C.Structure):
                 ("spec_host", C.c_void_p), ("spec_host_cap", C.c_uint64)]
 
 
+class AudioStats(C.Structure):
+    _fields_ = [("mean_squared", C.c_float), ("rms_dB", C.c_float), ("max_peak", C.c_float), ("max_peak_dB", C.c_float)]
+
+
 _P = C.POINTER
 _vp, _u8p = C.c_void_p, _P(C.c_uint8)
 _u64, _u32, _f32, _i = C.c_uint64, C.c_uint32, C.c_float, C.c_int
@@ -68,6 +72,8 @@ SIGNATURES = {
     "thb_n_bins": (_i, [_P(Setting), _u32, _P(_u32)]),
     "thb_hann_window": (_i, [_u64, _u64, _P(_f32)]),
     "thb_mel_fb": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
+    "thb_channel_stats": (_i, [_vp, _P(Track), C.c_size_t, _P(_f32), _P(_f32)]),
+    "thb_audio_stats": (_i, [_P(_f32), _P(_f32), _P(_u64), C.c_size_t, _P(AudioStats)]),
     "thb_mel_schedule_replay": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
     "thb_hz_range_to_idx": (_i, [_u32, _f32, _f32, _u32, _u64, _P(_u64), _P(_u64)]),
     "thb_spec_batch": (_i, [_vp, _P(Track), C.c_size_t, _P(Setting), _P(SpecOut)]),

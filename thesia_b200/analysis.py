@@ -322,6 +322,30 @@ class Context:
             return [o.tobytes() for o in outs]
         return [(dev[i], written[i]) for i in range(n)]
 
+    # ---- level statistics (dynamics/stats.rs:56-85 without the loudness leg) ----
+    def channel_stats(self, wavs: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+        """(sum_squares[n], abs_max[n]) of n channels (f32 or int16 arrays / tensors, host or device)."""
+        n = len(wavs)
+        arr = (Track * n)()
+        keep = []
+        for i, w in enumerate(wavs):
+            addr, ln, k, fmt = _ptr_len_fmt(w)
+            keep.append(k)
+            arr[i] = Track(addr, ln, i, 0, 0, 0, 0, 0, 0, fmt, 0)
+        ss, mx = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        check(lib().thb_channel_stats(self._h, arr, n, ss.ctypes.data_as(C.POINTER(C.c_float)),
+                                      mx.ctypes.data_as(C.POINTER(C.c_float))), self._h)
+        return ss, mx
+
+    def calc_stats(self, wavs: Sequence) -> dict:
+        """StatCalculator::calc for one track given its channels: rms_dB, max_peak, max_peak_dB (+ mean_squared)."""
+        ss, mx = self.channel_stats(wavs)
+        lens = (C.c_uint64 * len(wavs))(*[_ptr_len_fmt(w)[1] for w in wavs])
+        out = _lib.AudioStats()
+        check(lib().thb_audio_stats(ss.ctypes.data_as(C.POINTER(C.c_float)), mx.ctypes.data_as(C.POINTER(C.c_float)), lens,
+                                    len(wavs), C.byref(out)), self._h)
+        return dict(mean_squared=out.mean_squared, rms_dB=out.rms_dB, max_peak=out.max_peak, max_peak_dB=out.max_peak_dB)
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -1401,6 +1401,78 @@ int thb_waveform_level_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, ui
     return THB_OK;
 }
 
+int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *sum_squares, float *abs_max) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return THB_OK;
+    if (!channels || !sum_squares || !abs_max) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; i++) {
+        if (!channels[i].pcm && channels[i].len) return fail(ctx, THB_ERR_INVALID, "channel %zu: pcm is NULL", i);
+        if (channels[i].pcm_format > THB_PCM_I16) return fail(ctx, THB_ERR_INVALID, "channel %zu: pcm_format = %u", i, channels[i].pcm_format);
+    }
+    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 64) * n + 1024);
+    if (rc) return rc;
+    thb::TrackDesc *d_desc = nullptr;
+    thb::TrackDesc *h = arena_push<thb::TrackDesc>(ctx, n, &d_desc);
+    std::vector<void *> staging(n, nullptr);
+    long long max_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        const thb_track &t = channels[i];
+        const size_t esz = t.pcm_format == THB_PCM_I16 ? 2 : 4;
+        const void *d_pcm = t.pcm;
+        if (t.len && !is_device_ptr(t.pcm)) {
+            CK(cudaMallocAsync(&staging[i], esz * t.len + 64, ctx->stream));
+            CK(cudaMemcpyAsync(staging[i], t.pcm, esz * t.len, cudaMemcpyHostToDevice, ctx->stream));
+            d_pcm = staging[i];
+        }
+        memset(&h[i], 0, sizeof(thb::TrackDesc));
+        h[i].pcm = static_cast<const float *>(d_pcm);
+        h[i].slice_len = static_cast<long long>(t.len);
+        h[i].full_len = static_cast<long long>(t.len);
+        h[i].pcm_i16 = t.pcm_format == THB_PCM_I16 ? 1 : 0;
+        max_len = std::max(max_len, h[i].slice_len);
+    }
+    if ((rc = arena_commit(ctx))) return rc;
+    const size_t chunks = static_cast<size_t>(thb::stats_chunks(max_len));
+    double *d_part_ss = nullptr;
+    float *d_part_mx = nullptr, *d_out = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_part_ss), sizeof(double) * n * chunks, ctx->stream));
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_part_mx), sizeof(float) * n * chunks, ctx->stream));
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), sizeof(float) * 2 * n, ctx->stream));
+    {
+        ProfScope ps(ctx, "channel_stats", 2 * static_cast<int>((n + 65534) / 65535));
+        cudaError_t e = thb::launch_channel_stats(d_desc, static_cast<int>(n), max_len, d_part_ss, d_part_mx, d_out, d_out + n, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "channel_stats: %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(sum_squares, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(abs_max, d_out + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    for (size_t i = 0; i < n; i++)
+        if (staging[i]) CK(cudaFreeAsync(staging[i], ctx->stream));
+    CK(cudaFreeAsync(d_part_ss, ctx->stream));
+    CK(cudaFreeAsync(d_part_mx, ctx->stream));
+    CK(cudaFreeAsync(d_out, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_audio_stats(const float *sum_squares, const float *abs_max, const uint64_t *lens, size_t n_ch, thb_audio_stats_t *out) {
+    if (!sum_squares || !abs_max || !lens || !out) return fail(nullptr, THB_ERR_INVALID, "bad argument");
+    // stats.rs:66-79: the channels' f32 sums are added (rayon sum, f32), divided by the element count as f32
+    float total = 0.0f, peak = 0.0f;
+    uint64_t n_elem = 0;
+    for (size_t c = 0; c < n_ch; c++) {
+        total += sum_squares[c];
+        peak = std::max(peak, abs_max[c]);
+        n_elem += lens[c];
+    }
+    out->mean_squared = total / static_cast<float>(n_elem);
+    out->rms_dB = 10.0f * log10f(out->mean_squared);   // dB_from_power_default (decibel.rs:95-107)
+    out->max_peak = peak;
+    out->max_peak_dB = 20.0f * log10f(peak);           // dB_from_amp_default
+    return THB_OK;
+}
+
 int thb_waveform_level(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level, uint8_t *out,
                        size_t cap, size_t *written) {
     thb_track t{};

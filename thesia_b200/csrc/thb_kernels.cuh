@@ -129,6 +129,11 @@ cudaError_t launch_envelope(const EnvDesc *d_descs, int n, long long max_len, ui
                             uint64_t revision, uint32_t tile_begin, uint32_t tile_count,
                             cudaStream_t st);
 
+// per-channel sum of squares / absolute maximum (thb_stats.cu); only pcm, slice_len and pcm_i16 of a descriptor are read
+long long stats_chunks(long long max_len);
+cudaError_t launch_channel_stats(const TrackDesc *d_descs, int n, long long max_len, double *d_part_ss, float *d_part_mx,
+                                 float *d_out_ss, float *d_out_mx, cudaStream_t st);
+
 cudaError_t launch_synth_pcm(float *d_out, unsigned long long len, uint32_t sr, uint32_t track,
                              uint32_t channel, uint32_t flags, cudaStream_t st);
 

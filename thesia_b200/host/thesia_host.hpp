@@ -350,6 +350,26 @@ private:
     std::vector<uint64_t> no_spec_img_ids_;
 };
 
+// AudioStats of StatCalculator::calc (dynamics/stats.rs:56-85) without the loudness leg
+struct AudioStats {
+    float rms_dB = 0.0f, max_peak = 0.0f, max_peak_dB = 0.0f;
+};
+inline AudioStats calc_stats(Context &ctx, const Audio &audio) {
+    std::vector<thb_track> chans(audio.n_ch);
+    std::vector<uint64_t> lens(audio.n_ch, audio.len);
+    for (uint32_t ch = 0; ch < audio.n_ch; ch++) {
+        chans[ch] = thb_track{};
+        chans[ch].pcm = audio.channel(ch);
+        chans[ch].len = audio.len;
+        chans[ch].sr = audio.sr;
+    }
+    std::vector<float> ss(audio.n_ch), mx(audio.n_ch);
+    check(thb_channel_stats(ctx.get(), chans.data(), chans.size(), ss.data(), mx.data()), ctx.get());
+    thb_audio_stats_t st{};
+    check(thb_audio_stats(ss.data(), mx.data(), lens.data(), audio.n_ch, &st));
+    return AudioStats{st.rms_dB, st.max_peak, st.max_peak_dB};
+}
+
 // encode_waveform_tile(&[f32], u64, u32, u32) -> Vec<u8> (render_tiles.rs:232-279)
 inline std::vector<uint8_t> encode_waveform_tile(Context &ctx, const float *wav, uint64_t len, uint64_t revision, uint32_t level,
                                                  uint32_t tile_index) {

@@ -82,6 +82,16 @@ def envelope_case(ctx, n_ch, seconds, sr, reps, out):
         out({"config": "C5", "level": level, "columns_per_channel": bins, "channels": n_ch, "samples_per_channel": n,
              "envelope_ms": ms, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS,
              "audio_hours_per_s": n_ch * seconds / 3600.0 / (ms * 1e-3)})
+    # f3: sum of squares + absolute maximum of every channel (one pass over the same PCM)
+    ctx.channel_stats(wavs)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    for _ in range(reps):
+        ctx.channel_stats(wavs)
+    ms = ctx.profile_get("channel_stats")[0] / reps
+    ctx.profile_enable(False)
+    out({"config": "f3 channel_stats", "channels": n_ch, "samples_per_channel": n, "stats_ms": ms,
+         "algorithmic_GBps": n_ch * 4 * n / (ms * 1e-3) / 1e9, "hbm_frac": n_ch * 4 * n / (ms * 1e-3) / 1e9 / HBM_GBS})
     del pcm
     torch.cuda.empty_cache()
 
