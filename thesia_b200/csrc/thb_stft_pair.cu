@@ -51,7 +51,8 @@ __device__ __forceinline__ PairSmem carve(unsigned char *raw, int tile_f2) {
 // converted (I2F, exact), and the 2^-15 of "s / 32768" rides on the window table, so every product equals the f32
 // channel's bit for bit.  (Not the 1.5 * 2^23 exponent-pasting trick: the compiler distributes the window over its
 // subtraction, (x - M) w -> fma(x, w, -M w), which is no longer exact.)
-template <bool MEL, int NW, bool I16>
+// HS > 0: hop == 64 HS, so frame B's row n1 is frame A's row n1 + HS and 32 + HS loads serve both frames.
+template <bool MEL, int NW, bool I16, int HS>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
                                                                         long long n_items, RescueList rescue) {
@@ -116,6 +117,17 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                     const float b_im = static_cast<float>(static_cast<int>(wb) >> 16);
                     v[n1].re = make_float2(a_re * w.x, b_re * w.x);
                     v[n1].im = make_float2(a_im * w.y, b_im * w.y);
+                }
+            } else if constexpr (HS > 0) {
+                const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
+                float2 r[32 + HS];
+#pragma unroll
+                for (int n1 = 0; n1 < 32 + HS; n1++) r[n1] = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1));
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    v[n1].re = make_float2(r[n1].x * w.x, r[n1 + HS].x * w.x);
+                    v[n1].im = make_float2(r[n1].y * w.y, r[n1 + HS].y * w.y);
                 }
             } else {
                 const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
@@ -268,11 +280,11 @@ int pair_warps() {
     return (w == 8 || w == 10 || w == 12) ? w : 12;
 }
 
-template <bool MEL, int NW, bool I16>
+template <bool MEL, int NW, bool I16, int HS = 0>
 cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
                       cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
-    auto kern = stft2048_pair_kernel<MEL, NW, I16>;
+    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
@@ -299,6 +311,17 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
     if (pcm_i16) {  // the ingest variant exists for the tuned warp count only
         if (plan.n_mel) return launch_nw<true, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
+    // THB_PAIR_SHARE=0 turns the shared-load variants off (A/B runs)
+    const char *se = getenv("THB_PAIR_SHARE");
+    const bool share = !(se && atoi(se) == 0) && nw == 12;
+    if (share && plan.hop == 512) {
+        if (plan.n_mel) return launch_nw<true, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<false, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
+    if (share && plan.hop == 256) {
+        if (plan.n_mel) return launch_nw<true, 12, false, 4>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<false, 12, false, 4>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
     if (plan.n_mel) {
         if (nw == 8) return launch_nw<true, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
