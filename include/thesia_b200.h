@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define THB_ABI_VERSION 2
+#define THB_ABI_VERSION 3
 
 typedef enum thb_status {
     THB_OK = 0,
@@ -221,6 +221,43 @@ int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *
 int thb_audio_stats(const float *sum_squares, const float *abs_max, const uint64_t *lens, size_t n_ch,
                     thb_audio_stats_t *out);
 
+/* ---- gain normalisation + guard clipping ahead of the analysis --------------------------
+ * thb_normalize_gain: Normalize::normalize_default's gain for a target (dynamics/normalize.rs:23-45), from the ORIGINAL
+ * audio's statistics (host arithmetic, f32 like the reference; global_lufs is the reference's f64, narrowed first).
+ * thb_apply_gain: AudioTrack::apply_gain (track.rs:152-171: y = gain * original) + the guard clipping of Audio::mutate
+ * (audio.rs:49-63) + the level statistics `mutate` recomputes, for n channels in one pass over the samples.  Channels
+ * with the same `id` form one Audio (they must carry the same gain): ReduceGlobalLevel takes its peak over all of
+ * them (audio.rs:146-160).  A non-finite or unit gain restores the original (track.rs:160-161).  `pcm`, `out` and
+ * `before_clip` may each be host or device memory; `out` may equal `pcm` (f32).  `before_clip` (optional) receives
+ * GuardClippingResult::WavBeforeClip in Clip mode (what channel_for_drawing shows, audio.rs:71-79).  The limiter mode
+ * (audio.rs:161-178, limiter.rs:47-176) is a sequential recurrence and is not provided: THB_ERR_UNSUPPORTED. */
+#define THB_NORM_OFF 0u
+#define THB_NORM_LUFS 1u
+#define THB_NORM_RMS_DB 2u
+#define THB_NORM_PEAK_DB 3u
+float thb_normalize_gain(uint32_t target_kind, float target, double global_lufs, float rms_dB, float max_peak_dB);
+
+#define THB_GUARD_CLIP 0u                 /* GuardClippingMode::Clip (dynamics/guardclipping.rs:7-12) */
+#define THB_GUARD_REDUCE_GLOBAL_LEVEL 1u
+#define THB_GUARD_LIMITER 2u              /* not provided */
+typedef struct thb_gain_channel {
+    const void *pcm;     /* the ORIGINAL samples: f32, or i16 when pcm_format == THB_PCM_I16 */
+    uint64_t len;
+    uint64_t id;         /* track id: groups the channels of one Audio */
+    uint32_t pcm_format;
+    float gain;
+    float *out;          /* len floats: Audio.wavs after gain + guard clipping */
+    float *before_clip;  /* NULL, or len floats */
+} thb_gain_channel;
+typedef struct thb_gain_result {
+    float global_gain;           /* GuardClippingResult::GlobalGain (1 unless ReduceGlobalLevel reduced) */
+    float max_reduction_gain_dB; /* GuardClippingStats (dynamics/stats.rs:110-158) of this channel */
+    uint64_t reduction_cnt;
+    float sum_squares;           /* of the output channel: the inputs of thb_audio_stats */
+    float abs_max;
+} thb_gain_result;
+int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uint32_t mode, thb_gain_result *results /* [n] */);
+
 /* ---- multi-GPU: one process per GPU, one communicator per box ---------
  * NCCL is dlopen'ed ("libnccl.so.2") on first use.  Rank 0 creates the id, the host program
  * distributes the 128 bytes (torch.distributed / MPI / a file), every rank calls thb_comm_init. */
@@ -232,7 +269,7 @@ int thb_comm_destroy(thb_ctx *ctx);
  * Per-kernel CUDA-event timing on the ctx stream and a launch counter (bench.py's roofline /
  * gpu_launches).  Kernel names: "stft_mel_db", "stft_lin_db" (the main STFT kernel of a batch),
  * "stft_mel_db_edges", "stft_lin_db_edges" (file-edge frames and rescued tiles, when the main kernel
- * leaves them to the scalar one), "minmax_reduce", "minmax_array", "spec_to_img", "envelope". */
+ * leaves them to the scalar one), "minmax_reduce", "minmax_array", "spec_to_img", "envelope", "channel_stats", "gain_peak", "gain_apply". */
 int thb_profile_enable(thb_ctx *ctx, int on);
 int thb_profile_reset(thb_ctx *ctx);
 int thb_profile_get(thb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *launches);

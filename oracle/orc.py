@@ -69,6 +69,8 @@ def _load() -> C.CDLL:
         "orc_abs_max_f32": (C.c_float, [_pf32, _u64]),
         "orc_audio_stats_f32": (None, [_pf32, _u64, _u64, _pf32]),
         "orc_sum_simd_order_f32": (_f32, [_pf32, _u64, _u32]),
+        "orc_normalize_gain": (_f32, [_int, _f32, _f64, _f32, _f32]),
+        "orc_apply_gain": (_int, [_pf32, _u64, _u64, _f32, _int, _pf32, _pf32, _pf32, _pf32, _pu64]),
         "orc_encode_waveform_tile": (_u64, [_pf32, _u64, _u64, _u32, _u32, _pu8]),
         "orc_spec_to_img": (None, [_pf32, _u64, _u64, _u64, _u64, _f32, _f32, _int, _u32, _pu16]),
         "orc_clamp_minmax": (None, [_f32, _f32, _f32, _pf32, _pf32]),
@@ -250,6 +252,35 @@ def audio_stats(wavs):
     out = (C.c_float * 4)()
     lib().orc_audio_stats_f32(_p(w, _pf32), w.shape[0], w.shape[1], out)
     return tuple(out)
+
+
+NORM_OFF, NORM_LUFS, NORM_RMS_DB, NORM_PEAK_DB = 0, 1, 2, 3
+GUARD_CLIP, GUARD_REDUCE_GLOBAL_LEVEL, GUARD_LIMITER = 0, 1, 2
+
+
+def normalize_gain(kind: int, target: float, global_lufs: float = 0.0, rms_dB: float = 0.0,
+                   max_peak_dB: float = 0.0) -> float:
+    """Normalize::normalize_default's gain (dynamics/normalize.rs:23-45)."""
+    return lib().orc_normalize_gain(kind, target, global_lufs, rms_dB, max_peak_dB)
+
+
+def apply_gain(wavs, gain: float, mode: int = GUARD_CLIP):
+    """AudioTrack::apply_gain + guard clipping (track.rs:152-171, audio.rs:49-63,134-160).
+    Returns (out (n_ch, n), before_clip or None, global_gain, [(max_reduction_gain_dB, reduction_cnt)] per channel)."""
+    w = _f32c(wavs)
+    if w.ndim == 1:
+        w = w[None, :]
+    out = np.empty_like(w)
+    before = np.empty_like(w)
+    gg = _f32()
+    dB = np.zeros(w.shape[0], np.float32)
+    cnt = np.zeros(w.shape[0], np.uint64)
+    rc = lib().orc_apply_gain(_p(w, _pf32), w.shape[0], w.shape[1], gain, mode, _p(out, _pf32), _p(before, _pf32),
+                              C.byref(gg), _p(dB, _pf32), _p(cnt, _pu64))
+    if rc:
+        raise ValueError("limiter mode is not restated")
+    clipped = mode == GUARD_CLIP and np.isfinite(gain) and gain != 1.0
+    return out, (before if clipped else None), gg.value, list(zip(dB.tolist(), cnt.tolist()))
 
 
 def sum_simd_order(x, align_elems: int = 0) -> float:

@@ -419,6 +419,70 @@ ORC_API void orc_audio_stats_f32(const float *wavs, uint64_t n_ch, uint64_t n, f
     out[3] = 20.0f * log10f(peak);
 }
 
+/* ------------------------------------------------------------------------- */
+/* f4  gain normalisation + guard clipping           */
+/* ------------------------------------------------------------------------- */
+/* Normalize::normalize_default (dynamics/normalize.rs:23-45): the gain of a target, from the ORIGINAL audio's
+   stats.  kind 0 Off, 1 LUFS, 2 RMSdB, 3 PeakdB.  `global_lufs` is f64 in the reference and narrowed first. */
+ORC_API float orc_normalize_gain(int kind, float target, double global_lufs, float rms_dB, float max_peak_dB) {
+    switch (kind) {
+    case 1: return powf(10.0f, (target - (float)global_lufs) / 20.0f);
+    case 2: return powf(10.0f, (target - rms_dB) / 20.0f);
+    case 3: return powf(10.0f, (target - max_peak_dB) / 20.0f);
+    default: return 1.0f;
+    }
+}
+
+static inline float orc_clamp_unit(float x) { /* f32::clamp(-1, 1): NaN stays NaN */
+    if (x < -1.0f) return -1.0f;
+    if (x > 1.0f) return 1.0f;
+    return x;
+}
+
+/* AudioTrack::apply_gain (track.rs:152-171) followed by Audio::mutate's guard clipping (audio.rs:49-63) for the
+   two elementwise modes: 0 Clip (audio.rs:134-144), 1 ReduceGlobalLevel (audio.rs:146-160).  wavs is (n_ch, n)
+   row-major = AudioTrack.original; out receives AudioTrack.audio.wavs; before_clip (may be NULL) receives
+   GuardClippingResult::WavBeforeClip in mode 0.  *global_gain = the GlobalGain of mode 1 (1 otherwise).
+   gc_dB / gc_cnt [n_ch] = GuardClippingStats {max_reduction_gain_dB, reduction_cnt} per channel
+   (dynamics/stats.rs:133-158,176-186).  A non-finite or unit gain restores the original (track.rs:160-161),
+   whose guard-clip state is GlobalGain(1) (audio.rs:33-44).  Returns 0, or -1 for the limiter mode (a sequential
+   recurrence, not restated). */
+ORC_API int orc_apply_gain(const float *wavs, uint64_t n_ch, uint64_t n, float gain, int mode, float *out,
+                           float *before_clip, float *global_gain, float *gc_dB, uint64_t *gc_cnt) {
+    *global_gain = 1.0f;
+    if (!isfinite(gain) || gain == 1.0f) {
+        memcpy(out, wavs, sizeof(float) * n_ch * n);
+        for (uint64_t c = 0; c < n_ch; c++) { gc_dB[c] = log10f(1.0f) * 20.0f; gc_cnt[c] = 0; }
+        return 0;
+    }
+    if (mode != 0 && mode != 1) return -1;
+    for (uint64_t i = 0; i < n_ch * n; i++) out[i] = gain * wavs[i];     /* azip!(*y = gain * x) */
+    if (mode == 0) {
+        if (before_clip) memcpy(before_clip, out, sizeof(float) * n_ch * n);
+        for (uint64_t c = 0; c < n_ch; c++) {
+            float *y = out + c * n;
+            const float peak = orc_abs_max_f32(y, n);                   /* from_wav_before_clip */
+            gc_dB[c] = 0.0f; gc_cnt[c] = 0;
+            if (peak > 1.0f) {
+                gc_dB[c] = log10f(1.0f / peak) * 20.0f;
+                for (uint64_t i = 0; i < n; i++) gc_cnt[c] += fabsf(y[i]) > 1.0f;
+            }
+            for (uint64_t i = 0; i < n; i++) y[i] = orc_clamp_unit(y[i]);
+        }
+    } else {
+        const double peak = (double)orc_abs_max_f32(out, n_ch * n);      /* wavs.max_peak() as f64 */
+        float g32 = 1.0f;
+        if (peak > 1.0) {
+            const double g = 1.0 / peak;
+            for (uint64_t i = 0; i < n_ch * n; i++) out[i] = orc_clamp_unit((float)((double)out[i] * g));
+            g32 = (float)g;
+        }
+        *global_gain = g32;
+        for (uint64_t c = 0; c < n_ch; c++) { gc_dB[c] = log10f(g32) * 20.0f; gc_cnt[c] = 0; }  /* from_global_gain */
+    }
+    return 0;
+}
+
 /* sum_avx2 order (simd.rs:594-619): scalar prefix up to 32-byte alignment, 8 lane
    accumulators over the aligned middle, lanes reduced, scalar suffix. `align_elems` = number of
    prefix elements (0..7) -- the reference derives it from the slice ADDRESS, so the sum is

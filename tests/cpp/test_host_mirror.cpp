@@ -196,6 +196,31 @@ static void test_gpu_flow() {
         st = calc_stats(ctx, a);
         EXPECT(std::fabs(st.rms_dB - 20.0f * std::log10(0.5f)) < 1e-5f && st.max_peak == 0.5f);
     }
+    // ---- Normalize / guard clipping (normalize.rs:84-110, dynamics/stats.rs:224-275) ----
+    {
+        AudioTrack t;
+        t.original.sr = 48000; t.original.len = 3; t.original.n_ch = 2;
+        t.original.wavs = {0.0f, 0.6f, -0.25f, -1.0f, 0.0f, 0.5f};
+        t.original_stats = calc_stats(ctx, t.original);
+        EXPECT(t.original_stats.max_peak == 1.0f && t.original_stats.max_peak_dB == 0.0f);
+        t.apply_gain(ctx, 2.0f, GuardClippingMode::Clip);
+        EXPECT(t.wav_before_clip[1] == 1.2f && t.wav_before_clip[3] == -2.0f && t.audio.wavs[1] == 1.0f && t.audio.wavs[3] == -1.0f);
+        EXPECT(t.guard_clip_stats[0].reduction_cnt == 1 && t.guard_clip_stats[1].reduction_cnt == 1);
+        EXPECT(std::fabs(t.guard_clip_stats[0].max_reduction_gain_dB - 20.0f * std::log10(1.0f / 1.2f)) < 1e-5f);
+        EXPECT(std::fabs(t.guard_clip_stats[1].max_reduction_gain_dB - 20.0f * std::log10(0.5f)) < 1e-5f);
+        EXPECT(t.stats.max_peak == 1.0f && t.global_gain == 1.0f);
+        t.apply_gain(ctx, 2.0f, GuardClippingMode::ReduceGlobalLevel);
+        EXPECT(t.global_gain == 0.5f && t.audio.wavs == t.original.wavs && t.wav_before_clip.empty());
+        EXPECT(t.guard_clip_stats[0].reduction_cnt == 0 && std::fabs(t.guard_clip_stats[1].max_reduction_gain_dB + 6.0206f) < 1e-4f);
+        // PeakdB(-6) on a track whose peak is 0 dB: gain 10^(-6/20), nothing to guard
+        t.normalize(ctx, NormalizeTarget{NormalizeTarget::PeakdB, -6.0f}, GuardClippingMode::Clip);
+        EXPECT(std::fabs(t.stats.max_peak_dB + 6.0f) < 1e-4f && t.guard_clip_stats[0].reduction_cnt == 0 && t.guard_clip_stats[0].max_reduction_gain_dB == 0.0f);
+        t.normalize(ctx, NormalizeTarget{}, GuardClippingMode::Limiter);   // Off: unit gain restores the original, any mode
+        EXPECT(t.audio.wavs == t.original.wavs && t.global_gain == 1.0f);
+        bool threw = false;
+        try { t.apply_gain(ctx, 2.0f, GuardClippingMode::Limiter); } catch (const Error &) { threw = true; }
+        EXPECT(threw);
+    }
     // ---- waveform tile KATs (render_tiles.rs:408-433) ----
     {
         const float wav[8] = {-1.0f, 0.5f, 0.25f, -0.75f, 0.1f, 0.2f, -0.3f, 0.9f};

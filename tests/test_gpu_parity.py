@@ -231,6 +231,59 @@ def test_channel_stats_parity(ctx, orc):
     assert z["rms_dB"] == -math.inf and z["max_peak_dB"] == -math.inf
 
 
+def test_apply_gain_parity(ctx, orc):
+    """SURVEY.md 8 f4: AudioTrack::apply_gain + guard clipping (track.rs:152-171, audio.rs:49-63,134-160).
+    Samples, WavBeforeClip, GlobalGain, reduction counts and abs max: bit-exact.  max_reduction_gain_dB: <= 1e-5 dB
+    (one log10f).  Sum of squares of the result: within f32 rounding of the exact sum."""
+    import torch
+    # the reference's own vectors (dynamics/stats.rs:224-275) through the device
+    r = ctx.apply_gain([dict(wavs=[np.array([-0.75, -0.5, 0.25, 1.0], np.float32)], gain=2.0)], _lib.GUARD_CLIP, True)[0]
+    assert np.array_equal(r["before_clip"][0], [-1.5, -1.0, 0.5, 2.0]) and np.array_equal(r["wavs"][0], [-1.0, -1.0, 0.5, 1.0])
+    assert r["guard_clip_stats"][0][1] == 2 and abs(r["guard_clip_stats"][0][0] - orc.dB_scalar(0.5)) <= 1e-5
+    rng = np.random.default_rng(5)
+    lens = [1, 5, 1 << 17, (1 << 17) + 3, 48000 * 11 + 1]
+    for mode in (_lib.GUARD_CLIP, _lib.GUARD_REDUCE_GLOBAL_LEVEL):
+        tracks, want = [], []
+        for ti, n in enumerate(lens):
+            w = (rng.standard_normal((2, n)) * 0.3).astype(np.float32)
+            if ti == 2:
+                w[1, 77] = 2.75                     # a peak in the other channel of the track
+            gain = [3.0, 1.0, 1.7, 0.25, float("nan")][ti]
+            tracks.append(dict(wavs=[w[0], w[1]], gain=gain, id=100 + ti))
+            want.append(orc.apply_gain(w, gain, mode))
+        for dev in (False, True):
+            tr = tracks if not dev else [dict(t, wavs=[torch.from_numpy(c).cuda() for c in t["wavs"]]) for t in tracks]
+            got = ctx.apply_gain(tr, mode, want_before_clip=True)
+            for t, g, (out, before, gg, st) in zip(tracks, got, want):
+                outs = [o.cpu().numpy() if dev else o for o in g["wavs"]]
+                assert np.array_equal(np.stack(outs), out, equal_nan=True), (mode, dev, t["id"])
+                if before is not None:
+                    bs = [b.cpu().numpy() if dev else b for b in g["before_clip"]]
+                    assert np.array_equal(np.stack(bs), before)
+                assert g["global_gain"] == gg
+                for (dB, cnt), (wdB, wcnt) in zip(g["guard_clip_stats"], st):
+                    assert cnt == wcnt and abs(dB - wdB) <= 1e-5
+                for c in range(2):
+                    exact = float(np.sum(out[c].astype(np.float64) ** 2))
+                    assert abs(g["sum_squares"][c] - exact) <= 1.2e-7 * exact
+                    assert g["abs_max"][c] == orc.abs_max(out[c])
+    # in place on the device, an odd (4-byte aligned) start, and 16-bit originals
+    w = (rng.standard_normal(300001) * 0.5).astype(np.float32)
+    d = torch.from_numpy(w).cuda()
+    ctx.apply_gain([dict(wavs=[d[1:]], outs=[d[1:]], gain=2.5)], _lib.GUARD_CLIP)
+    assert np.array_equal(d.cpu().numpy()[1:], orc.apply_gain(w[1:], 2.5, orc.GUARD_CLIP)[0][0]) and d[0].item() == w[0]
+    q = rng.integers(-32768, 32768, 200003, dtype=np.int16)
+    f = q.astype(np.float32) / np.float32(32768.0)
+    a = ctx.apply_gain([dict(wavs=[q], gain=1.9)], _lib.GUARD_REDUCE_GLOBAL_LEVEL)[0]
+    b = orc.apply_gain(f, 1.9, orc.GUARD_REDUCE_GLOBAL_LEVEL)
+    assert np.array_equal(a["wavs"][0], b[0][0]) and a["global_gain"] == b[2]
+    # channels of one track must share the gain; the limiter is not provided
+    with pytest.raises(thb.ThbError):
+        ctx.apply_gain([dict(wavs=[w], gain=2.0, id=1), dict(wavs=[w], gain=3.0, id=1)])
+    with pytest.raises(thb.ThbError):
+        ctx.apply_gain([dict(wavs=[w], gain=2.0)], _lib.GUARD_LIMITER)
+
+
 def _tile_fields(b):
     rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
     return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)

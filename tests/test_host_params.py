@@ -126,3 +126,15 @@ def test_mel_warp_schedule_is_the_filterbank(sr, n_mel):
     assert stats[2] <= (64 if fb.shape[1] <= 512 else 80)
     if n_mel in (0, 128):
         assert stats[3] <= 8  # (almost) bank-conflict free for the headline configurations
+
+
+# dynamics/normalize.rs:84-110 through the C ABI's host arithmetic (no device needed)
+def test_normalize_gain_matches_reference_tests(orc):
+    from thesia_b200.analysis import normalize_gain
+    assert normalize_gain(_lib.NORM_OFF, -3.0, -23.0, -12.0, -6.0) == 1.0
+    assert abs(normalize_gain(_lib.NORM_LUFS, -20.0, -23.0, -12.0, -6.0) - 10 ** (3.0 / 20.0)) <= 1e-6
+    assert abs(normalize_gain(_lib.NORM_RMS_DB, -18.0, -23.0, -12.0, -6.0) - 10 ** (-6.0 / 20.0)) <= 1e-6
+    assert abs(normalize_gain(_lib.NORM_PEAK_DB, -1.0, -23.0, -12.0, -6.0) - 10 ** (5.0 / 20.0)) <= 1e-6
+    for kind in range(4):
+        for tgt, a, b, c in ((-14.0, -26.2033, -31.5, -4.25), (0.0, -3.0, 1.5, 2.0)):
+            assert normalize_gain(kind, tgt, a, b, c) == orc.normalize_gain(kind, tgt, a, b, c)

@@ -288,3 +288,40 @@ def test_audio_stats(orc):
     assert abs(rms_dB - 10 * math.log10(ms)) < 1e-5 and peak == 1.0 and peak_dB == 0.0
     ms, rms_dB, peak, peak_dB = orc.audio_stats(np.zeros((2, 16), np.float32))
     assert ms == 0.0 and rms_dB == -math.inf and peak == 0.0 and peak_dB == -math.inf
+
+
+# dynamics/normalize.rs:84-110: normalize_off_applies_unity_gain..., normalize_targets_use_original_stats_to_compute_gain
+# (stats of the recorder: lufs -23, rms_dB -12, max_peak 0.5, max_peak_dB -6)
+def test_normalize_targets(orc):
+    assert orc.normalize_gain(orc.NORM_OFF, 0.0, -23.0, -12.0, -6.0) == 1.0
+    assert abs(orc.normalize_gain(orc.NORM_LUFS, -20.0, -23.0, -12.0, -6.0) - 10 ** (3.0 / 20.0)) <= 1e-6
+    assert abs(orc.normalize_gain(orc.NORM_RMS_DB, -18.0, -23.0, -12.0, -6.0) - 10 ** (-6.0 / 20.0)) <= 1e-6
+    assert abs(orc.normalize_gain(orc.NORM_PEAK_DB, -1.0, -23.0, -12.0, -6.0) - 10 ** (5.0 / 20.0)) <= 1e-6
+
+
+# dynamics/stats.rs:224-275: guard_clipping_stats_describe_clipped_samples, guard_clipping_result_converts_to_channel_stats
+def test_guard_clipping_stats(orc):
+    dB_half = orc.dB_scalar(0.5)
+    # a gain of 2 over half the reference's vector gives its "before clip" samples exactly
+    out, before, gg, st = orc.apply_gain(np.array([-0.75, -0.5, 0.25, 1.0], np.float32), 2.0, orc.GUARD_CLIP)
+    assert np.array_equal(before[0], [-1.5, -1.0, 0.5, 2.0]) and np.array_equal(out[0], [-1.0, -1.0, 0.5, 1.0])
+    assert st[0][1] == 2 and abs(st[0][0] - dB_half) <= 1e-5 and f"{st[0][0]:.2f}" == "-6.02" and gg == 1.0
+    out, before, gg, st = orc.apply_gain(np.array([-0.5, 0.125, 0.5], np.float32), 2.0, orc.GUARD_CLIP)
+    assert st == [(0.0, 0)] and np.array_equal(out, before)                  # unclipped -> default stats
+    out, before, gg, st = orc.apply_gain(np.array([[0.0, 0.6, -0.25], [-1.0, 0.0, 0.5]], np.float32), 2.0, orc.GUARD_CLIP)
+    assert [s[1] for s in st] == [1, 1]
+    assert abs(st[0][0] - orc.dB_scalar(np.float32(1.0) / np.float32(1.2))) <= 1e-5 and abs(st[1][0] - dB_half) <= 1e-5
+    # ReduceGlobalLevel: one gain 1 / peak over every channel (audio.rs:146-160), stats from_global_gain
+    out, before, gg, st = orc.apply_gain(np.array([[0.0, 0.6, -0.25], [-1.0, 0.0, 0.5]], np.float32), 2.0,
+                                         orc.GUARD_REDUCE_GLOBAL_LEVEL)
+    assert before is None and gg == 0.5 and np.array_equal(out, np.array([[0.0, 0.6, -0.25], [-1.0, 0.0, 0.5]], np.float32))
+    assert all(c == 0 and f"{d:.2f}" == "-6.02" for d, c in st)
+    out, _, gg, st = orc.apply_gain(np.array([0.25, -0.5], np.float32), 1.5, orc.GUARD_REDUCE_GLOBAL_LEVEL)
+    assert gg == 1.0 and np.array_equal(out[0], [0.375, -0.75]) and st == [(0.0, 0)]
+    # unit / non-finite gain restores the original (track.rs:160-161)
+    w = np.array([3.0, -2.0, 0.5], np.float32)
+    for g in (1.0, math.inf, math.nan):
+        out, before, gg, st = orc.apply_gain(w, g, orc.GUARD_CLIP)
+        assert np.array_equal(out[0], w) and before is None and gg == 1.0 and st == [(0.0, 0)]
+    with pytest.raises(ValueError):
+        orc.apply_gain(w, 2.0, orc.GUARD_LIMITER)

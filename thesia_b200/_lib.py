@@ -53,6 +53,19 @@ class AudioStats(C.Structure):
     _fields_ = [("mean_squared", C.c_float), ("rms_dB", C.c_float), ("max_peak", C.c_float), ("max_peak_dB", C.c_float)]
 
 
+class GainChannel(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("len", C.c_uint64), ("id", C.c_uint64), ("pcm_format", C.c_uint32),
+                ("gain", C.c_float), ("out", C.c_void_p), ("before_clip", C.c_void_p)]
+
+
+class GainResult(C.Structure):
+    _fields_ = [("global_gain", C.c_float), ("max_reduction_gain_dB", C.c_float), ("reduction_cnt", C.c_uint64),
+                ("sum_squares", C.c_float), ("abs_max", C.c_float)]
+
+
+NORM_OFF, NORM_LUFS, NORM_RMS_DB, NORM_PEAK_DB = 0, 1, 2, 3
+GUARD_CLIP, GUARD_REDUCE_GLOBAL_LEVEL, GUARD_LIMITER = 0, 1, 2
+
 _P = C.POINTER
 _vp, _u8p = C.c_void_p, _P(C.c_uint8)
 _u64, _u32, _f32, _i = C.c_uint64, C.c_uint32, C.c_float, C.c_int
@@ -74,6 +87,8 @@ SIGNATURES = {
     "thb_mel_fb": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
     "thb_channel_stats": (_i, [_vp, _P(Track), C.c_size_t, _P(_f32), _P(_f32)]),
     "thb_audio_stats": (_i, [_P(_f32), _P(_f32), _P(_u64), C.c_size_t, _P(AudioStats)]),
+    "thb_normalize_gain": (_f32, [_u32, _f32, C.c_double, _f32, _f32]),
+    "thb_apply_gain": (_i, [_vp, _P(GainChannel), C.c_size_t, _u32, _P(GainResult)]),
     "thb_mel_schedule_replay": (_i, [_u32, _u64, _u32, _P(_f32), _P(_u32)]),
     "thb_hz_range_to_idx": (_i, [_u32, _f32, _f32, _u32, _u64, _P(_u64), _P(_u64)]),
     "thb_spec_batch": (_i, [_vp, _P(Track), C.c_size_t, _P(Setting), _P(SpecOut)]),
@@ -127,7 +142,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.thb_abi_version() != 2:
+        if l.thb_abi_version() != 3:
             raise RuntimeError("libthesia_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -104,6 +104,12 @@ def hz_range_to_idx(freq_scale: int, hz_range: Tuple[float, float], sr: int, n_b
     return a.value, b.value
 
 
+def normalize_gain(kind: int, target: float, global_lufs: float = 0.0, rms_dB: float = 0.0,
+                   max_peak_dB: float = 0.0) -> float:
+    """Normalize::normalize_default's gain (dynamics/normalize.rs:23-45); kind = _lib.NORM_*."""
+    return lib().thb_normalize_gain(kind, target, global_lufs, rms_dB, max_peak_dB)
+
+
 def _ptr_len_fmt(x) -> Tuple[int, int, object, int]:
     """(address, n_samples, keep-alive, pcm_format) of a 1-D PCM array: int16 arrays / tensors are handed over as
     THB_PCM_I16 (sample = s / 32768), everything else as float32."""
@@ -345,6 +351,52 @@ class Context:
         check(lib().thb_audio_stats(ss.ctypes.data_as(C.POINTER(C.c_float)), mx.ctypes.data_as(C.POINTER(C.c_float)), lens,
                                     len(wavs), C.byref(out)), self._h)
         return dict(mean_squared=out.mean_squared, rms_dB=out.rms_dB, max_peak=out.max_peak, max_peak_dB=out.max_peak_dB)
+
+    # ---- gain normalisation + guard clipping (track.rs:152-171, audio.rs:49-63,134-160) ----
+    def apply_gain(self, tracks: Sequence[dict], mode: int = _lib.GUARD_CLIP, want_before_clip: bool = False):
+        """tracks: [{"wavs": [channel, ...], "gain": g, "id": optional}] -- one entry per Audio; channels are 1-D f32
+        (or int16) arrays / tensors, host or device.  Outputs are allocated like the inputs (numpy -> numpy,
+        torch -> torch on the same device) unless "outs" is given.  Returns per track a dict(wavs, before_clip,
+        global_gain, guard_clip_stats=[(max_reduction_gain_dB, reduction_cnt)], sum_squares, abs_max)."""
+        chans = []
+        keep = []
+        res = []
+        for ti, t in enumerate(tracks):
+            outs = t.get("outs")
+            entry = dict(wavs=[], before_clip=[] if want_before_clip and mode == _lib.GUARD_CLIP else None)
+            for ci, w in enumerate(t["wavs"]):
+                addr, ln, k, fmt = _ptr_len_fmt(w)
+                keep.append(k)
+
+                def alloc():
+                    if hasattr(w, "data_ptr"):
+                        import torch
+                        return torch.empty(ln, dtype=torch.float32, device=w.device)
+                    return np.empty(ln, np.float32)
+                o = outs[ci] if outs is not None else alloc()
+                o_addr = o.data_ptr() if hasattr(o, "data_ptr") else o.ctypes.data
+                b_addr = None
+                if entry["before_clip"] is not None:
+                    b = alloc()
+                    entry["before_clip"].append(b)
+                    b_addr = b.data_ptr() if hasattr(b, "data_ptr") else b.ctypes.data
+                entry["wavs"].append(o)
+                chans.append(_lib.GainChannel(addr, ln, int(t.get("id", ti)), fmt, float(t["gain"]), o_addr, b_addr))
+            res.append(entry)
+        n = len(chans)
+        arr = (_lib.GainChannel * n)(*chans)
+        out = (_lib.GainResult * n)()
+        check(lib().thb_apply_gain(self._h, arr, n, mode, out), self._h)
+        k = 0
+        for t, entry in zip(tracks, res):
+            m = len(t["wavs"])
+            rs = out[k:k + m]
+            k += m
+            entry["global_gain"] = rs[0].global_gain if m else 1.0
+            entry["guard_clip_stats"] = [(r.max_reduction_gain_dB, r.reduction_cnt) for r in rs]
+            entry["sum_squares"] = np.array([r.sum_squares for r in rs], np.float32)
+            entry["abs_max"] = np.array([r.abs_max for r in rs], np.float32)
+        return res
 
     # ---- multi-GPU ----
     @staticmethod

@@ -78,6 +78,25 @@ struct EnvDesc {
     uint8_t *out;        // device, tiles of this level concatenated in wire format
 };
 
+// One channel of thb_apply_gain (thb_gain.cu)
+struct GainDesc {
+    const void *in;      // device; f32 samples, or int16_t when pcm_i16
+    float *out;          // device, len floats (may alias `in` for f32)
+    float *before;       // device or null: gain * x before clipping (Clip mode)
+    long long len;
+    float gain;
+    int group;           // index of the track this channel belongs to (ReduceGlobalLevel peaks are per track)
+    int pcm_i16;
+    int pad_;
+};
+struct GainOut {
+    float sum_squares;               // of the output channel
+    unsigned abs_max_bits;           // bit pattern of the output's abs max (>= 0)
+    unsigned before_max_bits;        // bit pattern of max |gain * x| (Clip mode)
+    unsigned pad_;
+    unsigned long long reduction_cnt;  // samples with |gain * x| > 1 (Clip mode)
+};
+
 // sample `idx` of a channel's slice as f32: 16-bit PCM converts as s / 32768 (exact)
 __device__ __forceinline__ float pcm_sample(const TrackDesc &d, long long idx) {
     if (d.pcm_i16) return static_cast<float>(__ldg(reinterpret_cast<const short *>(d.pcm) + idx)) * 3.0517578125e-05f;
@@ -133,6 +152,13 @@ cudaError_t launch_envelope(const EnvDesc *d_descs, int n, long long max_len, ui
 long long stats_chunks(long long max_len);
 cudaError_t launch_channel_stats(const TrackDesc *d_descs, int n, long long max_len, double *d_part_ss, float *d_part_mx,
                                  float *d_out_ss, float *d_out_mx, cudaStream_t st);
+
+// gain + guard clipping (thb_gain.cu).  mode 0 Clip, 1 ReduceGlobalLevel (d_group_peak from launch_gain_peak), 2 copy.
+// d_part_ss: n * gain_chunks(max_len) doubles of scratch; d_outs: n results, zeroed by the caller.
+long long gain_chunks(long long max_len);
+cudaError_t launch_gain_peak(const GainDesc *d_descs, int n, long long max_len, unsigned *d_group_peak, cudaStream_t st);
+cudaError_t launch_gain_apply(const GainDesc *d_descs, int n, long long max_len, int mode, const unsigned *d_group_peak,
+                              double *d_part_ss, GainOut *d_outs, cudaStream_t st);
 
 cudaError_t launch_synth_pcm(float *d_out, unsigned long long len, uint32_t sr, uint32_t track,
                              uint32_t channel, uint32_t flags, cudaStream_t st);

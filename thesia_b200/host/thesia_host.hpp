@@ -370,6 +370,63 @@ inline AudioStats calc_stats(Context &ctx, const Audio &audio) {
     return AudioStats{st.rms_dB, st.max_peak, st.max_peak_dB};
 }
 
+// ---- gain normalisation + guard clipping ----------------------------------------------------
+// GuardClippingMode (dynamics/guardclipping.rs:6-12), NormalizeTarget (dynamics/normalize.rs:6-15)
+enum class GuardClippingMode : uint32_t { Clip = THB_GUARD_CLIP, ReduceGlobalLevel = THB_GUARD_REDUCE_GLOBAL_LEVEL, Limiter = THB_GUARD_LIMITER };
+struct NormalizeTarget {
+    enum Kind : uint32_t { Off = THB_NORM_OFF, LUFS = THB_NORM_LUFS, RMSdB = THB_NORM_RMS_DB, PeakdB = THB_NORM_PEAK_DB } kind = Off;
+    float target = 0.0f;
+};
+// GuardClippingStats (dynamics/stats.rs:110-158)
+struct GuardClippingStats {
+    float max_reduction_gain_dB = 0.0f;
+    uint64_t reduction_cnt = 0;
+};
+// AudioTrack (track.rs:28-171), the part Normalize touches: `original` never changes, `audio` = gain * original after
+// guard clipping, with the statistics and guard-clip state Audio::mutate leaves behind (audio.rs:49-63).
+struct AudioTrack {
+    Audio original, audio;
+    AudioStats original_stats, stats;
+    double original_global_lufs = 0.0;       // the loudness leg is computed on the CPU by the host program
+    std::vector<float> wav_before_clip;      // GuardClippingResult::WavBeforeClip (Clip mode, when anything was scaled)
+    float global_gain = 1.0f;                // GuardClippingResult::GlobalGain
+    std::vector<GuardClippingStats> guard_clip_stats;
+
+    // Normalize::normalize_default (normalize.rs:23-45) + AudioTrack::apply_gain (track.rs:158-171)
+    void normalize(Context &ctx, NormalizeTarget target, GuardClippingMode mode) {
+        apply_gain(ctx, thb_normalize_gain(target.kind, target.target, original_global_lufs, original_stats.rms_dB, original_stats.max_peak_dB), mode);
+    }
+    void apply_gain(Context &ctx, float gain, GuardClippingMode mode) {
+        audio = original;
+        const bool restore = !std::isfinite(gain) || gain == 1.0f;
+        const bool clip = mode == GuardClippingMode::Clip && !restore;
+        wav_before_clip.assign(clip ? original.wavs.size() : 0, 0.0f);
+        std::vector<thb_gain_channel> chans(original.n_ch);
+        for (uint32_t ch = 0; ch < original.n_ch; ch++) {
+            chans[ch] = thb_gain_channel{};
+            chans[ch].pcm = original.channel(ch);
+            chans[ch].len = original.len;
+            chans[ch].gain = gain;
+            chans[ch].out = audio.wavs.data() + static_cast<size_t>(ch) * audio.len;
+            chans[ch].before_clip = clip ? wav_before_clip.data() + static_cast<size_t>(ch) * audio.len : nullptr;
+        }
+        std::vector<thb_gain_result> res(original.n_ch);
+        check(thb_apply_gain(ctx.get(), chans.data(), chans.size(), static_cast<uint32_t>(mode), res.data()), ctx.get());
+        guard_clip_stats.assign(original.n_ch, GuardClippingStats{});
+        std::vector<float> ss(original.n_ch), mx(original.n_ch);
+        std::vector<uint64_t> lens(original.n_ch, original.len);
+        for (uint32_t ch = 0; ch < original.n_ch; ch++) {
+            guard_clip_stats[ch] = GuardClippingStats{res[ch].max_reduction_gain_dB, res[ch].reduction_cnt};
+            ss[ch] = res[ch].sum_squares;
+            mx[ch] = res[ch].abs_max;
+        }
+        global_gain = original.n_ch ? res[0].global_gain : 1.0f;
+        thb_audio_stats_t st{};
+        check(thb_audio_stats(ss.data(), mx.data(), lens.data(), original.n_ch, &st));
+        stats = AudioStats{st.rms_dB, st.max_peak, st.max_peak_dB};
+    }
+};
+
 // encode_waveform_tile(&[f32], u64, u32, u32) -> Vec<u8> (render_tiles.rs:232-279)
 inline std::vector<uint8_t> encode_waveform_tile(Context &ctx, const float *wav, uint64_t len, uint64_t revision, uint32_t level,
                                                  uint32_t tile_index) {

@@ -92,7 +92,26 @@ def envelope_case(ctx, n_ch, seconds, sr, reps, out):
     ctx.profile_enable(False)
     out({"config": "f3 channel_stats", "channels": n_ch, "samples_per_channel": n, "stats_ms": ms,
          "algorithmic_GBps": n_ch * 4 * n / (ms * 1e-3) / 1e9, "hbm_frac": n_ch * 4 * n / (ms * 1e-3) / 1e9 / HBM_GBS})
-    del pcm
+    # f4: gain + guard clipping in place on the device, 64 stereo tracks (4 B read + 4 B written per sample;
+    # ReduceGlobalLevel adds the read-only peak pass).  A gain of 4 makes both guards bite.
+    from thesia_b200 import _lib
+    scratch = torch.empty_like(pcm)
+    outs = [scratch[c, :n] for c in range(n_ch)]
+    tracks = [dict(wavs=wavs[2 * t:2 * t + 2], outs=outs[2 * t:2 * t + 2], gain=4.0, id=t) for t in range(n_ch // 2)]
+    for mode, name in ((_lib.GUARD_CLIP, "clip"), (_lib.GUARD_REDUCE_GLOBAL_LEVEL, "reduce_global_level")):
+        ctx.apply_gain(tracks, mode)
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        for _ in range(reps):
+            ctx.apply_gain(tracks, mode)
+        ms = ctx.profile_get("gain_apply")[0] / reps
+        ms_peak = ctx.profile_get("gain_peak")[0] / reps
+        ctx.profile_enable(False)
+        alg = n_ch * 8 * n
+        out({"config": "f4 apply_gain " + name, "channels": n_ch, "samples_per_channel": n, "gain_apply_ms": ms,
+             "gain_peak_ms": ms_peak, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS,
+             "peak_pass_GBps": (n_ch * 4 * n / (ms_peak * 1e-3) / 1e9) if ms_peak else None})
+    del pcm, scratch
     torch.cuda.empty_cache()
 
 
