@@ -185,9 +185,41 @@ int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t
  * for; TrackManager.spec_imgs as a whole).  outs[i] is HOST memory for (H_i, T_i) u16, caps[i] its size in pixels. */
 int thb_img_read_batch(thb_ctx *ctx, size_t n, const uint64_t *ids, const uint32_t *chs, uint16_t *const *outs,
                        const uint64_t *caps);
+/* Install a caller-provided image (height, width = T) u16 row-major (host or device memory) as the retained image of
+ * (id, ch), whose spectrogram must exist with T == width: lets a host restore cached images, and lets tests drive the
+ * tile path with the reference's own vectors (render_tiles.rs:435-471). */
+int thb_img_put(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t *img, uint64_t height, uint64_t width);
 /* device view of a retained image: rows are `pitch` u16 apart */
 int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr,
                        uint64_t *height, uint64_t *width, uint64_t *pitch);
+
+/* ---- encode_spectrogram_tile (src-tauri/src/core/render_tiles.rs:281-393) ---------------
+ * What RenderTileCache::spectrogram_tile (render_tiles.rs:170-188, called by get_spectrogram_tile, lib.rs:369-389)
+ * returns for the retained image of (id, ch): 40-byte header {u64 revision, u32 width, height, level_x, level_y,
+ * tile_x, tile_y, origin_x, origin_y} (little endian), then width x height RGBA pixels, the LAST row of the tile
+ * first (high frequencies first).  The tile is the 512 x 512 core at (tile_x, tile_y) of the level of detail
+ * (ceil(W / 2^level_x), ceil(H / 2^level_y)) plus a gutter of 4 pixels, resampled from the u16 image with the
+ * separable Lanczos3 convolution of fast_image_resize 6.0.0 (U16 pixels; third-party arithmetic restated from the
+ * crate's published algorithm) and mapped through `colormap_rgba` (RGBA bytes, >= 1 colour):
+ * index = (value * (colours - 1) + 32767) / 65535.  `out` is HOST memory; out == NULL (cap 0) queries the size.
+ * thb_spectrogram_tile_geometry: geo = {lod_width, lod_height, origin_x, origin_y, width, height}
+ * (render_tiles.rs:290-312; host arithmetic, no device needed). */
+int thb_spectrogram_tile_geometry(uint64_t height, uint64_t width, uint32_t level_x, uint32_t level_y, uint32_t tile_x,
+                                  uint32_t tile_y, uint64_t geo[6]);
+int thb_spectrogram_tile(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint8_t *colormap_rgba, size_t colormap_bytes,
+                         uint64_t revision, uint32_t level_x, uint32_t level_y, uint32_t tile_x, uint32_t tile_y, uint8_t *out,
+                         size_t cap, size_t *written);
+/* n tiles (any mix of tracks, levels and positions) in one pair of launches: what a redraw of the viewport asks for */
+typedef struct thb_spec_tile_req {
+    uint64_t id;
+    uint32_t ch, level_x, level_y, tile_x, tile_y;
+    uint32_t reserved;
+    uint8_t *out;    /* HOST memory, or NULL to query `written` */
+    size_t cap;
+    size_t written;  /* out: 40 + width * height * 4 */
+} thb_spec_tile_req;
+int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_t colormap_bytes, uint64_t revision,
+                               thb_spec_tile_req *reqs, size_t n);
 
 /* ---- encode_waveform_tile (src-tauri/src/core/render_tiles.rs:232-279) ----------------------
  * Byte-identical wire format: u64 revision, u32 bin_count, u32 samples_per_bin, u32 tile_index,
@@ -269,7 +301,7 @@ int thb_comm_destroy(thb_ctx *ctx);
  * Per-kernel CUDA-event timing on the ctx stream and a launch counter (bench.py's roofline /
  * gpu_launches).  Kernel names: "stft_mel_db", "stft_lin_db" (the main STFT kernel of a batch),
  * "stft_mel_db_edges", "stft_lin_db_edges" (file-edge frames and rescued tiles, when the main kernel
- * leaves them to the scalar one), "minmax_reduce", "minmax_array", "spec_to_img", "envelope", "channel_stats", "gain_peak", "gain_apply". */
+ * leaves them to the scalar one), "minmax_reduce", "minmax_array", "spec_to_img", "envelope", "channel_stats", "gain_peak", "gain_apply", "spectrogram_tile". */
 int thb_profile_enable(thb_ctx *ctx, int on);
 int thb_profile_reset(thb_ctx *ctx);
 int thb_profile_get(thb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *launches);

@@ -72,6 +72,9 @@ def _load() -> C.CDLL:
         "orc_normalize_gain": (_f32, [_int, _f32, _f64, _f32, _f32]),
         "orc_apply_gain": (_int, [_pf32, _u64, _u64, _f32, _int, _pf32, _pf32, _pf32, _pf32, _pu64]),
         "orc_encode_waveform_tile": (_u64, [_pf32, _u64, _u64, _u32, _u32, _pu8]),
+        "orc_resize_spectrogram_tile": (None, [_pu16, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _pu16]),
+        "orc_spectrogram_tile_geometry": (None, [_u64, _u64, _u32, _u32, _u32, _u32, _pu64]),
+        "orc_encode_spectrogram_tile": (_u64, [_pu16, _u64, _u64, _pu8, _u64, _u64, _u32, _u32, _u32, _u32, _pu8]),
         "orc_spec_to_img": (None, [_pf32, _u64, _u64, _u64, _u64, _f32, _f32, _int, _u32, _pu16]),
         "orc_clamp_minmax": (None, [_f32, _f32, _f32, _pf32, _pf32]),
         "orc_analyzer_new": (C.c_void_p, [_u32, _f64, _u32, _u32, _int, _u64]),
@@ -304,6 +307,33 @@ def encode_waveform_tile(wav, revision: int, level: int, tile_index: int) -> byt
 
 
 # ---- a14
+def spectrogram_tile_geometry(H: int, W: int, level_x: int, level_y: int, tile_x: int, tile_y: int):
+    """(lod_width, lod_height, origin_x, origin_y, width, height) of render_tiles.rs:290-312."""
+    g = (C.c_uint64 * 6)()
+    lib().orc_spectrogram_tile_geometry(H, W, level_x, level_y, tile_x, tile_y, g)
+    return tuple(g)
+
+
+def resize_spectrogram_tile(img, lod_w: int, lod_h: int, start_x: int, start_y: int, width: int, height: int):
+    img = np.ascontiguousarray(img, np.uint16)
+    out = np.empty((height, width), np.uint16)
+    lib().orc_resize_spectrogram_tile(_p(img, _pu16), img.shape[0], img.shape[1], lod_w, lod_h, start_x, start_y, width,
+                                      height, _p(out, _pu16))
+    return out
+
+
+def encode_spectrogram_tile(img, colormap_rgba, revision: int, level_x: int, level_y: int, tile_x: int, tile_y: int) -> bytes:
+    """encode_spectrogram_tile (render_tiles.rs:281-350); img is (H, W) u16, colormap_rgba a byte string of RGBA."""
+    img = np.ascontiguousarray(img, np.uint16)
+    cm = np.frombuffer(bytes(colormap_rgba), np.uint8)
+    n = lib().orc_encode_spectrogram_tile(_p(img, _pu16), img.shape[0], img.shape[1], _p(cm, _pu8), cm.size, revision,
+                                          level_x, level_y, tile_x, tile_y, None)
+    out = np.empty(n, np.uint8)
+    lib().orc_encode_spectrogram_tile(_p(img, _pu16), img.shape[0], img.shape[1], _p(cm, _pu8), cm.size, revision,
+                                      level_x, level_y, tile_x, tile_y, _p(out, _pu8))
+    return out.tobytes()
+
+
 def spec_to_img(spec, i_freq_range, dB_range, colormap_length=None) -> np.ndarray:
     spec = _f32c(spec)
     T, B = spec.shape

@@ -557,6 +557,188 @@ ORC_API uint64_t orc_encode_waveform_tile(const float *wav, uint64_t len, uint64
 }
 
 /* ------------------------------------------------------------------------- */
+/* f2  encode_spectrogram_tile  (src-tauri/src/core/render_tiles.rs:15-16,281-393) */
+/* ------------------------------------------------------------------------- */
+/* The resize itself is THIRD-PARTY arithmetic that is not in the checkout: fast_image_resize 6.0.0
+   (src-tauri/Cargo.toml:32), Resizer::resize_typed with ResizeAlg::Convolution(FilterType::Lanczos3) on
+   pixels::U16 and a fractional crop box (render_tiles.rs:352-393).  PARITY UNPINNED for the resampled values: this
+   is a restatement of that crate's published algorithm (the Pillow-SIMD scheme it documents): per axis, f64
+   coefficients of the filter stretched by max(scale, 1), bounds trimmed of leading / trailing zero weights,
+   normalised to sum 1, quantised to i32 fixed point with the largest precision that keeps the largest weight inside
+   i32, i64 accumulation seeded with half an LSB, arithmetic shift, clamp to u16; horizontal pass over the rows the
+   vertical pass needs, then the vertical pass.  The reference's own tests pin the layout, the LOD / gutter
+   arithmetic, the row flip and saturated values (render_tiles.rs:435-471), all reproduced by
+   tests/test_oracle_kat.py. */
+#define ORC_SPEC_TILE 512u
+#define ORC_SPEC_GUTTER 4u
+
+static double orc_sinc(double x) {
+    if (x == 0.0) return 1.0;
+    x *= M_PI;
+    return sin(x) / x;
+}
+static double orc_lanczos3(double x) { return (x >= -3.0 && x < 3.0) ? orc_sinc(x) * orc_sinc(x / 3.0) : 0.0; }
+
+/* one axis: bounds start[out], size[out], i32 weights w[out * window]; returns window, *precision */
+typedef struct { uint32_t *start, *size; int32_t *w; uint32_t window; uint32_t precision; uint32_t n; } orc_axis;
+
+static void orc_axis_free(orc_axis *a) { free(a->start); free(a->size); free(a->w); memset(a, 0, sizeof *a); }
+
+static void orc_axis_coeffs(uint32_t in_size, double in0, double in1, uint32_t out_size, orc_axis *a) {
+    memset(a, 0, sizeof *a);
+    a->n = out_size;
+    const double scale = (in1 - in0) / (double)out_size;
+    const double filter_scale = scale > 1.0 ? scale : 1.0;
+    const double radius = 3.0 * filter_scale;
+    const uint32_t window = (uint32_t)ceil(radius) * 2u + 1u;
+    const double recip = 1.0 / filter_scale;
+    double *c = (double *)calloc((size_t)window * out_size, sizeof(double));
+    a->start = (uint32_t *)calloc(out_size, sizeof(uint32_t));
+    a->size = (uint32_t *)calloc(out_size, sizeof(uint32_t));
+    a->w = (int32_t *)calloc((size_t)window * out_size, sizeof(int32_t));
+    a->window = window;
+    double max_w = 0.0;
+    for (uint32_t o = 0; o < out_size; o++) {
+        const double in_center = in0 + ((double)o + 0.5) * scale;
+        double lo = floor(in_center - radius), hi = ceil(in_center + radius);
+        if (lo < 0.0) lo = 0.0;
+        if (hi > (double)in_size) hi = (double)in_size;
+        const uint32_t x_min = (uint32_t)lo, x_max = (uint32_t)hi;
+        const double center = in_center - 0.5;
+        double *row = c + (size_t)o * window;
+        uint32_t n = 0, b0 = x_min, b1 = x_max;
+        double ww = 0.0;
+        for (uint32_t x = x_min; x < x_max; x++) {
+            const double w = orc_lanczos3(((double)x - center) * recip);
+            if (x == b0 && w == 0.0) b0++;          /* no zero weights at the start of the bound */
+            else { row[n++] = w; ww += w; }
+        }
+        for (uint32_t i = n; i-- > 0;) {            /* ... nor at its end */
+            if (b1 <= b0 || row[i] != 0.0) break;
+            b1--;
+        }
+        if (ww != 0.0) for (uint32_t i = 0; i < n; i++) row[i] /= ww;
+        a->start[o] = b0;
+        a->size[o] = b1 - b0;
+        for (uint32_t i = 0; i < window; i++) if (row[i] > max_w) max_w = row[i];
+    }
+    /* Normalizer32: precision = the last p for which round(max_w * 2^(p+1)) still fits below 2^31 */
+    uint32_t precision = 0;
+    for (uint32_t p = 0; p < 31; p++) {
+        precision = p;
+        const double next = round(max_w * (double)((int64_t)1 << (p + 1)));
+        if (next >= 2147483648.0) break;
+    }
+    a->precision = precision;
+    const double q = (double)((int64_t)1 << precision);
+    for (size_t i = 0; i < (size_t)window * out_size; i++) a->w[i] = (int32_t)round(c[i] * q);
+    free(c);
+}
+
+static inline uint16_t orc_fixed_clip(int64_t ss, uint32_t precision) {
+    const int64_t v = ss >> precision;
+    return (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+}
+
+/* resize_spectrogram_tile (render_tiles.rs:352-393): the (width, height) window at (start_x, start_y) of the
+   (lod_height, lod_width) level of detail of img (H, W) row-major u16 */
+ORC_API void orc_resize_spectrogram_tile(const uint16_t *img, uint64_t H, uint64_t W, uint64_t lod_w, uint64_t lod_h,
+                                         uint64_t start_x, uint64_t start_y, uint64_t width, uint64_t height,
+                                         uint16_t *out) {
+    const double left = (double)start_x * (double)W / (double)lod_w, top = (double)start_y * (double)H / (double)lod_h;
+    const double right = (double)(start_x + width) * (double)W / (double)lod_w;
+    const double bottom = (double)(start_y + height) * (double)H / (double)lod_h;
+    /* options.crop(left, top, right - left, bottom - top): the box handed to the resizer is (left, top, w, h) */
+    const double cw = right - left, chh = bottom - top;
+    orc_axis ax, ay;
+    orc_axis_coeffs((uint32_t)W, left, left + cw, (uint32_t)width, &ax);
+    orc_axis_coeffs((uint32_t)H, top, top + chh, (uint32_t)height, &ay);
+    const uint32_t y_first = ay.start[0];
+    const uint32_t y_last = ay.start[height - 1] + ay.size[height - 1];
+    const uint32_t tmp_h = y_last - y_first;
+    uint16_t *tmp = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)tmp_h * width);
+    for (uint32_t y = 0; y < tmp_h; y++) {
+        const uint16_t *row = img + (size_t)(y_first + y) * W;
+        for (uint32_t x = 0; x < width; x++) {
+            int64_t ss = (int64_t)1 << (ax.precision - 1);
+            const int32_t *k = ax.w + (size_t)x * ax.window;
+            for (uint32_t i = 0; i < ax.size[x]; i++) ss += (int64_t)row[ax.start[x] + i] * (int64_t)k[i];
+            tmp[(size_t)y * width + x] = orc_fixed_clip(ss, ax.precision);
+        }
+    }
+    for (uint32_t y = 0; y < height; y++) {
+        const int32_t *k = ay.w + (size_t)y * ay.window;
+        const uint32_t y0 = ay.start[y] - y_first;
+        for (uint32_t x = 0; x < width; x++) {
+            int64_t ss = (int64_t)1 << (ay.precision - 1);
+            for (uint32_t i = 0; i < ay.size[y]; i++) ss += (int64_t)tmp[(size_t)(y0 + i) * width + x] * (int64_t)k[i];
+            out[(size_t)y * width + x] = orc_fixed_clip(ss, ay.precision);
+        }
+    }
+    free(tmp);
+    orc_axis_free(&ax);
+    orc_axis_free(&ay);
+}
+
+static uint64_t orc_sat_mul(uint64_t a, uint64_t b) { return (b && a > UINT64_MAX / b) ? UINT64_MAX : a * b; }
+static uint64_t orc_sat_sub(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
+static uint64_t orc_min_u64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+/* geometry of a tile (render_tiles.rs:290-312): geo = {lod_width, lod_height, origin_x, origin_y, width, height} */
+ORC_API void orc_spectrogram_tile_geometry(uint64_t H, uint64_t W, uint32_t level_x, uint32_t level_y, uint32_t tile_x,
+                                           uint32_t tile_y, uint64_t geo[6]) {
+    const uint64_t sx = level_x < 64 ? ((uint64_t)1 << level_x) : UINT64_MAX;   /* checked_shl */
+    const uint64_t sy = level_y < 64 ? ((uint64_t)1 << level_y) : UINT64_MAX;
+    const uint64_t lod_w = W / sx + (W % sx != 0), lod_h = H / sy + (H % sy != 0);
+    const uint64_t start_x = orc_sat_mul(tile_x, ORC_SPEC_TILE), start_y = orc_sat_mul(tile_y, ORC_SPEC_TILE);
+    const uint64_t core_w = orc_min_u64(orc_sat_sub(lod_w, start_x), ORC_SPEC_TILE);
+    const uint64_t core_h = orc_min_u64(orc_sat_sub(lod_h, start_y), ORC_SPEC_TILE);
+    const uint64_t ox = orc_sat_sub(start_x, ORC_SPEC_GUTTER), oy = orc_sat_sub(start_y, ORC_SPEC_GUTTER);
+    uint64_t w = 0, h = 0;
+    if (core_w && core_h) {
+        w = orc_sat_sub(orc_min_u64(lod_w, start_x + core_w + ORC_SPEC_GUTTER), ox);
+        h = orc_sat_sub(orc_min_u64(lod_h, start_y + core_h + ORC_SPEC_GUTTER), oy);
+    }
+    geo[0] = lod_w; geo[1] = lod_h; geo[2] = ox; geo[3] = oy; geo[4] = w; geo[5] = h;
+}
+
+/* encode_spectrogram_tile (render_tiles.rs:281-350): 40-byte header {u64 revision, u32 width, height, level_x,
+   level_y, tile_x, tile_y, origin_x, origin_y} then RGBA rows, LAST row of the tile first (high frequencies first).
+   Returns the byte count; out == NULL queries it. */
+ORC_API uint64_t orc_encode_spectrogram_tile(const uint16_t *img, uint64_t H, uint64_t W, const uint8_t *colormap_rgba,
+                                             uint64_t colormap_bytes, uint64_t revision, uint32_t level_x,
+                                             uint32_t level_y, uint32_t tile_x, uint32_t tile_y, uint8_t *out) {
+    uint64_t g[6];
+    orc_spectrogram_tile_geometry(H, W, level_x, level_y, tile_x, tile_y, g);
+    const uint64_t width = g[4], height = g[5];
+    if (!out) return 40 + width * height * 4;
+    for (int i = 0; i < 8; i++) out[i] = (uint8_t)(revision >> (8 * i));
+    orc_put_u32(out + 8, (uint32_t)width);
+    orc_put_u32(out + 12, (uint32_t)height);
+    orc_put_u32(out + 16, level_x);
+    orc_put_u32(out + 20, level_y);
+    orc_put_u32(out + 24, tile_x);
+    orc_put_u32(out + 28, tile_y);
+    orc_put_u32(out + 32, (uint32_t)g[2]);
+    orc_put_u32(out + 36, (uint32_t)g[3]);
+    if (!width || !height) return 40;
+    uint16_t *px = (uint16_t *)malloc(sizeof(uint16_t) * width * height);
+    orc_resize_spectrogram_tile(img, H, W, g[0], g[1], g[2], g[3], width, height, px);
+    const uint64_t colors = colormap_bytes / 4;
+    uint8_t *o = out + 40;
+    for (uint64_t r = height; r-- > 0;) {
+        for (uint64_t x = 0; x < width; x++) {
+            const uint64_t v = px[r * width + x];
+            const uint64_t ci = colors <= 1 ? 0 : (v * (colors - 1) + 65535u / 2u) / 65535u;
+            memcpy(o, colormap_rgba + ci * 4, 4);
+            o += 4;
+        }
+    }
+    free(px);
+    return 40 + width * height * 4;
+}
+
+/* ------------------------------------------------------------------------- */
 /* a14 convert_spectrogram_to_img  (src-tauri/src/core/visualize/drawing.rs:4-33) */
 /* ------------------------------------------------------------------------- */
 /* spec: (T, B) row-major dB.  out: (i1 - i0, T) row-major u16. */

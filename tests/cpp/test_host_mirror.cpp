@@ -221,6 +221,27 @@ static void test_gpu_flow() {
         try { t.apply_gain(ctx, 2.0f, GuardClippingMode::Limiter); } catch (const Error &) { threw = true; }
         EXPECT(threw);
     }
+    // ---- spectrogram tile KATs (render_tiles.rs:435-471) ----
+    {
+        RenderTileCache cache(ctx);
+        cache.set_colormap({0, 0, 0, 255, 255, 0, 0, 255});
+        EXPECT(cache.spectrogram_revision == 2);
+        cache.set_colormap({1, 2, 3});                      // ignored, but the revision moves
+        EXPECT(cache.colormap_rgba.size() == 8 && cache.spectrogram_revision == 3);
+        const float spec2[2] = {0.0f, 0.0f};                // (T = 1, B = 2): only the shape matters, the image is put below
+        check(thb_spec_put(ctx.get(), 77, 0, 48000, THB_FREQ_LINEAR, spec2, 1, 2), ctx.get());
+        const uint16_t img[2] = {0, 65535};                 // (H = 2, W = 1)
+        check(thb_img_put(ctx.get(), 77, 0, img, 2, 1), ctx.get());
+        const std::vector<uint8_t> t = cache.spectrogram_tile(77, 0, 0, 0, 0, 0);
+        EXPECT(t.size() == 48);
+        uint64_t rev; uint32_t w, h;
+        std::memcpy(&rev, t.data(), 8); std::memcpy(&w, t.data() + 8, 4); std::memcpy(&h, t.data() + 12, 4);
+        EXPECT(rev == 3 && w == 1 && h == 2);
+        const uint8_t hi[4] = {255, 0, 0, 255}, lo[4] = {0, 0, 0, 255};   // high frequencies first
+        EXPECT(std::memcmp(t.data() + 40, hi, 4) == 0 && std::memcmp(t.data() + 44, lo, 4) == 0);
+        EXPECT(cache.spectrogram_tile(77, 0, 0, 0, 3, 0).size() == 40);   // a tile past the image: header only
+        check(thb_release(ctx.get(), 77, 0), ctx.get());
+    }
     // ---- waveform tile KATs (render_tiles.rs:408-433) ----
     {
         const float wav[8] = {-1.0f, 0.5f, 0.25f, -0.75f, 0.1f, 0.2f, -0.3f, 0.9f};

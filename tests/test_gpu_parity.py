@@ -284,6 +284,39 @@ def test_apply_gain_parity(ctx, orc):
         ctx.apply_gain([dict(wavs=[w], gain=2.0)], _lib.GUARD_LIMITER)
 
 
+def test_spectrogram_tile_parity(ctx, orc):
+    """encode_spectrogram_tile (render_tiles.rs:281-393).  Integer arithmetic end to end: every tile
+    must equal the oracle's byte for byte (header, resampled pixels, colormap, row flip).  The resampler itself is
+    third-party (fast_image_resize 6.0.0) and its parity with the real crate is unpinned -- see the oracle header."""
+    colors = bytes([0, 0, 0, 255, 255, 0, 0, 255])
+    # the reference's own three tests (render_tiles.rs:435-471) through the device
+    cases = [(np.array([[0, 65535], [65535, 65535]], np.uint16), (1, 1, 0, 0)),
+             (np.full((513, 513), 65535, np.uint16), (0, 0, 1, 1)),
+             (np.array([[0], [65535]], np.uint16), (0, 0, 0, 0))]
+    rng = np.random.default_rng(9)
+    smooth = (np.add.outer(np.arange(347) * 90.0, np.arange(5000) * 7.0) % 65536).astype(np.uint16)
+    noisy = rng.integers(0, 65536, (128, 3001), dtype=np.uint16)
+    cm258 = rng.integers(0, 256, 258 * 4, dtype=np.uint8).tobytes()
+    for img, reqs, cm in ((cases[0][0], [cases[0][1]], colors), (cases[1][0], [cases[1][1], (0, 0, 0, 0), (0, 0, 5, 0)], colors),
+                          (cases[2][0], [cases[2][1]], colors),
+                          (smooth, [(0, 0, 0, 0), (0, 0, 9, 0), (1, 0, 2, 0), (2, 1, 1, 0), (3, 0, 0, 0), (0, 2, 4, 0), (5, 3, 0, 0),
+                                    (12, 9, 0, 0)], cm258),
+                          (noisy, [(0, 0, 5, 0), (1, 1, 1, 0), (4, 0, 0, 0), (2, 6, 0, 0), (7, 7, 0, 0)], cm258),
+                          (noisy, [(0, 0, 0, 0)], bytes([9, 8, 7, 6]))):
+        ctx.spec_put(900, 0, 48000, thb.FreqScale.Mel, np.zeros((img.shape[1], 1), np.float32))   # T = image width
+        ctx.img_put(900, 0, img)
+        got = ctx.spectrogram_tiles(cm, 4, [(900, 0) + r for r in reqs])
+        for r, g in zip(reqs, got):
+            want = orc.encode_spectrogram_tile(img, cm, 4, *r)
+            assert g == want, (img.shape, r, len(g), len(want))
+    assert ctx.spectrogram_tile(900, 0, colors, 4, 1, 1, 0, 0) == orc.encode_spectrogram_tile(noisy, colors, 4, 1, 1, 0, 0)
+    with pytest.raises(thb.ThbError):
+        ctx.spectrogram_tile(900, 0, b"\x00\x01\x02", 1, 0, 0, 0, 0)     # not RGBA (set_colormap, render_tiles.rs:80-85)
+    with pytest.raises(thb.ThbError):
+        ctx.spectrogram_tile(901, 0, colors, 1, 0, 0, 0, 0)                # no such track
+    ctx.release(900, 0)
+
+
 def _tile_fields(b):
     rev, bins, spb, idx, zero = struct.unpack_from("<QIIII", b, 0)
     return rev, bins, spb, idx, zero, np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)

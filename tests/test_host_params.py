@@ -138,3 +138,14 @@ def test_normalize_gain_matches_reference_tests(orc):
     for kind in range(4):
         for tgt, a, b, c in ((-14.0, -26.2033, -31.5, -4.25), (0.0, -3.0, 1.5, 2.0)):
             assert normalize_gain(kind, tgt, a, b, c) == orc.normalize_gain(kind, tgt, a, b, c)
+
+
+# render_tiles.rs:290-312 through the C ABI (host arithmetic): LOD sizes, gutters, partial and absent tiles
+def test_spectrogram_tile_geometry_matches_oracle(orc):
+    from thesia_b200.analysis import spectrogram_tile_geometry
+    assert spectrogram_tile_geometry(513, 513, 0, 0, 1, 1) == (513, 513, 508, 508, 5, 5)     # render_tiles.rs:447-463
+    assert spectrogram_tile_geometry(2, 2, 1, 1, 0, 0) == (1, 1, 0, 0, 1, 1)                 # render_tiles.rs:436-444
+    for H, W in ((128, 56251), (1025, 4128), (8193, 337501), (1, 1), (347, 675001)):
+        for lx, ly, tx, ty in ((0, 0, 0, 0), (0, 0, 3, 0), (3, 1, 1, 0), (9, 4, 0, 0), (40, 70, 0, 0), (2, 0, 10 ** 6, 0),
+                               (0, 0, W // 512, H // 512), (1, 1, (W // 2) // 512, 0), (0, 3, 5, 1)):
+            assert spectrogram_tile_geometry(H, W, lx, ly, tx, ty) == orc.spectrogram_tile_geometry(H, W, lx, ly, tx, ty)

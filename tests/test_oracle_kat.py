@@ -325,3 +325,46 @@ def test_guard_clipping_stats(orc):
         assert np.array_equal(out[0], w) and before is None and gg == 1.0 and st == [(0.0, 0)]
     with pytest.raises(ValueError):
         orc.apply_gain(w, 2.0, orc.GUARD_LIMITER)
+
+
+# render_tiles.rs:435-471: spectrogram_tile_handles_lod_and_edges, ..._handles_partial_last_tile,
+# ..._outputs_high_frequencies_first
+def _tile_hdr(b):
+    return struct.unpack_from("<QIIIIIIII", b, 0)
+
+
+def test_spectrogram_tile_kats(orc):
+    colors = bytes([0, 0, 0, 255, 255, 0, 0, 255])
+    b = orc.encode_spectrogram_tile(np.array([[0, 65535], [65535, 65535]], np.uint16), colors, 4, 1, 1, 0, 0)
+    assert _tile_hdr(b)[:3] == (4, 1, 1) and b[40:] == bytes([255, 0, 0, 255])
+    spec = np.full((513, 513), 65535, np.uint16)
+    b = orc.encode_spectrogram_tile(spec, colors, 4, 0, 0, 1, 1)
+    h = _tile_hdr(b)
+    assert h[1] == 5 and h[2] == 5 and h[7] == 508 and h[8] == 508
+    assert len(b) == 40 + 100 and all(b[40 + 4 * i:44 + 4 * i] == bytes([255, 0, 0, 255]) for i in range(25))
+    b = orc.encode_spectrogram_tile(np.array([[0], [65535]], np.uint16), colors, 4, 0, 0, 0, 0)
+    assert b[40:44] == bytes([255, 0, 0, 255]) and b[44:48] == bytes([0, 0, 0, 255])
+    # a tile past the image: header only, zero size
+    b = orc.encode_spectrogram_tile(spec, colors, 9, 0, 0, 7, 0)
+    assert len(b) == 40 and _tile_hdr(b)[1:3] == (0, 0)
+
+
+def test_spectrogram_tile_resampler_properties(orc):
+    """What the restated fast_image_resize convolution must satisfy whatever its rounding details: level 0 is the
+    identity (Lanczos weights at integer offsets vanish), a constant image stays constant at every level, and a
+    2x box-aligned downscale of a smooth ramp stays within 1 LSB of the ramp's own value at the new pixel centres."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 65536, (300, 700), dtype=np.uint16)
+    g = orc.spectrogram_tile_geometry(300, 700, 0, 0, 1, 0)
+    assert g == (700, 300, 508, 0, 192, 300)
+    out = orc.resize_spectrogram_tile(img, g[0], g[1], g[2], g[3], g[4], g[5])
+    assert np.array_equal(out, img[:, 508:700])
+    for lx, ly in ((1, 0), (0, 2), (3, 3), (5, 1)):
+        g = orc.spectrogram_tile_geometry(300, 700, lx, ly, 0, 0)
+        const = orc.resize_spectrogram_tile(np.full((300, 700), 12345, np.uint16), g[0], g[1], g[2], g[3], g[4], g[5])
+        assert const.shape == (g[5], g[4]) and np.all(const == 12345)
+    ramp = np.tile((np.arange(1024) * 32).astype(np.uint16), (8, 1))
+    g = orc.spectrogram_tile_geometry(8, 1024, 1, 0, 0, 0)
+    out = orc.resize_spectrogram_tile(ramp, g[0], g[1], g[2], g[3], g[4], g[5])
+    want = (np.arange(g[4]) * 2 + 0.5) * 32
+    assert np.abs(out[4, 8:-8].astype(np.float64) - want[8:-8]).max() <= 1.0

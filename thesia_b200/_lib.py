@@ -63,6 +63,12 @@ class GainResult(C.Structure):
                 ("sum_squares", C.c_float), ("abs_max", C.c_float)]
 
 
+class SpecTileReq(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("ch", C.c_uint32), ("level_x", C.c_uint32), ("level_y", C.c_uint32),
+                ("tile_x", C.c_uint32), ("tile_y", C.c_uint32), ("reserved", C.c_uint32), ("out", C.c_void_p),
+                ("cap", C.c_size_t), ("written", C.c_size_t)]
+
+
 NORM_OFF, NORM_LUFS, NORM_RMS_DB, NORM_PEAK_DB = 0, 1, 2, 3
 GUARD_CLIP, GUARD_REDUCE_GLOBAL_LEVEL, GUARD_LIMITER = 0, 1, 2
 
@@ -103,7 +109,12 @@ SIGNATURES = {
     "thb_update_spec_imgs": (_i, [_vp, _f32, _u32, _u32, _P(_u64), C.c_size_t, _P(_f32), _P(_f32)]),
     "thb_img_read": (_i, [_vp, _u64, _u32, _vp, _u64, _P(_u64), _P(_u64)]),
     "thb_img_read_batch": (_i, [_vp, C.c_size_t, _P(_u64), _P(_u32), _P(_vp), _P(_u64)]),
+    "thb_img_put": (_i, [_vp, _u64, _u32, _vp, _u64, _u64]),
     "thb_img_device_ptr": (_i, [_vp, _u64, _u32, _P(_vp), _P(_u64), _P(_u64), _P(_u64)]),
+    "thb_spectrogram_tile_geometry": (_i, [_u64, _u64, _u32, _u32, _u32, _u32, _P(_u64)]),
+    "thb_spectrogram_tile": (_i, [_vp, _u64, _u32, _vp, C.c_size_t, _u64, _u32, _u32, _u32, _u32, _vp, C.c_size_t,
+                                  _P(C.c_size_t)]),
+    "thb_spectrogram_tile_batch": (_i, [_vp, _vp, C.c_size_t, _u64, _P(SpecTileReq), C.c_size_t]),
     "thb_waveform_tile": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),
     "thb_waveform_level": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),
     "thb_waveform_level_batch": (_i, [_vp, _P(Track), C.c_size_t, _u64, _u32, _P(_vp), _P(C.c_size_t),

@@ -104,6 +104,16 @@ def hz_range_to_idx(freq_scale: int, hz_range: Tuple[float, float], sr: int, n_b
     return a.value, b.value
 
 
+SPECTROGRAM_TILE_SIZE = 512   # render_tiles.rs:15
+
+
+def spectrogram_tile_geometry(height: int, width: int, level_x: int, level_y: int, tile_x: int, tile_y: int):
+    """(lod_width, lod_height, origin_x, origin_y, width, height) of a tile (render_tiles.rs:290-312)."""
+    g = (C.c_uint64 * 6)()
+    check(lib().thb_spectrogram_tile_geometry(height, width, level_x, level_y, tile_x, tile_y, g))
+    return tuple(g)
+
+
 def normalize_gain(kind: int, target: float, global_lufs: float = 0.0, rms_dB: float = 0.0,
                    max_peak_dB: float = 0.0) -> float:
     """Normalize::normalize_default's gain (dynamics/normalize.rs:23-45); kind = _lib.NORM_*."""
@@ -274,6 +284,11 @@ class Context:
         check(lib().thb_img_read(self._h, id, ch, out.ctypes.data, out.size, None, None), self._h)
         return out
 
+    def img_put(self, id: int, ch: int, img: np.ndarray) -> None:
+        """thb_img_put: install an (H, T) u16 image as the retained image of (id, ch)."""
+        img = np.ascontiguousarray(img, np.uint16)
+        check(lib().thb_img_put(self._h, id, ch, img.ctypes.data, img.shape[0], img.shape[1]), self._h)
+
     def img_read_batch_into(self, id_chs: Sequence[IdCh], addrs: Sequence[int], caps: Sequence[int]) -> None:
         """thb_img_read_batch: all copies queued, one wait."""
         n = len(id_chs)
@@ -327,6 +342,28 @@ class Context:
         if want_host:
             return [o.tobytes() for o in outs]
         return [(dev[i], written[i]) for i in range(n)]
+
+    # ---- spectrogram tiles (render_tiles.rs:170-188,281-393) ----
+    def spectrogram_tile(self, id: int, ch: int, colormap_rgba: bytes, revision: int, level_x: int, level_y: int,
+                         tile_x: int, tile_y: int) -> bytes:
+        """encode_spectrogram_tile for the retained image of (id, ch)."""
+        return self.spectrogram_tiles(colormap_rgba, revision, [(id, ch, level_x, level_y, tile_x, tile_y)])[0]
+
+    def spectrogram_tiles(self, colormap_rgba: bytes, revision: int, reqs: Sequence[Tuple[int, int, int, int, int, int]],
+                          want_bytes: bool = True):
+        """n tiles (id, ch, level_x, level_y, tile_x, tile_y) in one pair of launches."""
+        n = len(reqs)
+        cm = np.frombuffer(bytes(colormap_rgba), np.uint8)
+        arr = (_lib.SpecTileReq * n)()
+        for i, r in enumerate(reqs):
+            arr[i] = _lib.SpecTileReq(int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]), 0, None, 0, 0)
+        check(lib().thb_spectrogram_tile_batch(self._h, cm.ctypes.data, cm.size, revision, arr, n), self._h)  # sizes
+        bufs = [np.empty(arr[i].written, np.uint8) for i in range(n)]
+        for i in range(n):
+            arr[i].out = bufs[i].ctypes.data
+            arr[i].cap = bufs[i].size
+        check(lib().thb_spectrogram_tile_batch(self._h, cm.ctypes.data, cm.size, revision, arr, n), self._h)
+        return [b.tobytes() for b in bufs] if want_bytes else bufs
 
     # ---- level statistics (dynamics/stats.rs:56-85 without the loudness leg) ----
     def channel_stats(self, wavs: Sequence) -> Tuple[np.ndarray, np.ndarray]:

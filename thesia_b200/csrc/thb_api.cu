@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -140,6 +141,15 @@ struct thb_ctx {
     size_t rescue_cap = 0;
 
     std::vector<void *> env_outputs;  // device buffers of the last waveform call
+
+    // resize axes of the spectrogram tiles (thb_host.hpp ResizeAxis) on the device, keyed by
+    // (in_size, lod_size, origin, out_size): every tile of one tile row / column of a level shares one
+    struct AxisDev {
+        unsigned *start = nullptr, *size = nullptr;
+        int *w = nullptr;
+        unsigned n = 0, window = 0, precision = 0, first = 0, end = 0;
+    };
+    std::map<std::tuple<uint32_t, uint64_t, uint64_t, uint32_t>, AxisDev> tile_axes;
 
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -572,6 +582,11 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     for (auto &kv : ctx->specs) spec_free(ctx, kv.second);
     ctx->specs.clear();
     for (void *p : ctx->env_outputs) cudaFreeAsync(p, ctx->stream);
+    for (auto &kv : ctx->tile_axes) {
+        cudaFree(kv.second.start);
+        cudaFree(kv.second.size);
+        cudaFree(kv.second.w);
+    }
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->plans)
         for (void *p : kv.second->allocs) cudaFree(p);
@@ -1325,6 +1340,23 @@ int thb_img_read_batch(thb_ctx *ctx, size_t n, const uint64_t *ids, const uint32
     return THB_OK;
 }
 
+int thb_img_put(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t *img, uint64_t height, uint64_t width) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!img && height * width) return fail(ctx, THB_ERR_INVALID, "img is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Spec *sp = find_spec(ctx, id, ch);
+    if (!sp) return fail(ctx, THB_ERR_NOT_FOUND, "no spectrogram for (%llu, %u)", (unsigned long long)id, ch);
+    if (sp->T != width) return fail(ctx, THB_ERR_INVALID, "image width %llu != %llu frames", (unsigned long long)width, (unsigned long long)sp->T);
+    int rc = img_prepare(ctx, *sp, height);
+    if (rc) return rc;
+    if (height && width)
+        CK(cudaMemcpy2DAsync(sp->d_img, sizeof(uint16_t) * sp->img_pitch, img, sizeof(uint16_t) * width, sizeof(uint16_t) * width, height,
+                             cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
 int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **dptr, uint64_t *height, uint64_t *width,
                        uint64_t *pitch) {
     if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
@@ -1336,6 +1368,178 @@ int thb_img_device_ptr(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint16_t **
     if (width) *width = sp->T;
     if (pitch) *pitch = sp->img_pitch;
     return THB_OK;
+}
+
+// ---- spectrogram tiles (render_tiles.rs:281-393) ----------------------------------------------------
+int thb_spectrogram_tile_geometry(uint64_t height, uint64_t width, uint32_t level_x, uint32_t level_y, uint32_t tile_x,
+                                  uint32_t tile_y, uint64_t geo[6]) {
+    if (!geo) return fail(nullptr, THB_ERR_INVALID, "geo is NULL");
+    const thb::TileGeometry g = thb::spectrogram_tile_geometry(height, width, level_x, level_y, tile_x, tile_y);
+    geo[0] = g.lod_width; geo[1] = g.lod_height; geo[2] = g.origin_x; geo[3] = g.origin_y; geo[4] = g.width; geo[5] = g.height;
+    return THB_OK;
+}
+
+namespace {
+int get_tile_axis(thb_ctx *ctx, uint32_t in_size, uint64_t lod_size, uint64_t origin, uint32_t out_size, const thb_ctx::AxisDev **out) {
+    const auto key = std::make_tuple(in_size, lod_size, origin, out_size);
+    auto it = ctx->tile_axes.find(key);
+    if (it != ctx->tile_axes.end()) {
+        *out = &it->second;
+        return THB_OK;
+    }
+    // render_tiles.rs:379-383: the crop box in source pixels, f64
+    const double in0 = static_cast<double>(origin) * static_cast<double>(in_size) / static_cast<double>(lod_size);
+    const double in1 = static_cast<double>(origin + out_size) * static_cast<double>(in_size) / static_cast<double>(lod_size);
+    const thb::ResizeAxis a = thb::resize_axis(in_size, in0, in0 + (in1 - in0), out_size);
+    thb_ctx::AxisDev d;
+    d.n = a.n;
+    d.window = a.window;
+    d.precision = a.precision;
+    d.first = UINT32_MAX;
+    d.end = 0;
+    for (uint32_t o = 0; o < a.n; o++) {
+        d.first = std::min(d.first, a.start[o]);
+        d.end = std::max(d.end, a.start[o] + a.size[o]);
+    }
+    CK(cudaMalloc(reinterpret_cast<void **>(&d.start), sizeof(unsigned) * a.n));
+    CK(cudaMalloc(reinterpret_cast<void **>(&d.size), sizeof(unsigned) * a.n));
+    CK(cudaMalloc(reinterpret_cast<void **>(&d.w), sizeof(int) * a.w_t.size()));
+    // the vectors die with this scope: plain (staged) copies, ordered before later work on the stream
+    CK(cudaMemcpyAsync(d.start, a.start.data(), sizeof(unsigned) * a.n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d.size, a.size.data(), sizeof(unsigned) * a.n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d.w, a.w_t.data(), sizeof(int) * a.w_t.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = &ctx->tile_axes.emplace(key, d).first->second;
+    return THB_OK;
+}
+}  // namespace
+
+int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_t colormap_bytes, uint64_t revision,
+                               thb_spec_tile_req *reqs, size_t n) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return THB_OK;
+    if (!reqs) return fail(ctx, THB_ERR_INVALID, "reqs is NULL");
+    if (!colormap_rgba || colormap_bytes < 4 || colormap_bytes % 4)  // RenderTileCache::set_colormap (render_tiles.rs:80-85)
+        return fail(ctx, THB_ERR_INVALID, "colormap must be a non-empty RGBA table");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    struct Work { size_t req; thb::TileGeometry g; const Spec *sp; };
+    std::vector<Work> work;
+    for (size_t i = 0; i < n; i++) {
+        thb_spec_tile_req &r = reqs[i];
+        const Spec *sp = find_spec(ctx, r.id, r.ch);
+        if (!sp || !sp->d_img) return fail(ctx, THB_ERR_NOT_FOUND, "no image for (%llu, %u)", (unsigned long long)r.id, r.ch);
+        const thb::TileGeometry g = thb::spectrogram_tile_geometry(sp->img_H, sp->T, r.level_x, r.level_y, r.tile_x, r.tile_y);
+        r.written = 40 + static_cast<size_t>(g.width) * g.height * 4;
+        if (!r.out || r.cap < r.written) {
+            if (r.out) return fail(ctx, THB_ERR_SMALL_BUFFER, "tile %zu: need %zu bytes", i, r.written);
+            continue;  // size query
+        }
+        uint8_t *o = r.out;   // header (render_tiles.rs:314-323), little endian
+        memcpy(o, &revision, 8);
+        const uint32_t hdr[8] = {static_cast<uint32_t>(g.width), static_cast<uint32_t>(g.height), r.level_x, r.level_y, r.tile_x, r.tile_y,
+                                 static_cast<uint32_t>(g.origin_x), static_cast<uint32_t>(g.origin_y)};
+        memcpy(o + 8, hdr, 32);
+        if (g.width && g.height) work.push_back({i, g, sp});
+    }
+    if (work.empty()) return THB_OK;
+    const size_t m = work.size();
+    std::vector<const thb_ctx::AxisDev *> axs(m), ays(m);
+    if (ctx->tile_axes.size() + 2 * m > 1024) {  // bound the cache: drop everything while nothing can be reading it
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (auto &kv : ctx->tile_axes) {
+            cudaFree(kv.second.start);
+            cudaFree(kv.second.size);
+            cudaFree(kv.second.w);
+        }
+        ctx->tile_axes.clear();
+    }
+    for (size_t k = 0; k < m; k++) {   // a cache miss synchronises: all lookups come before the arena is in use
+        const Work &w = work[k];
+        int rc = get_tile_axis(ctx, static_cast<uint32_t>(w.sp->T), w.g.lod_width, w.g.origin_x, static_cast<uint32_t>(w.g.width), &axs[k]);
+        if (!rc) rc = get_tile_axis(ctx, static_cast<uint32_t>(w.sp->img_H), w.g.lod_height, w.g.origin_y, static_cast<uint32_t>(w.g.height), &ays[k]);
+        if (rc) return rc;
+    }
+    int rc = arena_begin(ctx, (sizeof(thb::TileDesc) + 64) * m + 1024);
+    if (rc) return rc;
+    thb::TileDesc *d_desc = nullptr;
+    thb::TileDesc *h = arena_push<thb::TileDesc>(ctx, m, &d_desc);
+    size_t tmp_total = 0, out_total = 0;
+    unsigned max_w = 0, max_h = 0, max_tmp_h = 0;
+    for (size_t k = 0; k < m; k++) {
+        const unsigned tmp_h = ays[k]->end - ays[k]->first;
+        tmp_total += (static_cast<size_t>(tmp_h) * work[k].g.width + 7) & ~size_t(7);
+        out_total += static_cast<size_t>(work[k].g.width) * work[k].g.height * 4;
+        max_w = std::max<unsigned>(max_w, static_cast<unsigned>(work[k].g.width));
+        max_h = std::max<unsigned>(max_h, static_cast<unsigned>(work[k].g.height));
+        max_tmp_h = std::max(max_tmp_h, tmp_h);
+    }
+    uint16_t *d_tmp = nullptr;
+    uint8_t *d_out = nullptr;
+    uchar4 *d_cm = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_tmp), sizeof(uint16_t) * tmp_total + 16, ctx->stream));
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), out_total + 16, ctx->stream));
+    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_cm), colormap_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_cm, colormap_rgba, colormap_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    size_t tmp_off = 0, out_off = 0;
+    for (size_t k = 0; k < m; k++) {
+        const Work &w = work[k];
+        thb::TileDesc &t = h[k];
+        memset(&t, 0, sizeof t);
+        t.img = w.sp->d_img;
+        t.pitch = w.sp->img_pitch;
+        t.x_start = axs[k]->start;
+        t.x_size = axs[k]->size;
+        t.wx = axs[k]->w;
+        t.y_start = ays[k]->start;
+        t.y_size = ays[k]->size;
+        t.wy = ays[k]->w;
+        t.width = static_cast<unsigned>(w.g.width);
+        t.height = static_cast<unsigned>(w.g.height);
+        t.y_first = ays[k]->first;
+        t.tmp_h = ays[k]->end - ays[k]->first;
+        t.px = axs[k]->precision;
+        t.py = ays[k]->precision;
+        t.tmp = d_tmp + tmp_off;
+        t.out = d_out + out_off;
+        tmp_off += (static_cast<size_t>(t.tmp_h) * t.width + 7) & ~size_t(7);
+        out_off += static_cast<size_t>(t.width) * t.height * 4;
+    }
+    if ((rc = arena_commit(ctx))) return rc;
+    {
+        ProfScope ps(ctx, "spectrogram_tile", 2 * static_cast<int>((m + 65534) / 65535));
+        cudaError_t e = thb::launch_spectrogram_tiles(d_desc, static_cast<int>(m), max_w, max_h, max_tmp_h, d_cm,
+                                                      static_cast<unsigned>(colormap_bytes / 4), ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spectrogram_tile: %s", cudaGetErrorString(e));
+    }
+    out_off = 0;
+    for (size_t k = 0; k < m; k++) {
+        const size_t bytes = static_cast<size_t>(work[k].g.width) * work[k].g.height * 4;
+        CK(cudaMemcpyAsync(reqs[work[k].req].out + 40, d_out + out_off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        out_off += bytes;
+    }
+    CK(cudaFreeAsync(d_tmp, ctx->stream));
+    CK(cudaFreeAsync(d_out, ctx->stream));
+    CK(cudaFreeAsync(d_cm, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_spectrogram_tile(thb_ctx *ctx, uint64_t id, uint32_t ch, const uint8_t *colormap_rgba, size_t colormap_bytes,
+                         uint64_t revision, uint32_t level_x, uint32_t level_y, uint32_t tile_x, uint32_t tile_y, uint8_t *out,
+                         size_t cap, size_t *written) {
+    thb_spec_tile_req r{};
+    r.id = id;
+    r.ch = ch;
+    r.level_x = level_x;
+    r.level_y = level_y;
+    r.tile_x = tile_x;
+    r.tile_y = tile_y;
+    r.out = out;
+    r.cap = cap;
+    const int rc = thb_spectrogram_tile_batch(ctx, colormap_rgba, colormap_bytes, revision, &r, 1);
+    if (written) *written = r.written;
+    return rc;
 }
 
 // ---- waveform tiles ---------------------------------------------------------------------------------

@@ -434,6 +434,110 @@ void hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uin
     *i1 = c > 0.0f ? static_cast<uint64_t>(c) : 0;
 }
 
+// ---- spectrogram tiles --------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t kSpecTile = 512, kSpecGutter = 4;  // SPECTROGRAM_TILE_SIZE / _GUTTER (render_tiles.rs:15-16)
+uint64_t sat_mul(uint64_t a, uint64_t b) { return (b && a > UINT64_MAX / b) ? UINT64_MAX : a * b; }
+uint64_t sat_sub(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
+double lanczos3(double x) {  // truncated sinc * sinc(x / 3)
+    if (!(x >= -3.0 && x < 3.0)) return 0.0;
+    auto sinc = [](double t) {
+        if (t == 0.0) return 1.0;
+        t *= M_PI;
+        return std::sin(t) / t;
+    };
+    return sinc(x) * sinc(x / 3.0);
+}
+}  // namespace
+
+TileGeometry spectrogram_tile_geometry(uint64_t H, uint64_t W, uint32_t level_x, uint32_t level_y, uint32_t tile_x,
+                                       uint32_t tile_y) {
+    TileGeometry g;
+    const uint64_t sx = level_x < 64 ? (uint64_t(1) << level_x) : UINT64_MAX;  // checked_shl(..).unwrap_or(MAX)
+    const uint64_t sy = level_y < 64 ? (uint64_t(1) << level_y) : UINT64_MAX;
+    g.lod_width = W / sx + (W % sx != 0);                                       // div_ceil
+    g.lod_height = H / sy + (H % sy != 0);
+    const uint64_t start_x = sat_mul(tile_x, kSpecTile), start_y = sat_mul(tile_y, kSpecTile);
+    const uint64_t core_w = std::min(sat_sub(g.lod_width, start_x), kSpecTile);
+    const uint64_t core_h = std::min(sat_sub(g.lod_height, start_y), kSpecTile);
+    g.origin_x = sat_sub(start_x, kSpecGutter);
+    g.origin_y = sat_sub(start_y, kSpecGutter);
+    if (core_w && core_h) {
+        g.width = sat_sub(std::min(g.lod_width, start_x + core_w + kSpecGutter), g.origin_x);
+        g.height = sat_sub(std::min(g.lod_height, start_y + core_h + kSpecGutter), g.origin_y);
+    }
+    return g;
+}
+
+// fast_image_resize 6.0.0, convolution resize of one axis for U16 pixels (third-party arithmetic, restated from the
+// crate's published algorithm -- see oracle/thesia_oracle.c for the statement of what is and is not pinned):
+// filter stretched by max(scale, 1); bounds without leading / trailing zero weights; weights normalised to sum 1 in
+// f64, then quantised to i32 with the largest precision that keeps the largest weight inside i32.
+ResizeAxis resize_axis(uint32_t in_size, double in0, double in1, uint32_t out_size) {
+    ResizeAxis a;
+    a.n = out_size;
+    const double scale = (in1 - in0) / static_cast<double>(out_size);
+    const double filter_scale = scale > 1.0 ? scale : 1.0;
+    const double radius = 3.0 * filter_scale;
+    a.window = static_cast<uint32_t>(std::ceil(radius)) * 2u + 1u;
+    const double recip = 1.0 / filter_scale;
+    std::vector<double> c(static_cast<size_t>(a.window) * out_size, 0.0);
+    a.start.assign(out_size, 0);
+    a.size.assign(out_size, 0);
+    double max_w = 0.0;
+    for (uint32_t o = 0; o < out_size; o++) {
+        const double in_center = in0 + (static_cast<double>(o) + 0.5) * scale;
+        const double lo = std::max(std::floor(in_center - radius), 0.0);
+        const double hi = std::min(std::ceil(in_center + radius), static_cast<double>(in_size));
+        const uint32_t x_min = static_cast<uint32_t>(lo), x_max = static_cast<uint32_t>(hi);
+        const double center = in_center - 0.5;
+        double *row = c.data() + static_cast<size_t>(o) * a.window;
+        uint32_t n = 0, b0 = x_min, b1 = x_max;
+        double ww = 0.0;
+        for (uint32_t x = x_min; x < x_max; x++) {
+            const double w = lanczos3((static_cast<double>(x) - center) * recip);
+            if (x == b0 && w == 0.0) {
+                b0++;
+            } else {
+                row[n++] = w;
+                ww += w;
+            }
+        }
+        for (uint32_t i = n; i-- > 0;) {
+            if (b1 <= b0 || row[i] != 0.0) break;
+            b1--;
+        }
+        if (ww != 0.0)
+            for (uint32_t i = 0; i < n; i++) row[i] /= ww;
+        a.start[o] = b0;
+        a.size[o] = b1 - b0;
+        for (uint32_t i = 0; i < a.window; i++) max_w = std::max(max_w, row[i]);
+    }
+    a.precision = 0;
+    for (uint32_t p = 0; p < 31; p++) {
+        a.precision = p;
+        if (std::round(max_w * static_cast<double>(int64_t(1) << (p + 1))) >= 2147483648.0) break;
+    }
+    const double q = static_cast<double>(int64_t(1) << a.precision);
+    a.w_t.assign(static_cast<size_t>(a.window) * out_size, 0);
+    std::vector<int32_t> k(a.window);
+    for (uint32_t o = 0; o < out_size; o++) {
+        for (uint32_t i = 0; i < a.window; i++) k[i] = static_cast<int32_t>(std::round(c[static_cast<size_t>(o) * a.window + i] * q));
+        // taps whose weight quantised to zero add nothing to the i64 sum: drop them at both ends of the bound (the
+        // result is unchanged bit for bit; at scale 1 on a whole-pixel origin this leaves the single unit tap)
+        uint32_t lead = 0, n = a.size[o];
+        while (n && k[lead + n - 1] == 0) n--;
+        while (n && k[lead] == 0) {
+            lead++;
+            n--;
+        }
+        a.start[o] += lead;
+        a.size[o] = n;
+        for (uint32_t i = 0; i < n; i++) a.w_t[static_cast<size_t>(i) * out_size + o] = k[lead + i];
+    }
+    return a;
+}
+
 std::vector<float> twiddle_table(uint64_t n_fft) {
     std::vector<float> t(2 * n_fft);
     for (uint64_t i = 0; i < n_fft; i++) {

@@ -82,6 +82,23 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel);
 void hz_range_to_idx(uint32_t freq_scale, float hz0, float hz1, uint32_t sr, uint64_t n_bins,
                      uint64_t *i0, uint64_t *i1);
 
+// ---- spectrogram tiles (render_tiles.rs:281-393) ----
+// geometry of a tile (render_tiles.rs:290-312)
+struct TileGeometry {
+    uint64_t lod_width = 0, lod_height = 0, origin_x = 0, origin_y = 0, width = 0, height = 0;
+};
+TileGeometry spectrogram_tile_geometry(uint64_t H, uint64_t W, uint32_t level_x, uint32_t level_y, uint32_t tile_x,
+                                       uint32_t tile_y);
+// One axis of the Lanczos3 convolution resize the reference delegates to fast_image_resize 6.0.0 (U16 pixels): the
+// taps of output pixel o are input pixels start[o] .. start[o] + size[o], weights w_t[i * n + o] (tap-major, so that
+// neighbouring output pixels read neighbouring words) in i32 fixed point with `precision` fractional bits.
+struct ResizeAxis {
+    uint32_t n = 0, window = 0, precision = 0;
+    std::vector<uint32_t> start, size;
+    std::vector<int32_t> w_t;
+};
+ResizeAxis resize_axis(uint32_t in_size, double in0, double in1, uint32_t out_size);
+
 // exp(-2*pi*i*t/n_fft), t = 0..n_fft-1, computed in double and rounded once
 std::vector<float> twiddle_table(uint64_t n_fft);
 

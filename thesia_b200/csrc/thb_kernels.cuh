@@ -97,6 +97,19 @@ struct GainOut {
     unsigned long long reduction_cnt;  // samples with |gain * x| > 1 (Clip mode)
 };
 
+// One spectrogram tile (thb_tile.cu): the two axes of the resize (ResizeAxis, thb_host.hpp) and its buffers
+struct TileDesc {
+    const uint16_t *img;      // (H, pitch) u16, retained image
+    unsigned long long pitch;
+    const unsigned *x_start, *x_size, *y_start, *y_size;
+    const int *wx, *wy;       // tap-major: wx[i * width + x], wy[i * height + y]
+    unsigned width, height;   // of the tile
+    unsigned y_first, tmp_h;  // rows [y_first, y_first + tmp_h) of the image feed the vertical pass
+    unsigned px, py;          // fixed-point precisions
+    uint16_t *tmp;            // (tmp_h, width)
+    uint8_t *out;             // (height, width) RGBA, rows reversed
+};
+
 // sample `idx` of a channel's slice as f32: 16-bit PCM converts as s / 32768 (exact)
 __device__ __forceinline__ float pcm_sample(const TrackDesc &d, long long idx) {
     if (d.pcm_i16) return static_cast<float>(__ldg(reinterpret_cast<const short *>(d.pcm) + idx)) * 3.0517578125e-05f;
@@ -159,6 +172,10 @@ long long gain_chunks(long long max_len);
 cudaError_t launch_gain_peak(const GainDesc *d_descs, int n, long long max_len, unsigned *d_group_peak, cudaStream_t st);
 cudaError_t launch_gain_apply(const GainDesc *d_descs, int n, long long max_len, int mode, const unsigned *d_group_peak,
                               double *d_part_ss, GainOut *d_outs, cudaStream_t st);
+
+// spectrogram tiles (thb_tile.cu): grid y is sized for the largest tile of the batch, the others return early
+cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned max_w, unsigned max_h, unsigned max_tmp_h,
+                                     const uchar4 *d_colormap, unsigned colors, cudaStream_t st);
 
 cudaError_t launch_synth_pcm(float *d_out, unsigned long long len, uint32_t sr, uint32_t track,
                              uint32_t channel, uint32_t flags, cudaStream_t st);

@@ -1,0 +1,106 @@
+// thb_tile.cu -- spectrogram tile encode: encode_spectrogram_tile / resize_spectrogram_tile
+// (render_tiles.rs:281-393).  A tile is a <= 520 x 520 window of one level of detail of a retained u16 image,
+// resampled with the separable Lanczos3 convolution the reference delegates to fast_image_resize (U16 pixels: i32
+// fixed-point weights, i64 accumulation, half-LSB seed, arithmetic shift, clamp), mapped through the RGBA colormap
+// and written with its rows reversed (high frequencies first).
+//
+//   pass H  tmp[y][x] = clip((2^(p-1) + sum_i img[y_first + y][start_x[x] + i] * wx[i][x]) >> p)   y over the rows pass V needs
+//   pass V  px = clip((2^(q-1) + sum_i tmp[start_y[y] - y_first + i][x] * wy[i][y]) >> q) -> colormap -> out[height-1-y][x]
+//
+// Weights are tap-major (w[i][pixel]): in pass H neighbouring threads read neighbouring words, in pass V the weight
+// is uniform over the CTA.  Integer arithmetic only: a tile is bit-identical to the CPU restatement.
+#include "thb_device.cuh"
+#include "thb_kernels.cuh"
+
+namespace thb {
+namespace {
+
+constexpr int kTileThreads = 128;
+
+__device__ __forceinline__ unsigned clip_u16(long long ss, unsigned precision) {
+    const long long v = ss >> precision;
+    return static_cast<unsigned>(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+}
+
+// kTileRows rows per CTA: the weights of a column (pass H) are loaded once for all of them, and the descriptor,
+// bounds and grid overhead are amortised
+constexpr int kTileRows = 8;
+
+__global__ void __launch_bounds__(kTileThreads) tile_horiz_kernel(const TileDesc *__restrict__ descs) {
+    const TileDesc &d = descs[blockIdx.z];
+    const unsigned width = d.width, tmp_h = d.tmp_h;
+    const unsigned x = blockIdx.x * kTileThreads + threadIdx.x;
+    const unsigned y0 = blockIdx.y * kTileRows;
+    if (y0 >= tmp_h || x >= width) return;
+    const unsigned rows = min(static_cast<unsigned>(kTileRows), tmp_h - y0);
+    const size_t pitch = d.pitch;
+    const uint16_t *src = d.img + static_cast<size_t>(d.y_first + y0) * pitch + d.x_start[x];
+    const unsigned n = d.x_size[x];
+    const int *w = d.wx + x;
+    const unsigned prec = d.px;
+    long long ss[kTileRows];
+#pragma unroll
+    for (int r = 0; r < kTileRows; r++) ss[r] = 1ll << (prec - 1);
+    if (rows == kTileRows) {
+        for (unsigned i = 0; i < n; i++) {
+            const long long k = __ldg(w + static_cast<size_t>(i) * width);
+#pragma unroll
+            for (int r = 0; r < kTileRows; r++) ss[r] += static_cast<long long>(__ldg(src + r * pitch + i)) * k;
+        }
+    } else {
+        for (unsigned i = 0; i < n; i++) {
+            const long long k = __ldg(w + static_cast<size_t>(i) * width);
+            for (unsigned r = 0; r < rows; r++) ss[r] += static_cast<long long>(__ldg(src + r * pitch + i)) * k;
+        }
+    }
+    uint16_t *dst = d.tmp + static_cast<size_t>(y0) * width + x;
+#pragma unroll
+    for (int r = 0; r < kTileRows; r++)
+        if (static_cast<unsigned>(r) < rows) dst[static_cast<size_t>(r) * width] = static_cast<uint16_t>(clip_u16(ss[r], prec));
+}
+
+__global__ void __launch_bounds__(kTileThreads) tile_vert_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
+                                                                 unsigned colors) {
+    const TileDesc &d = descs[blockIdx.z];
+    const unsigned width = d.width, height = d.height;
+    const unsigned x = blockIdx.x * kTileThreads + threadIdx.x;
+    const unsigned y0 = blockIdx.y * kTileRows;
+    if (y0 >= height || x >= width) return;
+    const unsigned rows = min(static_cast<unsigned>(kTileRows), height - y0);
+    const unsigned prec = d.py, y_first = d.y_first;
+    const uint16_t *tmp = d.tmp + x;
+    uchar4 *out = reinterpret_cast<uchar4 *>(d.out);
+    for (unsigned r = 0; r < rows; r++) {
+        const unsigned y = y0 + r;
+        const unsigned n = d.y_size[y];
+        const uint16_t *col = tmp + static_cast<size_t>(d.y_start[y] - y_first) * width;
+        const int *w = d.wy + y;
+        long long ss = 1ll << (prec - 1);
+        for (unsigned i = 0; i < n; i++)
+            ss += static_cast<long long>(col[static_cast<size_t>(i) * width]) * __ldg(w + static_cast<size_t>(i) * height);
+        const unsigned long long v = clip_u16(ss, prec);
+        // render_tiles.rs:339-346: (value * (color_count - 1) + u16::MAX / 2) / u16::MAX
+        const unsigned ci = colors <= 1 ? 0u : static_cast<unsigned>((v * (colors - 1) + 32767ull) / 65535ull);
+        out[static_cast<size_t>(height - 1 - y) * width + x] = __ldg(colormap + ci);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned max_w, unsigned max_h, unsigned max_tmp_h,
+                                     const uchar4 *d_colormap, unsigned colors, cudaStream_t st) {
+    if (n <= 0 || !max_w || !max_h) return cudaSuccess;
+    const unsigned gx = (max_w + kTileThreads - 1) / kTileThreads;
+    for (int c0 = 0; c0 < n; c0 += 65535) {
+        const unsigned nc = static_cast<unsigned>(n - c0 < 65535 ? n - c0 : 65535);
+        tile_horiz_kernel<<<dim3(gx, (max_tmp_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        tile_vert_kernel<<<dim3(gx, (max_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0, d_colormap, colors);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace thb

@@ -370,6 +370,37 @@ inline AudioStats calc_stats(Context &ctx, const Audio &audio) {
     return AudioStats{st.rms_dB, st.max_peak, st.max_peak_dB};
 }
 
+// ---- spectrogram tiles --------------------------------------------------------------------
+// The spectrogram half of RenderTileCache (render_tiles.rs:51-188): colormap + revision, and spectrogram_tile() for
+// the image TrackManager retains for (id, ch) (get_spectrogram_tile, lib.rs:369-389).
+constexpr uint64_t SPECTROGRAM_TILE_SIZE = 512;
+class RenderTileCache {
+public:
+    explicit RenderTileCache(Context &ctx) : ctx_(ctx) {}
+    uint64_t spectrogram_revision = 1;
+    std::vector<uint8_t> colormap_rgba = {0, 0, 0, 255, 255, 255, 255, 255};
+    void set_colormap(std::vector<uint8_t> rgba) {  // render_tiles.rs:80-85: an invalid table is ignored, the revision still moves
+        if (rgba.size() >= 4 && rgba.size() % 4 == 0) colormap_rgba = std::move(rgba);
+        invalidate_spectrogram();
+    }
+    void invalidate_spectrogram() {
+        spectrogram_revision += 1;
+        if (spectrogram_revision == 0) spectrogram_revision = 1;  // wrapping_add(1).max(1)
+    }
+    std::vector<uint8_t> spectrogram_tile(uint64_t id, uint32_t ch, uint32_t level_x, uint32_t level_y, uint32_t tile_x, uint32_t tile_y) {
+        size_t need = 0;
+        check(thb_spectrogram_tile(ctx_.get(), id, ch, colormap_rgba.data(), colormap_rgba.size(), spectrogram_revision, level_x, level_y,
+                                   tile_x, tile_y, nullptr, 0, &need), ctx_.get());
+        std::vector<uint8_t> out(need);
+        check(thb_spectrogram_tile(ctx_.get(), id, ch, colormap_rgba.data(), colormap_rgba.size(), spectrogram_revision, level_x, level_y,
+                                   tile_x, tile_y, out.data(), out.size(), &need), ctx_.get());
+        return out;
+    }
+
+private:
+    Context &ctx_;
+};
+
 // ---- gain normalisation + guard clipping ----------------------------------------------------
 // GuardClippingMode (dynamics/guardclipping.rs:6-12), NormalizeTarget (dynamics/normalize.rs:6-15)
 enum class GuardClippingMode : uint32_t { Clip = THB_GUARD_CLIP, ReduceGlobalLevel = THB_GUARD_REDUCE_GLOBAL_LEVEL, Limiter = THB_GUARD_LIMITER };

@@ -115,6 +115,37 @@ def envelope_case(ctx, n_ch, seconds, sr, reps, out):
     torch.cuda.empty_cache()
 
 
+def tile_case(ctx, n_ch, seconds, sr, reps, out):
+    """f2: every tile of a level for n_ch mel-default spectrogram images (347 x 56 251 at 10 min), levels 0 / 2 / 4 in x."""
+    from thesia_b200.analysis import spectrogram_tile_geometry
+    n = int(sr * seconds)
+    pcm = synth(ctx, n_ch, n, sr)
+    setting = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 0)
+    ctx.spec_batch([dict(pcm=pcm[c, :n], id=c, ch=0, sr=sr) for c in range(n_ch)], setting, want_host=False)
+    ctx.update_spec_imgs(100.0, 258)
+    H, W = ctx.img_read(0, 0).shape
+    cm = bytes((i * 7 + j * 31) & 255 for i in range(258) for j in range(4))
+    for lx, ly in ((0, 0), (2, 0), (4, 1)):
+        g = spectrogram_tile_geometry(H, W, lx, ly, 0, 0)
+        tiles_x, tiles_y = -(-g[0] // 512), -(-g[1] // 512)
+        reqs = [(c, 0, lx, ly, tx, ty) for c in range(n_ch) for ty in range(tiles_y) for tx in range(tiles_x)]
+        bufs = ctx.spectrogram_tiles(cm, 1, reqs, want_bytes=False)
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        for _ in range(reps):
+            ctx.spectrogram_tiles(cm, 1, reqs, want_bytes=False)
+        ms = ctx.profile_get("spectrogram_tile")[0] / reps
+        ctx.profile_enable(False)
+        out_bytes = sum(b.size - 40 for b in bufs)
+        alg = n_ch * 2 * H * W + out_bytes
+        out({"config": "f2 spectrogram tiles", "level_x": lx, "level_y": ly, "images": n_ch, "image_shape": [H, W], "tiles": len(reqs),
+             "tile_kernels_ms": ms, "rgba_bytes": out_bytes, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
+             "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS, "Mpixels_per_s": out_bytes / 4 / (ms * 1e-3) / 1e6})
+    ctx.release_all()
+    del pcm
+    torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="C1,C2,C2D,C3D,C4L,C4M,C5")
@@ -149,6 +180,8 @@ def main():
         stft_case(ctx, "C4 linear 16384/1024 @96 kHz, 1 track", 1, a.c4_seconds, 96000, 16384 / 96.0, 16, Lin, 0, max(1, a.reps - 1), out)
     if "C5" in only:
         envelope_case(ctx, 128, 600, 48000, a.reps, out)
+    if "F2" in only:
+        tile_case(ctx, 16, 600, 48000, a.reps, out)
     ctx.close()
 
 
