@@ -135,6 +135,26 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def gpu_numa_cpus(torch, index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when the box does not say.  Pinned buffers
+    allocated and filled by a thread running there are local to the GPU's PCIe root: with several ranks on a
+    two-socket box this is what keeps the host <-> device copies off the inter-socket link."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in (Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
 # -------------------------------------------------------------------------------------------------
 def cpu_reference_run(n_ch: int, seconds: int, steps: int, warmup: int, threads: int, want_imgs: bool = True):
     """Times the oracle port (reference-like f32, dense mel product, threaded like mod.rs:152) on
@@ -296,7 +316,15 @@ def run_b200(args) -> None:
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
     e2e_i16 = None
+    host_affinity = "unbound"
     if not args.no_e2e:
+        # the host side of a rank lives next to its GPU: bind before the pinned buffers are allocated and touched
+        # (restored before the CPU baseline, which uses every core)
+        affinity_before = os.sched_getaffinity(0)
+        numa = gpu_numa_cpus(torch, local_rank)
+        if numa is not None:
+            os.sched_setaffinity(0, numa[1])
+            host_affinity = f"NUMA node {numa[0]} of the GPU ({len(numa[1])} CPUs)"
         img_bytes = n_ch_total * N_MEL * T * 2
         img_stride = N_MEL * T
         host_img_p = C.c_void_p()
@@ -371,6 +399,8 @@ def run_b200(args) -> None:
         _lib.lib().thb_host_free(host_pcm_p)
         _lib.lib().thb_host_free(host_i16_p)
         _lib.lib().thb_host_free(host_img_p)
+        os.sched_setaffinity(0, affinity_before)
+        e2e["host_affinity"] = host_affinity
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample ----
     cpu = None
