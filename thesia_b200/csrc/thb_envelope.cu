@@ -85,7 +85,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) envelope_kernel(const Env
             Acc a = acc_init();
             unsigned long long s = b0 + 4ull * lane;
             if (vec_ok) {
-                // b0 is a multiple of 128 samples -> 16-byte aligned float4 loads
+                // b0 is a multiple of 128 samples -> 16-byte aligned float4 loads; four of them in flight per lane
+                // (2 KB per warp and step) so that a 64-warp SM keeps enough bytes outstanding to cover HBM latency
+                for (; s + 3 * 128 + 3 < b1; s += 512) {
+                    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(pcm + s));
+                    const float4 v1 = __ldg(reinterpret_cast<const float4 *>(pcm + s + 128));
+                    const float4 v2 = __ldg(reinterpret_cast<const float4 *>(pcm + s + 256));
+                    const float4 v3 = __ldg(reinterpret_cast<const float4 *>(pcm + s + 384));
+                    acc_add(a, v0.x); acc_add(a, v0.y); acc_add(a, v0.z); acc_add(a, v0.w);
+                    acc_add(a, v1.x); acc_add(a, v1.y); acc_add(a, v1.z); acc_add(a, v1.w);
+                    acc_add(a, v2.x); acc_add(a, v2.y); acc_add(a, v2.z); acc_add(a, v2.w);
+                    acc_add(a, v3.x); acc_add(a, v3.y); acc_add(a, v3.z); acc_add(a, v3.w);
+                }
                 for (; s + 3 < b1; s += 128) {
                     const float4 v = __ldg(reinterpret_cast<const float4 *>(pcm + s));
                     acc_add(a, v.x); acc_add(a, v.y); acc_add(a, v.z); acc_add(a, v.w);
