@@ -23,6 +23,7 @@
 //   dB_from_amp (decibel.rs:198-202), find_min_max (mod.rs:169-178).
 #include "thb_packed.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace thb {
@@ -32,7 +33,7 @@ namespace {
 using namespace packed;
 
 constexpr int kNC = 8192;        // complex points
-constexpr int kThreads = 256;
+constexpr int kCols = 256;       // columns of step 1: z[256 n1 + col]
 constexpr int kRow17 = 17;       // padded row of 16 elements
 constexpr int kPairsPerItem = 8; // frame pairs a CTA takes at a time
 // element index of A[k1][x][y] (steps 1-3) and of Z[k] (natural order)
@@ -57,7 +58,13 @@ __device__ __forceinline__ float db_of(float s, float re, float im) {
     return amp_to_db(hypotf(re, im));
 }
 
-template <bool MEL>
+// kThreads = 256: one thread per column, 32-point DFT in registers (dft32p).
+// kThreads = 512: two threads per column and per (k1, n3) / (k1, k2) task.  Thread h = t >> 8 of a column computes the
+// outputs k1 = 2 q + h of the 32-point DFT as one radix-2 stage + a 16-point DFT (y_0[n] = x[n] + x[n+16],
+// y_1[n] = (x[n] - x[n+16]) W_32^n; X[2q + h] = DFT16(y_h)[q]), and steps 2 / 3 take one task per thread instead of
+// two: the same shared-memory layout and tables, 16 warps per SM instead of 8, <= 128 registers per thread.
+// WS: the padded window (64 KB) lives in shared memory instead of L2 / L1
+template <bool MEL, int kThreads, bool WS>
 __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
                                                                long long n_items, long long items_per_track) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,6 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
     float2 *tw_a = reinterpret_cast<float2 *>(buf + kBufElems);   // [31][16] W_512^(n2 k1)
     float2 *tw_b = tw_a + 31 * 16;                                          // [32][16] W_8192^(n3 k1)
     float2 *tw_c = tw_b + 32 * 16;                                          // [16][16] W_256^(n3 k2)
+    float *wsm = reinterpret_cast<float *>(tw_c + 16 * 16);                 // [16384] padded window (WS only)
     __shared__ float red_max[kThreads / 32], red_nmin[kThreads / 32];
     // After the real split the FFT buffer is reused in place: |X[k]| of both frames replaces the first 8 bytes of
     // element idxn(k) (each element is read by exactly one thread before it is overwritten), and the mel partial
@@ -73,11 +81,17 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
     auto part_at = [&](int q) -> float2 & { return buf[q].im; };
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int col = t & (kCols - 1), hsel = t >> 8;  // kThreads == 512: hsel picks the parity of k1 / the upper k1 half
     for (int i = t; i < 31 * 16 + 32 * 16 + 16 * 16; i += kThreads) tw_a[i] = __ldg(&p.big_tw[i]);
+    if constexpr (WS) {
+        for (int i = t; i < 2 * kNC / 4; i += kThreads)
+            reinterpret_cast<float4 *>(wsm)[i] = __ldg(reinterpret_cast<const float4 *>(p.big_wpad) + i);
+    }
     // (the mel walk reads up to 31 bins past a piece with weight 0: idxn(8192 + 31) = 8479 is inside the buffer, and
     // what it finds there is left-over FFT data, finite whenever the frame is)
     __syncthreads();
     const int half = p.win / 2;
+    const float2 w_own = __ldg(&p.twiddle[t]);  // W_16384^t (real split, 512-thread variant)
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const long long track = item / items_per_track, chunk = item - track * items_per_track;
@@ -90,8 +104,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
         for (long long fa = f_begin; fa < f_end; fa += 2) {
             const bool has_b = fa + 1 < f_end;
             const long long fb = has_b ? fa + 1 : fa;  // an odd last frame is computed twice, stored once
-            cx v[32];
             // ---- step 1: load + window, 32-point DFT over n1 ----
+            if constexpr (kThreads == 256) {
+            cx v[32];
             {
                 const long long tap0[2] = {(d.frame_begin + fa) * p.hop - half, (d.frame_begin + fb) * p.hop - half};
                 const float *wsrc = p.big_wpad + 2 * t;
@@ -155,11 +170,83 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                     buf[idx3(k1, n2, n3)] = to_elem(o);
                 }
             }
+            } else {
+                // two threads per column: this one computes the outputs k1 = 2 q + hsel
+                const long long tap0[2] = {(d.frame_begin + fa) * p.hop - half, (d.frame_begin + fb) * p.hop - half};
+                const float *wsrc = (WS ? wsm : p.big_wpad) + 2 * col;
+                bool interior[2];
+#pragma unroll
+                for (int f = 0; f < 2; f++) {
+                    const long long first = tap0[f] - p.pad_left;
+                    interior[f] = !d.pcm_i16 && tap0[f] >= 0 && tap0[f] + p.win <= d.full_len && first >= d.pcm_offset &&
+                                  first + 2 * kNC <= d.pcm_offset + d.slice_len &&
+                                  ((reinterpret_cast<uintptr_t>(d.pcm + (first - d.pcm_offset))) & 7) == 0;
+                }
+                cx y[16];
+                auto fold = [&](int n, float2 xa0, float2 xb0, float2 xa1, float2 xb1) {
+                    // windowed samples of rows n and n + 16 of both frames, then the radix-2 stage
+                    const float2 w0 = WS ? *reinterpret_cast<const float2 *>(wsrc + 512 * n) : __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n));
+                    const float2 w1 = WS ? *reinterpret_cast<const float2 *>(wsrc + 512 * (n + 16))
+                                         : __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * (n + 16)));
+                    cx lo, hi;
+                    lo.re = make_float2(xa0.x * w0.x, xb0.x * w0.x);
+                    lo.im = make_float2(xa0.y * w0.y, xb0.y * w0.y);
+                    hi.re = make_float2(xa1.x * w1.x, xb1.x * w1.x);
+                    hi.im = make_float2(xa1.y * w1.y, xb1.y * w1.y);
+                    y[n] = hsel ? csub2(lo, hi) : cadd2(lo, hi);
+                };
+                if (interior[0] && interior[1] && has_b && p.hop == 1024) {
+                    // frame B is frame A two rows later: rows 0 .. 33 serve both frames (34 distinct loads)
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * col;
+                    float2 r[34];
+#pragma unroll
+                    for (int n1 = 0; n1 < 34; n1++) r[n1] = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
+#pragma unroll
+                    for (int n = 0; n < 16; n++) fold(n, r[n], r[n + 2], r[n + 16], r[n + 18]);
+                } else if (interior[0] && interior[1]) {
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * col;
+                    const float *src_b = d.pcm + (tap0[1] - p.pad_left - d.pcm_offset) + 2 * col;
+#pragma unroll
+                    for (int n = 0; n < 16; n++)
+                        fold(n, __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n)),
+                             __ldg(reinterpret_cast<const float2 *>(src_b + 512 * n)),
+                             __ldg(reinterpret_cast<const float2 *>(src_a + 512 * (n + 16))),
+                             __ldg(reinterpret_cast<const float2 *>(src_b + 512 * (n + 16))));
+                } else {
+                    auto tap = [&](int f, int pos) -> float {
+                        const int a = pos - p.pad_left;
+                        if (a < 0 || a >= p.win) return 0.0f;
+                        return pcm_sample(d, reflect_index(tap0[f] + a, d.full_len) - d.pcm_offset);
+                    };
+#pragma unroll
+                    for (int n = 0; n < 16; n++) {
+                        const int p0 = 512 * n + 2 * col, p1 = 512 * (n + 16) + 2 * col;
+                        fold(n, make_float2(tap(0, p0), tap(0, p0 + 1)), make_float2(tap(1, p0), tap(1, p0 + 1)),
+                             make_float2(tap(0, p1), tap(0, p1 + 1)), make_float2(tap(1, p1), tap(1, p1 + 1)));
+                    }
+                }
+                if (hsel) {
+#pragma unroll
+                    for (int n = 1; n < 16; n++) y[n] = cmul_s(y[n], kC32[n], -kS32[n]);   // * W_32^n
+                }
+                dft16p(y);
+                const int n2 = col >> 4, n3 = col & 15;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int k1 = 2 * q + hsel;
+                    cx o = y[perm16(q)];
+                    if (k1) {
+                        const float2 w = tw_a[(k1 - 1) * 16 + n2];
+                        o = cmul_s(o, w.x, w.y);
+                    }
+                    buf[idx3(k1, n2, n3)] = to_elem(o);
+                }
+            }
             __syncthreads();
             // ---- step 2: 16-point DFT over n2, twiddle W_8192^(n3 (k1 + 32 k2)) ----
 #pragma unroll 1
-            for (int pr = 0; pr < 2; pr++) {
-                const int k1 = (t >> 4) + 16 * pr, n3 = t & 15;
+            for (int pr = (kThreads == 512 ? hsel : 0); pr < (kThreads == 512 ? hsel + 1 : 2); pr++) {
+                const int k1 = (col >> 4) + 16 * pr, n3 = col & 15;
                 cx u[16];
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) u[n2] = to_cx(buf[idx3(k1, n2, n3)]);
@@ -176,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
             }
             __syncthreads();
             // ---- step 3: 16-point DFT over n3 -> Z[k1 + 32 k2 + 512 k3], then natural order ----
-            {
+            if constexpr (kThreads == 256) {
                 cx u0[16], u1[16];
                 const int k2 = t & 15, k1a = t >> 4, k1b = k1a + 16;
 #pragma unroll
@@ -192,18 +279,35 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                     buf[idxn(k1a + 32 * k2 + 512 * k3)] = to_elem(u0[perm16(k3)]);
                     buf[idxn(k1b + 32 * k2 + 512 * k3)] = to_elem(u1[perm16(k3)]);
                 }
+            } else {
+                cx u[16];
+                const int k2 = col & 15, k1 = (col >> 4) + 16 * hsel;
+#pragma unroll
+                for (int n3 = 0; n3 < 16; n3++) u[n3] = to_cx(buf[idx3(k1, k2, n3)]);
+                dft16p(u);
+                __syncthreads();
+#pragma unroll
+                for (int k3 = 0; k3 < 16; k3++) buf[idxn(k1 + 32 * k2 + 512 * k3)] = to_elem(u[perm16(k3)]);
             }
             __syncthreads();
             // ---- real split: pairs (k, 8192 - k), k = t + 256 j; |X|^2 -> dB, or |X| -> mag[] ----
             float *orow_a = d.out + fa * p.n_bins, *orow_b = d.out + fb * p.n_bins;
 #pragma unroll 4
-            for (int j = 0; j <= 16; j++) {
-                const int k = t + 256 * j;
-                if (j == 16 && t != 0) break;  // k = 4096 pairs with itself: one thread
+            for (int j = 0; j <= kNC / 2 / kThreads; j++) {
+                const int k = t + kThreads * j;
+                if (j == kNC / 2 / kThreads && t != 0) break;  // k = 4096 pairs with itself: one thread
                 const int kp = (kNC - k) & (kNC - 1);
                 const cx zk = to_cx(buf[idxn(k)]), zn = to_cx(buf[idxn(kp)]);
                 const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
-                const float2 w = __ldg(&p.twiddle[k]);
+                float2 w;
+                if constexpr (kThreads == 512) {
+                    // W_16384^(t + 512 j) = W_16384^t * W_32^j: the thread's own factor sits in a register pair, the
+                    // other is a 9-entry constant table -- no L2 round trip per bin pair
+                    const float c = kC32[j], sn = -kS32[j];
+                    w = make_float2(fmaf(-w_own.y, sn, w_own.x * c), fmaf(w_own.x, sn, w_own.y * c));
+                } else {
+                    w = __ldg(&p.twiddle[k]);
+                }
                 const f2 wr = pfma(di, bc(-w.y), pmul(dr, bc(w.x))), wi = pfma(dr, bc(w.y), pmul(di, bc(w.x)));
                 const f2 ar = padd(er, wi), ai = psub(ei, wr), br = psub(er, wi), bi = padd(ei, wr);
                 const f2 sa = pfma(ar, ar, pmul(ai, ai)), sb = pfma(br, br, pmul(bi, bi));
@@ -302,7 +406,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
     }
 }
 
-size_t big_smem_bytes(const PlanDev &) { return sizeof(Elem) * (kBufElems) + sizeof(float2) * (31 * 16 + 32 * 16 + 16 * 16); }
+size_t big_smem_bytes(const PlanDev &, bool ws = false) {
+    return sizeof(Elem) * (kBufElems) + sizeof(float2) * (31 * 16 + 32 * 16 + 16 * 16) + (ws ? sizeof(float) * 2 * kNC : 0);
+}
 
 }  // namespace
 
@@ -312,24 +418,37 @@ bool stft_big_supported(const PlanDev &p) {
     return big_smem_bytes(p) <= 226 * 1024;
 }
 
+namespace {
+template <bool MEL, int NT, bool WS>
+cudaError_t launch_big_nt(const PlanDev &plan, const TrackDesc *d_tracks, long long n_items, long long items_per_track, int grid,
+                          cudaStream_t st) {
+    const size_t smem = big_smem_bytes(plan, WS);
+    cudaError_t e = cudaFuncSetAttribute(stft16384_kernel<MEL, NT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    stft16384_kernel<MEL, NT, WS><<<grid, NT, smem, st>>>(plan, d_tracks, n_items, items_per_track);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
                             int sm_count, cudaStream_t st) {
     if (n_tracks <= 0 || max_frames <= 0) return cudaSuccess;
-    const size_t smem = big_smem_bytes(plan);
     const long long items_per_track = (max_frames + 2 * kPairsPerItem - 1) / (2 * kPairsPerItem);
     const long long n_items = items_per_track * n_tracks;
     const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
-    cudaError_t e;
+    // A/B knobs: THB_BIG_THREADS = 256 | 512, THB_BIG_WSMEM = 0 | 1 (512 only)
+    const char *e = getenv("THB_BIG_THREADS");
+    const int nt = (e && atoi(e) == 256) ? 256 : 512;
+    const char *w = getenv("THB_BIG_WSMEM");
+    const bool ws = nt == 512 && !(w && atoi(w) == 0);
     if (plan.n_mel) {
-        e = cudaFuncSetAttribute(stft16384_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        stft16384_kernel<true><<<grid, kThreads, smem, st>>>(plan, d_tracks, n_items, items_per_track);
-    } else {
-        e = cudaFuncSetAttribute(stft16384_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        stft16384_kernel<false><<<grid, kThreads, smem, st>>>(plan, d_tracks, n_items, items_per_track);
+        if (nt == 256) return launch_big_nt<true, 256, false>(plan, d_tracks, n_items, items_per_track, grid, st);
+        if (ws) return launch_big_nt<true, 512, true>(plan, d_tracks, n_items, items_per_track, grid, st);
+        return launch_big_nt<true, 512, false>(plan, d_tracks, n_items, items_per_track, grid, st);
     }
-    return cudaGetLastError();
+    if (nt == 256) return launch_big_nt<false, 256, false>(plan, d_tracks, n_items, items_per_track, grid, st);
+    if (ws) return launch_big_nt<false, 512, true>(plan, d_tracks, n_items, items_per_track, grid, st);
+    return launch_big_nt<false, 512, false>(plan, d_tracks, n_items, items_per_track, grid, st);
 }
 
 }  // namespace thb
