@@ -353,6 +353,9 @@ CASES = [
     ("default-40ms-96k", 96000, thb.SpecSetting(), 200000, 0),               # n_fft 4096
     ("C4-linear-16384-1024", 96000, thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Linear), 300000, 0),
     ("C4-meldefault-16384", 96000, thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Mel), 200000, 0),
+    ("default-40ms-192k", 192000, thb.SpecSetting(), 400000, ZERO_GAP),      # win 7680 in n_fft 8192 (large-FFT kernel, R1 = 16)
+    ("linear-8192-1024", 96000, thb.SpecSetting(8192 / 96.0, 8, 1, thb.FreqScale.Linear), 150000, 0),
+    ("mel128-4096-512", 48000, thb.SpecSetting(4096 / 48.0, 8, 1, thb.FreqScale.Mel, 128), 120000, 0),
     ("foverlap2", 48000, thb.SpecSetting(40.0, 4, 2, thb.FreqScale.Linear), 60000, 0),   # n_fft 4096, win 1920
     ("nfft32768", 96000, thb.SpecSetting(300.0, 2, 1, thb.FreqScale.Mel, 64), 200000, 0),
     ("tiny-1ms-8k", 8000, thb.SpecSetting(1.0, 1, 1, thb.FreqScale.Linear), 4000, 0),    # win 8, n_fft 8
@@ -443,22 +446,23 @@ def test_frame_range_shards_equal_whole(ctx):
     assert e.value.code == _lib.THB_ERR_INVALID
 
 
+@pytest.mark.parametrize("n_fft_want", [16384, 8192, 4096])
 @pytest.mark.parametrize("scale,n_mel", [(thb.FreqScale.Linear, 0), (thb.FreqScale.Mel, 0), (thb.FreqScale.Mel, 128)])
-def test_large_fft_kernel_shards_edges_and_i16(ctx, orc, scale, n_mel):
-    """n_fft 16384 (config C4) runs on the two-frame large-FFT kernel, which handles every frame itself: file edges,
+def test_large_fft_kernel_shards_edges_and_i16(ctx, orc, scale, n_mel, n_fft_want):
+    """n_fft 16384 (config C4), 8192 and 4096 run on the two-frame large-FFT kernel, which handles every frame itself: file edges,
     odd frame counts, frame-range shards (bit-equal to the whole file) and 16-bit PCM (bit-equal to f32)."""
     from thesia_b200.sharding import split_frames
     sr = 96000
-    s = thb.SpecSetting(16384 / 96.0, 16, 1, scale, n_mel)
+    s = thb.SpecSetting(n_fft_want / 96.0, 16, 1, scale, n_mel)
     hop, win, n_fft = s.calc_framing_params(sr)
-    assert (hop, win, n_fft) == (1024, 16384, 16384)
-    x = synth_pcm(100003, sr, 5, 0, ZERO_GAP)
+    assert (hop, win, n_fft) == (n_fft_want // 16, n_fft_want, n_fft_want)
+    x = synth_pcm(100003 if n_fft_want == 16384 else 60000 + 3 * hop // 4, sr, 5, 0, 0 if n_fft_want == 4096 else ZERO_GAP)
     whole = ctx.calc_spec(x, sr, s, id=30)
-    assert whole.shape[0] == orc.n_frames(x.size, win, hop) and whole.shape[0] % 2 == 0  # 98 frames
+    assert whole.shape[0] == orc.n_frames(x.size, win, hop) and whole.shape[0] % 2 == 0  # 98 frames at n_fft 16384
     check_spec(orc, whole, x, sr, s, "big-whole")
-    odd = ctx.calc_spec(x[:100003 - 1024], sr, s, id=31)  # 97 frames: the last one is paired with itself
+    odd = ctx.calc_spec(x[:x.size - hop], sr, s, id=31)  # one frame less: the last one is paired with itself
     assert odd.shape[0] == whole.shape[0] - 1
-    check_spec(orc, odd, x[:100003 - 1024], sr, s, "big-odd")
+    check_spec(orc, odd, x[:x.size - hop], sr, s, "big-odd")
     for parts in (2, 3, 5):
         units = split_frames(32, 0, sr, x.size, win, hop, parts)
         pieces = []

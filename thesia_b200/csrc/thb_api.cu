@@ -357,24 +357,25 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     std::vector<float> bwpad, btw;
     std::vector<uint32_t> bpieces, bpptr;
     std::vector<float> bgw;
-    if (d.n_fft == 16384) {
-        // tables of the two-frame large-FFT kernel (thb_stft_big.cu)
-        bwpad.assign(16384, 0.0f);
+    if (d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384) {
+        // tables of the two-frame large-FFT kernel (thb_stft_big.cu): the frame is 256 R1 complex points = R1 x 16 x 16
+        const int r1 = d.n_fft / 512, ncx = d.n_fft / 2;
+        bwpad.assign(d.n_fft, 0.0f);
         for (int a = 0; a < d.win; a++) bwpad[a + d.pad_left] = 0.5f * win[a];
-        // [31][16] W_512^(n2 k1), k1 = 1..31; [32][16] W_8192^(n3 k1); [16][16] W_256^(n3 k2)
-        btw.resize(2 * (31 * 16 + 32 * 16 + 16 * 16));
+        // [R1 - 1][16] W_(16 R1)^(n2 k1), k1 = 1..R1-1; [R1][16] W_NC^(n3 k1); [16][16] W_256^(n3 k2)
+        btw.resize(2 * ((r1 - 1) * 16 + r1 * 16 + 16 * 16));
         const double tau = 6.283185307179586476925286766559;
         auto put_tw = [&](size_t at, long long num, long long den) {
             const double a = -tau * static_cast<double>(num % den) / static_cast<double>(den);
             btw[2 * at] = static_cast<float>(std::cos(a));
             btw[2 * at + 1] = static_cast<float>(std::sin(a));
         };
-        for (int k1 = 1; k1 < 32; k1++)
-            for (int n2 = 0; n2 < 16; n2++) put_tw((k1 - 1) * 16 + n2, n2 * k1, 512);
-        for (int k1 = 0; k1 < 32; k1++)
-            for (int n3 = 0; n3 < 16; n3++) put_tw(31 * 16 + k1 * 16 + n3, n3 * k1, 8192);
+        for (int k1 = 1; k1 < r1; k1++)
+            for (int n2 = 0; n2 < 16; n2++) put_tw((k1 - 1) * 16 + n2, n2 * k1, 16 * r1);
+        for (int k1 = 0; k1 < r1; k1++)
+            for (int n3 = 0; n3 < 16; n3++) put_tw((r1 - 1) * 16 + k1 * 16 + n3, n3 * k1, ncx);
         for (int k2 = 0; k2 < 16; k2++)
-            for (int n3 = 0; n3 < 16; n3++) put_tw(31 * 16 + 32 * 16 + k2 * 16 + n3, n3 * k2, 256);
+            for (int n3 = 0; n3 < 16; n3++) put_tw((r1 - 1) * 16 + r1 * 16 + k2 * 16 + n3, n3 * k2, 256);
         if ((rc = upload(ctx, pl.get(), bwpad, &d.big_wpad))) return rc;
         const float *btwp = nullptr;
         if ((rc = upload(ctx, pl.get(), btw, &btwp))) return rc;

@@ -32,15 +32,26 @@ namespace {
 
 using namespace packed;
 
-constexpr int kNC = 8192;        // complex points
 constexpr int kCols = 256;       // columns of step 1: z[256 n1 + col]
 constexpr int kRow17 = 17;       // padded row of 16 elements
 constexpr int kPairsPerItem = 8; // frame pairs a CTA takes at a time
 // element index of A[k1][x][y] (steps 1-3) and of Z[k] (natural order)
 __device__ __forceinline__ int idx3(int k1, int x, int y) { return k1 * (16 * kRow17) + x * kRow17 + y; }
 __device__ __forceinline__ int idxn(int k) { return k + (k >> 5); }
-constexpr int kBufElems = 32 * 16 * kRow17;  // 8704 elements of 16 bytes = 136 KB
-static_assert(kBufElems >= kNC + kNC / 32, "the natural-order layout (8448 elements) fits the same buffer");
+// R1 = n_fft / 512 = 8, 16 or 32: the frame is 256 R1 complex points = R1 x 16 x 16
+constexpr int buf_elems(int r1) { return r1 * 16 * kRow17; }  // R1 = 32: 8704 elements of 16 bytes = 136 KB
+static_assert(buf_elems(32) >= 8192 + 8192 / 32 + 32 && buf_elems(8) >= 2048 + 2048 / 32 + 32,
+              "the natural-order layout (+ the 31 bins a mel piece may read past its end) fits the same buffer");
+
+// in-register R-point DFT of both frames; output X[k] is left in v[perm_r<R>(k)]
+template <int R>
+__device__ __forceinline__ void dft_r(cx (&v)[R]) {
+    if constexpr (R == 32) dft32p(v);
+    else if constexpr (R == 16) dft16p(v);
+    else dft8p(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+}
+template <int R>
+__device__ __forceinline__ constexpr int perm_r(int k) { return R == 32 ? perm32(k) : (R == 16 ? perm16(k) : k); }
 
 struct alignas(16) Elem {
     float2 re, im;
@@ -64,15 +75,21 @@ __device__ __forceinline__ float db_of(float s, float re, float im) {
 // y_1[n] = (x[n] - x[n+16]) W_32^n; X[2q + h] = DFT16(y_h)[q]), and steps 2 / 3 take one task per thread instead of
 // two: the same shared-memory layout and tables, 16 warps per SM instead of 8, <= 128 registers per thread.
 // WS: the padded window (64 KB) lives in shared memory instead of L2 / L1
-template <bool MEL, int kThreads, bool WS>
-__global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
+// R1 = 8 / 16 (n_fft 4096 / 8192): the same three steps with an 8- / 16-point first DFT, one task per thread
+// (kThreads = 16 R1 = 128 / 256; R1 = 8 walks two columns per thread in step 1), 35 / 70 KB of shared memory and
+// four / two CTAs per SM.
+template <bool MEL, int kThreads, bool WS, int R1>
+__global__ void __launch_bounds__(kThreads, R1 == 8 ? 4 : (R1 == 16 ? 2 : 1)) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
                                                                long long n_items, long long items_per_track) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kNC = 256 * R1;             // complex points
+    constexpr int kBufElems = buf_elems(R1);
+    static_assert(kThreads == 16 * R1 || (R1 == 32 && kThreads == 256), "one (k1, n3) task per thread, or the two-task R1 = 32 variant");
     Elem *buf = reinterpret_cast<Elem *>(smem_raw);                         // [kBufElems]
-    float2 *tw_a = reinterpret_cast<float2 *>(buf + kBufElems);   // [31][16] W_512^(n2 k1)
-    float2 *tw_b = tw_a + 31 * 16;                                          // [32][16] W_8192^(n3 k1)
-    float2 *tw_c = tw_b + 32 * 16;                                          // [16][16] W_256^(n3 k2)
-    float *wsm = reinterpret_cast<float *>(tw_c + 16 * 16);                 // [16384] padded window (WS only)
+    float2 *tw_a = reinterpret_cast<float2 *>(buf + kBufElems);   // [R1 - 1][16] W_(16 R1)^(n2 k1)
+    float2 *tw_b = tw_a + (R1 - 1) * 16;                                    // [R1][16] W_NC^(n3 k1)
+    float2 *tw_c = tw_b + R1 * 16;                                          // [16][16] W_256^(n3 k2)
+    float *wsm = reinterpret_cast<float *>(tw_c + 16 * 16);                 // [n_fft] padded window (WS only)
     __shared__ float red_max[kThreads / 32], red_nmin[kThreads / 32];
     // After the real split the FFT buffer is reused in place: |X[k]| of both frames replaces the first 8 bytes of
     // element idxn(k) (each element is read by exactly one thread before it is overwritten), and the mel partial
@@ -82,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int col = t & (kCols - 1), hsel = t >> 8;  // kThreads == 512: hsel picks the parity of k1 / the upper k1 half
-    for (int i = t; i < 31 * 16 + 32 * 16 + 16 * 16; i += kThreads) tw_a[i] = __ldg(&p.big_tw[i]);
+    for (int i = t; i < (R1 - 1) * 16 + R1 * 16 + 16 * 16; i += kThreads) tw_a[i] = __ldg(&p.big_tw[i]);
     if constexpr (WS) {
         for (int i = t; i < 2 * kNC / 4; i += kThreads)
             reinterpret_cast<float4 *>(wsm)[i] = __ldg(reinterpret_cast<const float4 *>(p.big_wpad) + i);
@@ -91,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
     // what it finds there is left-over FFT data, finite whenever the frame is)
     __syncthreads();
     const int half = p.win / 2;
-    const float2 w_own = __ldg(&p.twiddle[t]);  // W_16384^t (real split, 512-thread variant)
+    const float2 w_own = __ldg(&p.twiddle[t]);  // W_n_fft^t (real split, 512-thread variant)
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const long long track = item / items_per_track, chunk = item - track * items_per_track;
@@ -105,11 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
             const bool has_b = fa + 1 < f_end;
             const long long fb = has_b ? fa + 1 : fa;  // an odd last frame is computed twice, stored once
             // ---- step 1: load + window, 32-point DFT over n1 ----
-            if constexpr (kThreads == 256) {
-            cx v[32];
+            if constexpr (kThreads != 512) {
+#pragma unroll 1
+            for (int c = t; c < kCols; c += kThreads) {   // one column per thread (two when R1 = 8)
+            cx v[R1];
             {
                 const long long tap0[2] = {(d.frame_begin + fa) * p.hop - half, (d.frame_begin + fb) * p.hop - half};
-                const float *wsrc = p.big_wpad + 2 * t;
+                const float *wsrc = p.big_wpad + 2 * c;
                 bool interior[2];
 #pragma unroll
                 for (int f = 0; f < 2; f++) {
@@ -118,23 +137,29 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                                   first + 2 * kNC <= d.pcm_offset + d.slice_len &&
                                   ((reinterpret_cast<uintptr_t>(d.pcm + (first - d.pcm_offset))) & 7) == 0;
                 }
-                if (interior[0] && interior[1] && has_b && p.hop == 1024) {
-                    // frame B starts hop = 1024 samples = 2 rows of 256 complex later: 34 loads serve both frames
-                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * t;
-                    float2 r[34];
+                bool done = false;
+                if constexpr (R1 == 32) {
+                    if (interior[0] && interior[1] && has_b && p.hop == 1024) {
+                        // frame B starts hop = 1024 samples = 2 rows of 256 complex later: 34 loads serve both frames
+                        const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * c;
+                        float2 r[34];
 #pragma unroll
-                    for (int n1 = 0; n1 < 34; n1++) r[n1] = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
+                        for (int n1 = 0; n1 < 34; n1++) r[n1] = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; n1++) {
-                        const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
-                        v[n1].re = make_float2(r[n1].x * w.x, r[n1 + 2].x * w.x);
-                        v[n1].im = make_float2(r[n1].y * w.y, r[n1 + 2].y * w.y);
+                        for (int n1 = 0; n1 < 32; n1++) {
+                            const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
+                            v[n1].re = make_float2(r[n1].x * w.x, r[n1 + 2].x * w.x);
+                            v[n1].im = make_float2(r[n1].y * w.y, r[n1 + 2].y * w.y);
+                        }
+                        done = true;
                     }
+                }
+                if (done) {
                 } else if (interior[0] && interior[1]) {
-                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * t;
-                    const float *src_b = d.pcm + (tap0[1] - p.pad_left - d.pcm_offset) + 2 * t;
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * c;
+                    const float *src_b = d.pcm + (tap0[1] - p.pad_left - d.pcm_offset) + 2 * c;
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; n1++) {
+                    for (int n1 = 0; n1 < R1; n1++) {
                         const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 512 * n1));
                         const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 512 * n1));
                         const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
@@ -149,26 +174,27 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                         return pcm_sample(d, reflect_index(tap0[f] + a, d.full_len) - d.pcm_offset);
                     };
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; n1++) {
-                        const int pos = 512 * n1 + 2 * t;
+                    for (int n1 = 0; n1 < R1; n1++) {
+                        const int pos = 512 * n1 + 2 * c;
                         const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
                         v[n1].re = make_float2(tap(0, pos) * w.x, tap(1, pos) * w.x);
                         v[n1].im = make_float2(tap(0, pos + 1) * w.y, tap(1, pos + 1) * w.y);
                     }
                 }
             }
-            dft32p(v);
+            dft_r<R1>(v);
             {
-                const int n2 = t >> 4, n3 = t & 15;
+                const int n2 = c >> 4, n3 = c & 15;
 #pragma unroll
-                for (int k1 = 0; k1 < 32; k1++) {
-                    cx o = v[perm32(k1)];
+                for (int k1 = 0; k1 < R1; k1++) {
+                    cx o = v[perm_r<R1>(k1)];
                     if (k1) {
                         const float2 w = tw_a[(k1 - 1) * 16 + n2];
                         o = cmul_s(o, w.x, w.y);
                     }
                     buf[idx3(k1, n2, n3)] = to_elem(o);
                 }
+            }
             }
             } else {
                 // two threads per column: this one computes the outputs k1 = 2 q + hsel
@@ -243,10 +269,10 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                 }
             }
             __syncthreads();
-            // ---- step 2: 16-point DFT over n2, twiddle W_8192^(n3 (k1 + 32 k2)) ----
+            // ---- step 2: 16-point DFT over n2, twiddle W_NC^(n3 (k1 + R1 k2)) ----
 #pragma unroll 1
-            for (int pr = (kThreads == 512 ? hsel : 0); pr < (kThreads == 512 ? hsel + 1 : 2); pr++) {
-                const int k1 = (col >> 4) + 16 * pr, n3 = col & 15;
+            for (int task = t; task < 16 * R1; task += kThreads) {
+                const int k1 = task >> 4, n3 = task & 15;
                 cx u[16];
 #pragma unroll
                 for (int n2 = 0; n2 < 16; n2++) u[n2] = to_cx(buf[idx3(k1, n2, n3)]);
@@ -262,8 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                 }
             }
             __syncthreads();
-            // ---- step 3: 16-point DFT over n3 -> Z[k1 + 32 k2 + 512 k3], then natural order ----
-            if constexpr (kThreads == 256) {
+            // ---- step 3: 16-point DFT over n3 -> Z[k1 + R1 k2 + 16 R1 k3], then natural order ----
+            if constexpr (kThreads == 256 && R1 == 32) {
                 cx u0[16], u1[16];
                 const int k2 = t & 15, k1a = t >> 4, k1b = k1a + 16;
 #pragma unroll
@@ -281,13 +307,13 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                 }
             } else {
                 cx u[16];
-                const int k2 = col & 15, k1 = (col >> 4) + 16 * hsel;
+                const int k2 = t & 15, k1 = t >> 4;   // kThreads == 16 R1: one (k1, k2) task per thread
 #pragma unroll
                 for (int n3 = 0; n3 < 16; n3++) u[n3] = to_cx(buf[idx3(k1, k2, n3)]);
                 dft16p(u);
                 __syncthreads();
 #pragma unroll
-                for (int k3 = 0; k3 < 16; k3++) buf[idxn(k1 + 32 * k2 + 512 * k3)] = to_elem(u[perm16(k3)]);
+                for (int k3 = 0; k3 < 16; k3++) buf[idxn(k1 + R1 * k2 + 16 * R1 * k3)] = to_elem(u[perm16(k3)]);
             }
             __syncthreads();
             // ---- real split: pairs (k, 8192 - k), k = t + 256 j; |X|^2 -> dB, or |X| -> mag[] ----
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
                 const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
                 float2 w;
                 if constexpr (kThreads == 512) {
-                    // W_16384^(t + 512 j) = W_16384^t * W_32^j: the thread's own factor sits in a register pair, the
+                    // W_16384^(t + 512 j) = W_16384^t * W_32^j (R1 = 32): the thread's own factor sits in a register pair, the
                     // other is a 9-entry constant table -- no L2 round trip per bin pair
                     const float c = kC32[j], sn = -kS32[j];
                     w = make_float2(fmaf(-w_own.y, sn, w_own.x * c), fmaf(w_own.x, sn, w_own.y * c));
@@ -406,26 +432,30 @@ __global__ void __launch_bounds__(kThreads, 1) stft16384_kernel(const PlanDev p,
     }
 }
 
-size_t big_smem_bytes(const PlanDev &, bool ws = false) {
-    return sizeof(Elem) * (kBufElems) + sizeof(float2) * (31 * 16 + 32 * 16 + 16 * 16) + (ws ? sizeof(float) * 2 * kNC : 0);
+int big_r1(const PlanDev &p) { return p.n_fft / 512; }
+size_t big_smem_bytes(const PlanDev &p, bool ws = false) {
+    const int r1 = big_r1(p);
+    return sizeof(Elem) * buf_elems(r1) + sizeof(float2) * ((r1 - 1) * 16 + r1 * 16 + 16 * 16) + (ws ? sizeof(float) * p.n_fft : 0);
 }
 
 }  // namespace
 
 bool stft_big_supported(const PlanDev &p) {
-    if (p.n_fft != 2 * kNC || !p.big_wpad || !p.big_tw) return false;
-    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > kBufElems)) return false;
-    return big_smem_bytes(p) <= 226 * 1024;
+    if ((p.n_fft != 4096 && p.n_fft != 8192 && p.n_fft != 16384) || !p.big_wpad || !p.big_tw) return false;
+    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > buf_elems(big_r1(p)))) return false;
+    return big_smem_bytes(p, true) <= 226 * 1024 || big_smem_bytes(p) <= 226 * 1024;
 }
 
 namespace {
-template <bool MEL, int NT, bool WS>
-cudaError_t launch_big_nt(const PlanDev &plan, const TrackDesc *d_tracks, long long n_items, long long items_per_track, int grid,
+template <bool MEL, int NT, bool WS, int R1>
+cudaError_t launch_big_nt(const PlanDev &plan, const TrackDesc *d_tracks, long long n_items, long long items_per_track, int sm_count,
                           cudaStream_t st) {
     const size_t smem = big_smem_bytes(plan, WS);
-    cudaError_t e = cudaFuncSetAttribute(stft16384_kernel<MEL, NT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(stft16384_kernel<MEL, NT, WS, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    stft16384_kernel<MEL, NT, WS><<<grid, NT, smem, st>>>(plan, d_tracks, n_items, items_per_track);
+    const long long slots = static_cast<long long>(sm_count) * (R1 == 8 ? 4 : (R1 == 16 ? 2 : 1));  // persistent grid
+    const int grid = static_cast<int>(n_items < slots ? n_items : slots);
+    stft16384_kernel<MEL, NT, WS, R1><<<grid, NT, smem, st>>>(plan, d_tracks, n_items, items_per_track);
     return cudaGetLastError();
 }
 }  // namespace
@@ -435,20 +465,26 @@ cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int 
     if (n_tracks <= 0 || max_frames <= 0) return cudaSuccess;
     const long long items_per_track = (max_frames + 2 * kPairsPerItem - 1) / (2 * kPairsPerItem);
     const long long n_items = items_per_track * n_tracks;
-    const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
-    // A/B knobs: THB_BIG_THREADS = 256 | 512, THB_BIG_WSMEM = 0 | 1 (512 only)
+    const bool mel = plan.n_mel != 0;
+    if (plan.n_fft == 4096)
+        return mel ? launch_big_nt<true, 128, false, 8>(plan, d_tracks, n_items, items_per_track, sm_count, st)
+                   : launch_big_nt<false, 128, false, 8>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+    if (plan.n_fft == 8192)
+        return mel ? launch_big_nt<true, 256, false, 16>(plan, d_tracks, n_items, items_per_track, sm_count, st)
+                   : launch_big_nt<false, 256, false, 16>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+    // n_fft 16384.  A/B knobs: THB_BIG_THREADS = 256 | 512, THB_BIG_WSMEM = 0 | 1 (512 only)
     const char *e = getenv("THB_BIG_THREADS");
     const int nt = (e && atoi(e) == 256) ? 256 : 512;
     const char *w = getenv("THB_BIG_WSMEM");
     const bool ws = nt == 512 && !(w && atoi(w) == 0);
-    if (plan.n_mel) {
-        if (nt == 256) return launch_big_nt<true, 256, false>(plan, d_tracks, n_items, items_per_track, grid, st);
-        if (ws) return launch_big_nt<true, 512, true>(plan, d_tracks, n_items, items_per_track, grid, st);
-        return launch_big_nt<true, 512, false>(plan, d_tracks, n_items, items_per_track, grid, st);
+    if (mel) {
+        if (nt == 256) return launch_big_nt<true, 256, false, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+        if (ws) return launch_big_nt<true, 512, true, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+        return launch_big_nt<true, 512, false, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
     }
-    if (nt == 256) return launch_big_nt<false, 256, false>(plan, d_tracks, n_items, items_per_track, grid, st);
-    if (ws) return launch_big_nt<false, 512, true>(plan, d_tracks, n_items, items_per_track, grid, st);
-    return launch_big_nt<false, 512, false>(plan, d_tracks, n_items, items_per_track, grid, st);
+    if (nt == 256) return launch_big_nt<false, 256, false, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+    if (ws) return launch_big_nt<false, 512, true, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
+    return launch_big_nt<false, 512, false, 32>(plan, d_tracks, n_items, items_per_track, sm_count, st);
 }
 
 }  // namespace thb

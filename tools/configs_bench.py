@@ -178,6 +178,11 @@ def main():
         stft_case(ctx, "C4 mel-default 16384/1024 @96 kHz, 2 tracks", 2, a.c4_seconds, 96000, 16384 / 96.0, 16, Mel, 0, max(1, a.reps - 1), out)
     if "C4L" in only:  # large FFT, linear (8193 bins: 11 GB of f32 per track), 1 track
         stft_case(ctx, "C4 linear 16384/1024 @96 kHz, 1 track", 1, a.c4_seconds, 96000, 16384 / 96.0, 16, Lin, 0, max(1, a.reps - 1), out)
+    if "G" in only:    # other sample rates with the reference's default setting (40 ms / 4): the general kernel's sizes
+        stft_case(ctx, "G default setting @16 kHz (640/160/1024, mel default), 32 ch x 10 min", 32, 600, 16000, 40.0, 4, Mel, 0, a.reps, out)
+        stft_case(ctx, "G default setting @8 kHz (320/80/512, mel default), 32 ch x 10 min", 32, 600, 8000, 40.0, 4, Mel, 0, a.reps, out)
+        stft_case(ctx, "G default setting @96 kHz (3840/960/4096, mel default), 8 ch x 10 min", 8, 600, 96000, 40.0, 4, Mel, 0, a.reps, out)
+        stft_case(ctx, "G default setting @96 kHz linear (3840/960/4096), 8 ch x 10 min", 8, 600, 96000, 40.0, 4, Lin, 0, a.reps, out)
     if "C5" in only:
         envelope_case(ctx, 128, 600, 48000, a.reps, out)
     if "F2" in only:
