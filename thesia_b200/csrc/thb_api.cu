@@ -357,7 +357,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     std::vector<float> bwpad, btw;
     std::vector<uint32_t> bpieces, bpptr;
     std::vector<float> bgw;
-    if (d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384) {
+    if (d.n_fft == 1024 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384) {
         // tables of the two-frame large-FFT kernel (thb_stft_big.cu): the frame is 256 R1 complex points = R1 x 16 x 16
         const int r1 = d.n_fft / 512, ncx = d.n_fft / 2;
         bwpad.assign(d.n_fft, 0.0f);

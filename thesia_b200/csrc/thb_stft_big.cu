@@ -39,16 +39,20 @@ constexpr int kPairsPerItem = 8; // frame pairs a CTA takes at a time
 __device__ __forceinline__ int idx3(int k1, int x, int y) { return k1 * (16 * kRow17) + x * kRow17 + y; }
 __device__ __forceinline__ int idxn(int k) { return k + (k >> 5); }
 // R1 = n_fft / 512 = 8, 16 or 32: the frame is 256 R1 complex points = R1 x 16 x 16
-constexpr int buf_elems(int r1) { return r1 * 16 * kRow17; }  // R1 = 32: 8704 elements of 16 bytes = 136 KB
-static_assert(buf_elems(32) >= 8192 + 8192 / 32 + 32 && buf_elems(8) >= 2048 + 2048 / 32 + 32,
-              "the natural-order layout (+ the 31 bins a mel piece may read past its end) fits the same buffer");
+// the three-step layout needs 272 R1 elements, the natural-order one 264 R1 (+ the 31 bins a mel piece may read past its end)
+constexpr int buf_elems(int r1) { return r1 * 16 * kRow17 > 264 * r1 + 32 ? r1 * 16 * kRow17 : 264 * r1 + 32; }  // R1 = 32: 136 KB
 
 // in-register R-point DFT of both frames; output X[k] is left in v[perm_r<R>(k)]
 template <int R>
 __device__ __forceinline__ void dft_r(cx (&v)[R]) {
     if constexpr (R == 32) dft32p(v);
     else if constexpr (R == 16) dft16p(v);
-    else dft8p(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    else if constexpr (R == 8) dft8p(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    else {
+        const cx a = v[0], b = v[1];
+        v[0] = cadd2(a, b);
+        v[1] = csub2(a, b);
+    }
 }
 template <int R>
 __device__ __forceinline__ constexpr int perm_r(int k) { return R == 32 ? perm32(k) : (R == 16 ? perm16(k) : k); }
@@ -77,9 +81,10 @@ __device__ __forceinline__ float db_of(float s, float re, float im) {
 // WS: the padded window (64 KB) lives in shared memory instead of L2 / L1
 // R1 = 8 / 16 (n_fft 4096 / 8192): the same three steps with an 8- / 16-point first DFT, one task per thread
 // (kThreads = 16 R1 = 128 / 256; R1 = 8 walks two columns per thread in step 1), 35 / 70 KB of shared memory and
-// four / two CTAs per SM.
+// four / two CTAs per SM.  R1 = 2 (n_fft 1024): one warp per CTA walks eight columns in step 1, 11 KB of shared
+// memory, sixteen CTAs per SM.
 template <bool MEL, int kThreads, bool WS, int R1>
-__global__ void __launch_bounds__(kThreads, R1 == 8 ? 4 : (R1 == 16 ? 2 : 1)) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
+__global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 == 16 ? 2 : 1))) stft16384_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks,
                                                                long long n_items, long long items_per_track) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kNC = 256 * R1;             // complex points
@@ -129,13 +134,13 @@ __global__ void __launch_bounds__(kThreads, R1 == 8 ? 4 : (R1 == 16 ? 2 : 1)) st
             {
                 const long long tap0[2] = {(d.frame_begin + fa) * p.hop - half, (d.frame_begin + fb) * p.hop - half};
                 const float *wsrc = p.big_wpad + 2 * c;
-                bool interior[2];
+                bool interior[2], inside[2];   // inside: plain f32 loads, no reflection; interior: and 8-byte aligned
 #pragma unroll
                 for (int f = 0; f < 2; f++) {
                     const long long first = tap0[f] - p.pad_left;  // file index of FFT position 0
-                    interior[f] = !d.pcm_i16 && tap0[f] >= 0 && tap0[f] + p.win <= d.full_len && first >= d.pcm_offset &&
-                                  first + 2 * kNC <= d.pcm_offset + d.slice_len &&
-                                  ((reinterpret_cast<uintptr_t>(d.pcm + (first - d.pcm_offset))) & 7) == 0;
+                    inside[f] = !d.pcm_i16 && tap0[f] >= 0 && tap0[f] + p.win <= d.full_len && first >= d.pcm_offset &&
+                                first + 2 * kNC <= d.pcm_offset + d.slice_len;
+                    interior[f] = inside[f] && ((reinterpret_cast<uintptr_t>(d.pcm + (first - d.pcm_offset))) & 7) == 0;
                 }
                 bool done = false;
                 if constexpr (R1 == 32) {
@@ -166,8 +171,18 @@ __global__ void __launch_bounds__(kThreads, R1 == 8 ? 4 : (R1 == 16 ? 2 : 1)) st
                         v[n1].re = make_float2(xa.x * w.x, xb.x * w.x);
                         v[n1].im = make_float2(xa.y * w.y, xb.y * w.y);
                     }
+                } else if (inside[0] && inside[1]) {
+                    // an odd hop or an odd channel start: the same samples through 4-byte loads
+                    const float *src_a = d.pcm + (tap0[0] - p.pad_left - d.pcm_offset) + 2 * c;
+                    const float *src_b = d.pcm + (tap0[1] - p.pad_left - d.pcm_offset) + 2 * c;
+#pragma unroll
+                    for (int n1 = 0; n1 < R1; n1++) {
+                        const float2 w = __ldg(reinterpret_cast<const float2 *>(wsrc + 512 * n1));
+                        v[n1].re = make_float2(__ldg(src_a + 512 * n1) * w.x, __ldg(src_b + 512 * n1) * w.x);
+                        v[n1].im = make_float2(__ldg(src_a + 512 * n1 + 1) * w.y, __ldg(src_b + 512 * n1 + 1) * w.y);
+                    }
                 } else {
-                    // file edges (numpy-style reflect, utils.rs:111-137), 16-bit PCM, unaligned channels
+                    // file edges (numpy-style reflect, utils.rs:111-137), 16-bit PCM
                     auto tap = [&](int f, int pos) -> float {
                         const int a = pos - p.pad_left;
                         if (a < 0 || a >= p.win) return 0.0f;
@@ -441,7 +456,7 @@ size_t big_smem_bytes(const PlanDev &p, bool ws = false) {
 }  // namespace
 
 bool stft_big_supported(const PlanDev &p) {
-    if ((p.n_fft != 4096 && p.n_fft != 8192 && p.n_fft != 16384) || !p.big_wpad || !p.big_tw) return false;
+    if ((p.n_fft != 1024 && p.n_fft != 4096 && p.n_fft != 8192 && p.n_fft != 16384) || !p.big_wpad || !p.big_tw) return false;
     if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > buf_elems(big_r1(p)))) return false;
     return big_smem_bytes(p, true) <= 226 * 1024 || big_smem_bytes(p) <= 226 * 1024;
 }
@@ -453,7 +468,7 @@ cudaError_t launch_big_nt(const PlanDev &plan, const TrackDesc *d_tracks, long l
     const size_t smem = big_smem_bytes(plan, WS);
     cudaError_t e = cudaFuncSetAttribute(stft16384_kernel<MEL, NT, WS, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const long long slots = static_cast<long long>(sm_count) * (R1 == 8 ? 4 : (R1 == 16 ? 2 : 1));  // persistent grid
+    const long long slots = static_cast<long long>(sm_count) * (R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 == 16 ? 2 : 1)));  // persistent grid
     const int grid = static_cast<int>(n_items < slots ? n_items : slots);
     stft16384_kernel<MEL, NT, WS, R1><<<grid, NT, smem, st>>>(plan, d_tracks, n_items, items_per_track);
     return cudaGetLastError();
@@ -466,6 +481,9 @@ cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int 
     const long long items_per_track = (max_frames + 2 * kPairsPerItem - 1) / (2 * kPairsPerItem);
     const long long n_items = items_per_track * n_tracks;
     const bool mel = plan.n_mel != 0;
+    if (plan.n_fft == 1024)
+        return mel ? launch_big_nt<true, 32, false, 2>(plan, d_tracks, n_items, items_per_track, sm_count, st)
+                   : launch_big_nt<false, 32, false, 2>(plan, d_tracks, n_items, items_per_track, sm_count, st);
     if (plan.n_fft == 4096)
         return mel ? launch_big_nt<true, 128, false, 8>(plan, d_tracks, n_items, items_per_track, sm_count, st)
                    : launch_big_nt<false, 128, false, 8>(plan, d_tracks, n_items, items_per_track, sm_count, st);
