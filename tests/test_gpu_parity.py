@@ -446,6 +446,39 @@ def test_frame_range_shards_equal_whole(ctx):
     assert e.value.code == _lib.THB_ERR_INVALID
 
 
+def test_odd_hop_and_odd_starts_run_on_the_pair_kernel_bit_identically(ctx, monkeypatch):
+    """The reference default at 44.1 kHz has hop 441: frames start on odd samples, so the frame-pair kernel reads them
+    with 4-byte loads.  Its results must equal the scalar kernel's bit for bit (same operation order), whatever the
+    split between them: whole file vs frame-range shards, host vs an odd device pointer, pair kernel vs forced scalar."""
+    import torch
+    from thesia_b200.sharding import split_frames
+    sr = 44100
+    x = synth_pcm(200001, sr, 13, 0, ZERO_GAP)
+    for s in (thb.SpecSetting(), thb.SpecSetting(40.0, 4, 1, thb.FreqScale.Linear)):
+        hop, win, n_fft = s.calc_framing_params(sr)
+        assert (hop, win, n_fft) == (441, 1764, 2048)
+        whole = ctx.calc_spec(x, sr, s, id=40)
+        for parts in (2, 3):
+            units = split_frames(41, 0, sr, x.size, win, hop, parts)
+            pieces = []
+            for k, u in enumerate(units):
+                tr = dict(pcm=x[u.pcm_lo:u.pcm_hi].copy(), id=300 + k, ch=0, sr=sr, full_len=x.size, pcm_offset=u.pcm_lo,
+                          frame_begin=u.frame_begin, frame_count=u.frame_count)
+                pieces.append(ctx.spec_batch([tr], s, want_host=True)[0][2])
+            assert np.array_equal(np.concatenate(pieces, axis=0), whole, equal_nan=True), parts
+        d = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), x])).cuda()
+        assert np.array_equal(ctx.calc_spec(d[1:], sr, s, id=42), whole, equal_nan=True)      # 4-byte aligned start
+        monkeypatch.setenv("THB_STFT_KERNEL", "fast")
+        assert np.array_equal(ctx.calc_spec(x, sr, s, id=43), whole, equal_nan=True)          # scalar kernel only
+        monkeypatch.delenv("THB_STFT_KERNEL")
+    # an even hop on an odd start (48 kHz default from an odd device pointer)
+    s = thb.SpecSetting()
+    y = synth_pcm(150000, 48000, 2, 1, 0)
+    d = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), y])).cuda()
+    assert np.array_equal(ctx.calc_spec(d[1:], 48000, s, id=44), ctx.calc_spec(y, 48000, s, id=45))
+    ctx.release_all()
+
+
 @pytest.mark.parametrize("n_fft_want", [16384, 8192, 4096])
 @pytest.mark.parametrize("scale,n_mel", [(thb.FreqScale.Linear, 0), (thb.FreqScale.Mel, 0), (thb.FreqScale.Mel, 128)])
 def test_large_fft_kernel_shards_edges_and_i16(ctx, orc, scale, n_mel, n_fft_want):

@@ -893,6 +893,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         size_t pair_tiles = 0;
         int stage = 0;
         bool i16 = false;
+        bool pair_unaligned = false;  // some f32 channel of the group needs 4-byte loads (odd hop / odd start)
     };
     std::vector<Launch> launches;
     size_t max_pair_tiles = 0;
@@ -937,7 +938,11 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 const int esz = L.i16 ? 2 : 4;
                 const bool aligned = (addr & (esz - 1)) == 0 && (H & 1) == 0 &&
                                      ((static_cast<long long>(addr / esz) + lo * H - half - padl - f.pcm_offset) & 1) == 0;
-                cnt = aligned ? (cnt & ~1ll) : 0;
+                // f32 channels that miss the 8-byte rule (the 44.1 kHz default has hop 441) still run on the frame-pair
+                // kernel, through its 4-byte-load variant; 16-bit channels that miss it go to the scalar kernel
+                const bool usable = aligned || (!L.i16 && (addr & 3) == 0);
+                if (usable && !aligned && cnt >= 2) L.pair_unaligned = true;
+                cnt = usable ? (cnt & ~1ll) : 0;
                 if (cnt < 2) {
                     if (f.n_frames) edges.push_back(f);
                     continue;
@@ -1021,7 +1026,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
                 {
                     ProfScope ps(ctx, kname, 1);  // the frame-pair kernel alone: this is the roofline kernel
-                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, ctx->sm_count, ctx->stream);
+                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream);
                 }
                 if (e == cudaSuccess) {
                     ProfScope ps(ctx, ename, 1);

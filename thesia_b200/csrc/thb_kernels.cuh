@@ -132,9 +132,10 @@ cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int 
 
 // two frames per warp in packed f32x2 arithmetic, n_fft == 2048
 bool stft_pair_supported(const PlanDev &plan);
-// (every descriptor of one launch holds the same PCM format: pcm_i16 says which)
+// (every descriptor of one launch holds the same PCM format: pcm_i16 says which; `unaligned`: f32 frames need not
+// start on an 8-byte boundary -- odd hops, odd channel starts -- and are read with 4-byte loads)
 cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
-                             bool pcm_i16, int sm_count, cudaStream_t st);
+                             bool pcm_i16, bool unaligned, int sm_count, cudaStream_t st);
 // frames per work item of the frame-pair kernel (a multiple of twice its warps per CTA)
 int stft_pair_tile_frames();
 // the scalar kernel over the tiles on a rescue list (persistent grid; a no-op when the list is empty)

@@ -52,6 +52,8 @@ __device__ __forceinline__ PairSmem carve(unsigned char *raw, int tile_f2) {
 // channel's bit for bit.  (Not the 1.5 * 2^23 exponent-pasting trick: the compiler distributes the window over its
 // subtraction, (x - M) w -> fma(x, w, -M w), which is no longer exact.)
 // HS > 0: hop == 64 HS, so frame B's row n1 is frame A's row n1 + HS and 32 + HS loads serve both frames.
+// HS < 0: frames may start on any 4-byte boundary (odd hop such as the 44.1 kHz default's 441, odd channel start):
+// the same samples through 4-byte loads, everything after the loads is identical.
 template <bool MEL, int NW, bool I16, int HS>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
@@ -128,6 +130,15 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                     const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
                     v[n1].re = make_float2(r[n1].x * w.x, r[n1 + HS].x * w.x);
                     v[n1].im = make_float2(r[n1].y * w.y, r[n1 + HS].y * w.y);
+                }
+            } else if constexpr (HS < 0) {
+                const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
+                const float *src_b = src_a + p.hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    v[n1].re = make_float2(__ldg(src_a + 64 * n1) * w.x, __ldg(src_b + 64 * n1) * w.x);
+                    v[n1].im = make_float2(__ldg(src_a + 64 * n1 + 1) * w.y, __ldg(src_b + 64 * n1 + 1) * w.y);
                 }
             } else {
                 const float *src_a = d.pcm + (first_a - d.pcm_offset) + 2 * lane;
@@ -305,9 +316,13 @@ bool stft_pair_supported(const PlanDev &p) {
 
 // rescue.tile_frames must be stft_pair_tile_frames() and rescue.tiles_per_track = ceil(max n_frames / tile_frames)
 cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
-                             bool pcm_i16, int sm_count, cudaStream_t st) {
+                             bool pcm_i16, bool unaligned, int sm_count, cudaStream_t st) {
     if (n_tracks <= 0 || rescue.tiles_per_track == 0) return cudaSuccess;
     const int nw = pair_warps();
+    if (unaligned && !pcm_i16) {
+        if (plan.n_mel) return launch_nw<true, 12, false, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<false, 12, false, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
     if (pcm_i16) {  // the ingest variant exists for the tuned warp count only
         if (plan.n_mel) return launch_nw<true, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);

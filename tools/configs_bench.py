@@ -178,6 +178,8 @@ def main():
         stft_case(ctx, "C4 mel-default 16384/1024 @96 kHz, 2 tracks", 2, a.c4_seconds, 96000, 16384 / 96.0, 16, Mel, 0, max(1, a.reps - 1), out)
     if "C4L" in only:  # large FFT, linear (8193 bins: 11 GB of f32 per track), 1 track
         stft_case(ctx, "C4 linear 16384/1024 @96 kHz, 1 track", 1, a.c4_seconds, 96000, 16384 / 96.0, 16, Lin, 0, max(1, a.reps - 1), out)
+    if "C3S" in only:  # the reference default at 44.1 kHz: hop 441 is odd, every other frame starts on an odd sample
+        stft_case(ctx, "C3'' default setting 40 ms/4 @44.1 kHz (1764/441/2048, mel default), 32 ch x 10 min", 32, 600, 44100, 40.0, 4, Mel, 0, a.reps, out)
     if "G" in only:    # other sample rates with the reference's default setting (40 ms / 4): the general kernel's sizes
         stft_case(ctx, "G default setting @16 kHz (640/160/1024, mel default), 32 ch x 10 min", 32, 600, 16000, 40.0, 4, Mel, 0, a.reps, out)
         stft_case(ctx, "G default setting @8 kHz (320/80/512, mel default), 32 ch x 10 min", 32, 600, 8000, 40.0, 4, Mel, 0, a.reps, out)
