@@ -468,6 +468,11 @@ def test_odd_hop_and_odd_starts_run_on_the_pair_kernel_bit_identically(ctx, monk
             assert np.array_equal(np.concatenate(pieces, axis=0), whole, equal_nan=True), parts
         d = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), x])).cuda()
         assert np.array_equal(ctx.calc_spec(d[1:], sr, s, id=42), whole, equal_nan=True)      # 4-byte aligned start
+        q = np.round(x * 32768.0).astype(np.int16)                                            # CD audio: 16-bit at 44.1 kHz
+        assert np.array_equal(q.astype(np.float32) / np.float32(32768.0), x)
+        assert np.array_equal(ctx.calc_spec(q, sr, s, id=46), whole, equal_nan=True)
+        dq = torch.from_numpy(np.concatenate([np.zeros(1, np.int16), q])).cuda()
+        assert np.array_equal(ctx.calc_spec(dq[1:], sr, s, id=47), whole, equal_nan=True)     # 2-byte aligned start
         monkeypatch.setenv("THB_STFT_KERNEL", "fast")
         assert np.array_equal(ctx.calc_spec(x, sr, s, id=43), whole, equal_nan=True)          # scalar kernel only
         monkeypatch.delenv("THB_STFT_KERNEL")

@@ -893,7 +893,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         size_t pair_tiles = 0;
         int stage = 0;
         bool i16 = false;
-        bool pair_unaligned = false;  // some f32 channel of the group needs 4-byte loads (odd hop / odd start)
+        bool pair_unaligned = false;  // some channel of the group needs one load per sample (odd hop / odd start)
     };
     std::vector<Launch> launches;
     size_t max_pair_tiles = 0;
@@ -938,9 +938,9 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 const int esz = L.i16 ? 2 : 4;
                 const bool aligned = (addr & (esz - 1)) == 0 && (H & 1) == 0 &&
                                      ((static_cast<long long>(addr / esz) + lo * H - half - padl - f.pcm_offset) & 1) == 0;
-                // f32 channels that miss the 8-byte rule (the 44.1 kHz default has hop 441) still run on the frame-pair
-                // kernel, through its 4-byte-load variant; 16-bit channels that miss it go to the scalar kernel
-                const bool usable = aligned || (!L.i16 && (addr & 3) == 0);
+                // channels that miss the sample-pair rule (the 44.1 kHz default has hop 441) still run on the frame-pair
+                // kernel, through its one-load-per-sample variant
+                const bool usable = aligned || (addr & (esz - 1)) == 0;
                 if (usable && !aligned && cnt >= 2) L.pair_unaligned = true;
                 cnt = usable ? (cnt & ~1ll) : 0;
                 if (cnt < 2) {

@@ -104,7 +104,21 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             cx v[32];
             // ---- load + window: v[n1] = z[32 n1 + lane] of both frames ----
             const long long first_a = (d.frame_begin + fa) * p.hop - half - p.pad_left;  // file index of FFT position 0
-            if constexpr (I16) {
+            if constexpr (I16 && HS < 0) {
+                // 16-bit PCM on an odd hop / odd start (CD audio with the default setting): one 2-byte load per sample
+                const short *src_a = reinterpret_cast<const short *>(d.pcm) + (first_a - d.pcm_offset) + 2 * lane;
+                const short *src_b = src_a + p.hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
+                    const float a_re = static_cast<float>(static_cast<int>(__ldg(src_a + 64 * n1)));
+                    const float a_im = static_cast<float>(static_cast<int>(__ldg(src_a + 64 * n1 + 1)));
+                    const float b_re = static_cast<float>(static_cast<int>(__ldg(src_b + 64 * n1)));
+                    const float b_im = static_cast<float>(static_cast<int>(__ldg(src_b + 64 * n1 + 1)));
+                    v[n1].re = make_float2(a_re * w.x, b_re * w.x);
+                    v[n1].im = make_float2(a_im * w.y, b_im * w.y);
+                }
+            } else if constexpr (I16) {
                 const uint32_t *src_a = reinterpret_cast<const uint32_t *>(reinterpret_cast<const short *>(d.pcm) +
                                                                            (first_a - d.pcm_offset) + 2 * lane);
                 const uint32_t *src_b = src_a + (p.hop >> 1);
@@ -322,6 +336,10 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
     if (unaligned && !pcm_i16) {
         if (plan.n_mel) return launch_nw<true, 12, false, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, false, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
+    if (unaligned) {
+        if (plan.n_mel) return launch_nw<true, 12, true, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        return launch_nw<false, 12, true, -1>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
     if (pcm_i16) {  // the ingest variant exists for the tuned warp count only
         if (plan.n_mel) return launch_nw<true, 12, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
