@@ -114,6 +114,23 @@ def spectrogram_tile_geometry(height: int, width: int, level_x: int, level_y: in
     return tuple(g)
 
 
+class PreparedTracks:
+    """A thb_track array built once from track dicts (and the buffers it points at, kept alive)."""
+
+    def __init__(self, tracks: Sequence[dict]):
+        self.n = len(tracks)
+        self.arr = (Track * max(self.n, 1))()
+        self.keep = []
+        for i, t in enumerate(tracks):
+            addr, ln, k, fmt = _ptr_len_fmt(t["pcm"])
+            self.keep.append(k)
+            self.arr[i] = Track(addr, ln, int(t["id"]), int(t.get("ch", 0)), int(t["sr"]), int(t.get("full_len", 0)),
+                                int(t.get("pcm_offset", 0)), int(t.get("frame_begin", 0)), int(t.get("frame_count", 0)), fmt, 0)
+
+    def __len__(self) -> int:
+        return self.n
+
+
 def normalize_gain(kind: int, target: float, global_lufs: float = 0.0, rms_dB: float = 0.0,
                    max_peak_dB: float = 0.0) -> float:
     """Normalize::normalize_default's gain (dynamics/normalize.rs:23-45); kind = _lib.NORM_*."""
@@ -184,9 +201,19 @@ class Context:
         check(lib().thb_synchronize(self._h), self._h)
 
     # ---- update_specs seam ----
+    @staticmethod
+    def prepare_tracks(tracks: Sequence[dict]) -> "PreparedTracks":
+        """Marshal a track list into the C array once; pass the result to spec_batch() as often as needed."""
+        return PreparedTracks(tracks)
+
     def spec_batch(self, tracks: Sequence[dict], setting: SpecSetting, want_host: bool = False):
         """tracks: dicts with pcm, id, ch, sr and optional full_len, pcm_offset, frame_begin,
         frame_count.  Returns a list of (n_frames, n_bins[, spec ndarray])."""
+        if isinstance(tracks, PreparedTracks):   # descriptors marshalled once (a host program keeps its thb_track array)
+            if want_host:
+                raise ValueError("prepared track lists are for device-resident results")
+            check(lib().thb_spec_batch(self._h, tracks.arr, tracks.n, C.byref(setting._c()), None), self._h)
+            return None
         n = len(tracks)
         if n == 0:
             return []
