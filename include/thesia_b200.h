@@ -162,6 +162,14 @@ int thb_spec_minmax(thb_ctx *ctx, uint64_t id, uint32_t ch, float *mn, float *mx
 int thb_release(thb_ctx *ctx, uint64_t id, uint32_t ch);
 int thb_release_all(thb_ctx *ctx);
 
+/* SpectrogramAnalyzer::prepare / retain (spectrogram.rs:116-185): the per-(sr, win, n_fft[, mel]) plan cache (window,
+ * twiddles, mel schedules; KBs each, built on first use by thb_spec_batch).  thb_plans_prepare builds the plans of
+ * `setting` for the n sample rates ahead of time; thb_plans_retain drops every cached plan that `setting` does not need
+ * for those sample rates -- what TrackManager does after remove_tracks / set_setting (mod.rs:96-99,110-112) -- and
+ * reports how many are left. */
+int thb_plans_prepare(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n);
+int thb_plans_retain(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n, size_t *n_left);
+
 /* ---- TrackManager::update_spec_imgs (mod.rs:168-230) ----------------------------------------
  * thb_minmax_global: global (min, max) over every retained spectrogram (mod.rs:169-178), reduced
  * across ranks with one ncclAllReduce(max) of {max, -min} when a communicator is attached, then

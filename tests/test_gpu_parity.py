@@ -515,6 +515,24 @@ def test_large_fft_kernel_shards_edges_and_i16(ctx, orc, scale, n_mel, n_fft_wan
     ctx.release_all()
 
 
+def test_plan_cache_prepare_and_retain(ctx):
+    """SpectrogramAnalyzer::prepare / retain (spectrogram.rs:116-185): plans are cached per (sr, win, n_fft[, mel]) and
+    dropped when the track list no longer needs them; results do not depend on the cache state."""
+    a = thb.SpecSetting(40.0, 4, 1, thb.FreqScale.Mel, 0)
+    b = thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Linear)
+    assert ctx.plans_retain(a, []) == 0                       # empty track list: nothing is kept
+    ctx.plans_prepare(a, [48000, 44100, 16000])
+    assert ctx.plans_retain(a, [48000, 44100, 16000]) == 3
+    x = synth_pcm(60000, 48000, 1, 0, 0)
+    first = ctx.calc_spec(x, 48000, a, id=70)
+    ctx.calc_spec(x, 48000, b, id=71)                         # a fourth plan (other setting)
+    assert ctx.plans_retain(a, [48000]) == 1                  # set_setting(a) with only 48 kHz tracks left
+    assert np.array_equal(ctx.calc_spec(x, 48000, a, id=70), first)
+    assert ctx.plans_retain(b, [48000]) == 0                  # the setting changed: a's plan goes, b's is rebuilt on use
+    assert np.array_equal(ctx.calc_spec(x, 48000, a, id=70), first)
+    ctx.release_all()
+
+
 def test_error_behaviour(ctx):
     with pytest.raises(thb.ThbError) as e:
         ctx.calc_spec(np.zeros(1, np.float32), 48000, thb.SpecSetting())

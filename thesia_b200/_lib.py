@@ -104,6 +104,8 @@ SIGNATURES = {
     "thb_spec_minmax": (_i, [_vp, _u64, _u32, _P(_f32), _P(_f32)]),
     "thb_release": (_i, [_vp, _u64, _u32]),
     "thb_release_all": (_i, [_vp]),
+    "thb_plans_prepare": (_i, [_vp, _P(Setting), _P(_u32), C.c_size_t]),
+    "thb_plans_retain": (_i, [_vp, _P(Setting), _P(_u32), C.c_size_t, _P(C.c_size_t)]),
     "thb_minmax_global": (_i, [_vp, _f32, _P(_f32), _P(_f32)]),
     "thb_spec_to_img": (_i, [_vp, _u64, _u32, _u64, _u64, _f32, _f32, _u32, _vp, _u64]),
     "thb_update_spec_imgs": (_i, [_vp, _f32, _u32, _u32, _P(_u64), C.c_size_t, _P(_f32), _P(_f32)]),

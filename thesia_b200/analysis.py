@@ -248,6 +248,20 @@ class Context:
                 res.append((outs[i].n_frames, outs[i].n_bins))
         return res
 
+    def plans_prepare(self, setting: SpecSetting, srs: Iterable[int]) -> None:
+        """SpectrogramAnalyzer::prepare (spectrogram.rs:116-154) for the sample rates of the track list."""
+        v = [int(x) for x in srs]
+        arr = (C.c_uint32 * max(len(v), 1))(*v)
+        check(lib().thb_plans_prepare(self._h, C.byref(setting._c()), arr, len(v)), self._h)
+
+    def plans_retain(self, setting: SpecSetting, srs: Iterable[int]) -> int:
+        """SpectrogramAnalyzer::retain (spectrogram.rs:156-185); returns the number of cached plans left."""
+        v = [int(x) for x in srs]
+        arr = (C.c_uint32 * max(len(v), 1))(*v)
+        left = C.c_size_t()
+        check(lib().thb_plans_retain(self._h, C.byref(setting._c()), arr, len(v), C.byref(left)), self._h)
+        return left.value
+
     def calc_spec(self, wav, sr: int, setting: SpecSetting, id: int = 0, ch: int = 0) -> np.ndarray:
         """SpectrogramAnalyzer::calc_spec (spectrogram.rs:187-212): dB spectrogram (T, B)."""
         return self.spec_batch([dict(pcm=wav, id=id, ch=ch, sr=sr)], setting, want_host=True)[0][2]
@@ -589,6 +603,8 @@ class TrackManager:
                 self.ctx.release(*tup)
                 self._spec_keys.discard(tup)
                 self._img_keys.discard(tup)
+        # spec_analyzer.retain(construct_all_sr_win_nfft_set(setting), freq_scale)  (mod.rs:96-99)
+        self.ctx.plans_retain(self.setting, sorted({tracklist.sr(i) for i in tracklist.all_ids()}))
 
     # -- mod.rs:102-105
     def apply_track_list_changes(self, tracklist: TrackList):
@@ -598,6 +614,7 @@ class TrackManager:
     # -- mod.rs:107-115
     def set_setting(self, tracklist: TrackList, setting: SpecSetting) -> None:
         self.setting = replace(setting)
+        self.ctx.plans_retain(self.setting, sorted({tracklist.sr(i) for i in tracklist.all_ids()}))   # mod.rs:110-112
         self._update_specs(tracklist, tracklist.id_ch_tuples())
         self._update_spec_imgs(tracklist, True)
 

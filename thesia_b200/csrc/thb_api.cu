@@ -1170,6 +1170,53 @@ int thb_release_all(thb_ctx *ctx) {
     return THB_OK;
 }
 
+// ---- SpectrogramAnalyzer::prepare / retain (spectrogram.rs:116-185): the plan cache ---------------------
+int thb_plans_prepare(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!setting || (!srs && n)) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; i++) {
+        const Plan *pl = nullptr;
+        int rc = get_plan(ctx, *setting, srs[i], &pl);
+        if (rc) return rc;
+    }
+    return THB_OK;
+}
+
+int thb_plans_retain(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n, size_t *n_left) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!setting || (!srs && n)) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    // the SrWinNfft set of the track list under this setting (track.rs construct_all_sr_win_nfft_set)
+    std::vector<PlanKey> keep;
+    for (size_t i = 0; i < n; i++) {
+        const thb::Framing f = thb::framing_params(*setting, srs[i]);
+        keep.push_back(PlanKey{srs[i], f.hop, f.win, f.n_fft, setting->freq_scale, setting->freq_scale == THB_FREQ_MEL ? setting->n_mel : 0u});
+    }
+    bool synced = false;
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end();) {
+        const PlanKey &k = it->first;
+        bool wanted = false;
+        for (const PlanKey &w : keep)
+            wanted |= k.sr == w.sr && k.win == w.win && k.n_fft == w.n_fft && k.hop == w.hop && k.freq_scale == w.freq_scale &&
+                      k.n_mel_req == w.n_mel_req;
+        if (wanted) {
+            ++it;
+            continue;
+        }
+        if (!synced) {  // a kernel of an earlier batch may still be reading the tables
+            CK(cudaStreamSynchronize(ctx->stream));
+            synced = true;
+        }
+        for (void *p : it->second->allocs) cudaFree(p);
+        it = ctx->plans.erase(it);
+    }
+    if (n_left) *n_left = ctx->plans.size();
+    return THB_OK;
+}
+
 // ---- update_spec_imgs -----------------------------------------------------------------------------
 int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB) {
     if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");

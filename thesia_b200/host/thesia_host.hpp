@@ -238,13 +238,24 @@ public:
         no_spec_img_ids_.insert(no_spec_img_ids_.end(), reloaded_ids.begin(), reloaded_ids.end());
     }
     // mod.rs:86-100
-    void remove_tracks(const TrackList &, const std::vector<IdCh> &removed_id_ch_tuples) {
+    // SpectrogramAnalyzer::retain (spectrogram.rs:156-185) for the sample rates still in the track list
+    size_t retain_plans(const TrackList &tracklist) {
+        std::set<uint32_t> srs;
+        for (uint64_t id : tracklist.all_ids()) srs.insert(tracklist.get(id).sr);
+        const std::vector<uint32_t> v(srs.begin(), srs.end());
+        const thb_setting s = setting.c();
+        size_t left = 0;
+        check(thb_plans_retain(ctx_.get(), &s, v.data(), v.size(), &left), ctx_.get());
+        return left;
+    }
+    void remove_tracks(const TrackList &tracklist, const std::vector<IdCh> &removed_id_ch_tuples) {
         for (const IdCh &tup : removed_id_ch_tuples) {
             if (!specs_.count(tup)) continue;
             check(thb_release(ctx_.get(), tup.first, tup.second), ctx_.get());
             specs_.erase(tup);
             spec_imgs_.erase(tup);
         }
+        retain_plans(tracklist);  // spec_analyzer.retain(construct_all_sr_win_nfft_set(setting), freq_scale), mod.rs:96-99
     }
     // mod.rs:102-105
     std::pair<std::set<uint64_t>, uint32_t> apply_track_list_changes(const TrackList &tracklist) {
@@ -254,6 +265,7 @@ public:
     // mod.rs:107-121
     void set_setting(const TrackList &tracklist, const SpecSetting &new_setting) {
         setting = new_setting;
+        retain_plans(tracklist);  // mod.rs:110-112
         update_specs(tracklist, tracklist.id_ch_tuples());
         update_spec_imgs(tracklist, true);
     }
