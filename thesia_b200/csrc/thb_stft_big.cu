@@ -37,10 +37,14 @@ constexpr int kRow17 = 17;       // padded row of 16 elements
 constexpr int kPairsPerItem = 8; // frame pairs a CTA takes at a time
 // element index of A[k1][x][y] (steps 1-3) and of Z[k] (natural order)
 __device__ __forceinline__ int idx3(int k1, int x, int y) { return k1 * (16 * kRow17) + x * kRow17 + y; }
-__device__ __forceinline__ int idxn(int k) { return k + (k >> 5); }
+// natural order: one pad element every P = min(R1, 32) elements (shift = log2 P).  Step 3 writes Z[k1 + R1 k2 + ...] with
+// k2 running over the lanes: a stride of R1 elements of 16 bytes would put a quarter warp on one or two bank groups;
+// with the pad the stride becomes R1 + 1 (odd) and the eight 16-byte stores of a quarter warp hit eight bank groups.
+constexpr int pad_shift(int r1) { return r1 == 16 ? 4 : (r1 == 8 ? 3 : 5); }  // R1 = 2 keeps P = 32: a stride of 2 is a 2-way conflict at worst
 // R1 = n_fft / 512 = 8, 16 or 32: the frame is 256 R1 complex points = R1 x 16 x 16
-// the three-step layout needs 272 R1 elements, the natural-order one 264 R1 (+ the 31 bins a mel piece may read past its end)
-constexpr int buf_elems(int r1) { return r1 * 16 * kRow17 > 264 * r1 + 32 ? r1 * 16 * kRow17 : 264 * r1 + 32; }  // R1 = 32: 136 KB
+// the three-step layout needs 272 R1 elements, the natural-order one NC (1 + 1/P) (+ the 31 bins a mel piece may read past its end)
+constexpr int natural_elems(int r1) { return 256 * r1 + ((256 * r1) >> pad_shift(r1)) + 40; }
+constexpr int buf_elems(int r1) { return r1 * 16 * kRow17 > natural_elems(r1) ? r1 * 16 * kRow17 : natural_elems(r1); }  // R1 = 32: 136 KB
 
 // in-register R-point DFT of both frames; output X[k] is left in v[perm_r<R>(k)]
 template <int R>
@@ -89,6 +93,8 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kNC = 256 * R1;             // complex points
     constexpr int kBufElems = buf_elems(R1);
+    constexpr int kPadShift = pad_shift(R1);
+    auto idxn = [](int k) { return k + (k >> kPadShift); };
     static_assert(kThreads == 16 * R1 || (R1 == 32 && kThreads == 256), "one (k1, n3) task per thread, or the two-task R1 = 32 variant");
     Elem *buf = reinterpret_cast<Elem *>(smem_raw);                         // [kBufElems]
     float2 *tw_a = reinterpret_cast<float2 *>(buf + kBufElems);   // [R1 - 1][16] W_(16 R1)^(n2 k1)

@@ -180,6 +180,8 @@ def main():
         stft_case(ctx, "C4 linear 16384/1024 @96 kHz, 1 track", 1, a.c4_seconds, 96000, 16384 / 96.0, 16, Lin, 0, max(1, a.reps - 1), out)
     if "C3S" in only:  # the reference default at 44.1 kHz: hop 441 is odd, every other frame starts on an odd sample
         stft_case(ctx, "C3'' default setting 40 ms/4 @44.1 kHz (1764/441/2048, mel default), 32 ch x 10 min", 32, 600, 44100, 40.0, 4, Mel, 0, a.reps, out)
+    if "G96" in only:  # the 96 kHz default (n_fft 4096, mel default) alone: profiling target
+        stft_case(ctx, "G default setting @96 kHz (3840/960/4096, mel default), 8 ch x 10 min", 8, 600, 96000, 40.0, 4, Mel, 0, a.reps, out)
     if "G" in only:    # other sample rates with the reference's default setting (40 ms / 4): the general kernel's sizes
         stft_case(ctx, "G default setting @16 kHz (640/160/1024, mel default), 32 ch x 10 min", 32, 600, 16000, 40.0, 4, Mel, 0, a.reps, out)
         stft_case(ctx, "G default setting @8 kHz (320/80/512, mel default), 32 ch x 10 min", 32, 600, 8000, 40.0, 4, Mel, 0, a.reps, out)
