@@ -381,7 +381,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         if ((rc = upload(ctx, pl.get(), btw, &btwp))) return rc;
         d.big_tw = reinterpret_cast<const float2 *>(btwp);
         if (d.n_mel) {
-            // Band-major pieces of <= 32 bins.  32 consecutive pieces form a group that one warp walks in lock step:
+            // Band-major pieces of <= 31 bins.  32 consecutive pieces form a group that one warp walks in lock step:
             // the group's weights are stored step-major ([step][lane], zero padded to the longest piece), so every
             // step is one coalesced 128-byte load.
             const thb::MelBank mb = thb::mel_bank(sr, f.n_fft, s.n_mel);
@@ -389,9 +389,11 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
             std::vector<uint32_t> p_start, p_len, p_wofs;
             for (uint32_t m = 0; m < mb.n_mel; m++) {
                 const uint32_t len = mb.ptr[m + 1] - mb.ptr[m];
-                for (uint32_t o = 0; o < len; o += 32) {
+                // 31, not 32: consecutive pieces of one band then start an odd number of bins apart and land on different
+                // shared-memory banks when sixteen lanes read them in lock step
+                for (uint32_t o = 0; o < len; o += 31) {
                     p_start.push_back(mb.k0[m] + o);
-                    p_len.push_back(std::min<uint32_t>(32, len - o));
+                    p_len.push_back(std::min<uint32_t>(31, len - o));
                     p_wofs.push_back(mb.ptr[m] + o);
                 }
                 bpptr[m + 1] = static_cast<uint32_t>(p_start.size());

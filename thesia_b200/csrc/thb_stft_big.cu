@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
     float2 *tw_c = tw_b + R1 * 16;                                          // [16][16] W_256^(n3 k2)
     float *wsm = reinterpret_cast<float *>(tw_c + 16 * 16);                 // [n_fft] padded window (WS only)
     __shared__ float red_max[kThreads / 32], red_nmin[kThreads / 32];
-    // After the real split the FFT buffer is reused in place: |X[k]| of both frames replaces the first 8 bytes of
-    // element idxn(k) (each element is read by exactly one thread before it is overwritten), and the mel partial
-    // sums go to the second 8 bytes of elements 0, 1, 2, ...
-    auto mag_at = [&](int k) -> float2 & { return buf[idxn(k)].re; };
-    auto part_at = [&](int q) -> float2 & { return buf[q].im; };
+    // After the real split (and a barrier) the FFT buffer is reused: |X[k]| of both frames goes to float2 slot k, the mel
+    // partial sums follow at slot NC + 64.
+    float2 *cmag = reinterpret_cast<float2 *>(buf);            // compact |X[k]| of both frames, bins 0 .. NC (+ 31 read past)
+    float2 *cpart = cmag + kNC + 64;                            // mel partial sums, one per piece
+    auto mag_at = [&](int k) -> float2 & { return cmag[k]; };
+    auto part_at = [&](int q) -> float2 & { return cpart[q]; };
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int col = t & (kCols - 1), hsel = t >> 8;  // kThreads == 512: hsel picks the parity of k1 / the upper k1 half
@@ -339,10 +340,10 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
             __syncthreads();
             // ---- real split: pairs (k, 8192 - k), k = t + 256 j; |X|^2 -> dB, or |X| -> mag[] ----
             float *orow_a = d.out + fa * p.n_bins, *orow_b = d.out + fb * p.n_bins;
-#pragma unroll 4
-            for (int j = 0; j <= kNC / 2 / kThreads; j++) {
+            constexpr int kJ = kNC / 2 / kThreads;   // k = t + kThreads j, j = 0 .. kJ (k = NC / 2 pairs with itself: thread 0 alone)
+            auto split = [&](int j, float2 &mag_lo, float2 &mag_hi) {
                 const int k = t + kThreads * j;
-                if (j == kNC / 2 / kThreads && t != 0) break;  // k = 4096 pairs with itself: one thread
+                if (j == kJ && t != 0) return;
                 const int kp = (kNC - k) & (kNC - 1);
                 const cx zk = to_cx(buf[idxn(k)]), zn = to_cx(buf[idxn(kp)]);
                 const f2 er = padd(zk.re, zn.re), ei = psub(zk.im, zn.im), dr = psub(zk.re, zn.re), di = padd(zk.im, zn.im);
@@ -358,10 +359,10 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
                 const f2 wr = pfma(di, bc(-w.y), pmul(dr, bc(w.x))), wi = pfma(dr, bc(w.y), pmul(di, bc(w.x)));
                 const f2 ar = padd(er, wi), ai = psub(ei, wr), br = psub(er, wi), bi = padd(ei, wr);
                 const f2 sa = pfma(ar, ar, pmul(ai, ai)), sb = pfma(br, br, pmul(bi, bi));
-                const int k_hi = kNC - k;  // bin of the partner: 8192 for k = 0, 4096 for k = 4096 (same bin)
+                const int k_hi = kNC - k;  // bin of the partner: NC for k = 0, NC / 2 for k = NC / 2 (same bin)
                 if (MEL) {
-                    mag_at(k) = make_float2(mag_of(sa.x, ar.x, ai.x), mag_of(sa.y, ar.y, ai.y));
-                    if (k_hi != k) mag_at(k_hi) = make_float2(mag_of(sb.x, br.x, bi.x), mag_of(sb.y, br.y, bi.y));
+                    mag_lo = make_float2(mag_of(sa.x, ar.x, ai.x), mag_of(sa.y, ar.y, ai.y));
+                    mag_hi = make_float2(mag_of(sb.x, br.x, bi.x), mag_of(sb.y, br.y, bi.y));
                 } else {
                     const float a0 = db_of(sa.x, ar.x, ai.x), a1 = db_of(sa.y, ar.y, ai.y);
                     orow_a[k] = a0;
@@ -384,6 +385,27 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
                         }
                     }
                 }
+            };
+            if constexpr (MEL) {
+                // The magnitudes wait in registers until every thread has read its Z[k], Z[NC - k]; then they are stored
+                // COMPACTLY (8 bytes per bin, bin k at float2 slot k of the buffer) so that the mel walk's 32 lanes, each on
+                // its own run of bins, spread over sixteen 8-byte bank pairs instead of the eight a 16-byte element stride
+                // would leave them.
+                float2 mg[2 * (kJ + 1)];
+#pragma unroll
+                for (int j = 0; j <= kJ; j++) split(j, mg[2 * j], mg[2 * j + 1]);
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j <= kJ; j++) {
+                    const int k = t + kThreads * j;
+                    if (j == kJ && t != 0) continue;
+                    cmag[k] = mg[2 * j];
+                    if (kNC - k != k) cmag[kNC - k] = mg[2 * j + 1];
+                }
+            } else {
+                float2 unused0, unused1;
+#pragma unroll 4
+                for (int j = 0; j <= kJ; j++) split(j, unused0, unused1);
             }
             __syncthreads();
             if (MEL) {
@@ -463,7 +485,8 @@ size_t big_smem_bytes(const PlanDev &p, bool ws = false) {
 
 bool stft_big_supported(const PlanDev &p) {
     if ((p.n_fft != 1024 && p.n_fft != 4096 && p.n_fft != 8192 && p.n_fft != 16384) || !p.big_wpad || !p.big_tw) return false;
-    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > buf_elems(big_r1(p)))) return false;
+    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > 2 * buf_elems(big_r1(p)) - (p.n_fft / 2 + 64)))
+        return false;   // compact magnitudes + one partial sum per piece share the FFT buffer
     return big_smem_bytes(p, true) <= 226 * 1024 || big_smem_bytes(p) <= 226 * 1024;
 }
 
