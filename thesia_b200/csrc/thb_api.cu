@@ -336,9 +336,15 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     d.mi_words = d.mi_groups = d.mi_min_start = d.mi_max_reach = 0;
     d.mi_blob = nullptr;
     std::vector<uint32_t> mi_blob;
-    if (d.n_mel && d.n_fft == 2048) {
+    if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
+        // (the large-FFT kernel walks the same bin-major schedule out of global memory)
         const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
         if (mi.valid) mi_blob = mi.blob();
+        if (d.n_fft != 2048 && mi.valid) {
+            // the large-FFT kernel keeps magnitudes (16 lead slots + reach) and two partial sums per slot in its FFT buffer
+            const long long need = 16 + ((static_cast<long long>(mi.max_reach) + 2) & ~1ll) + 2ll * mi.n_groups * 32 + 1;
+            if (mi.min_start < -15 || need > thb::stft_big_buffer_slots(d.n_fft)) mi_blob.clear();  // band-major fallback
+        }
     }
     if (!mi_blob.empty()) {
         const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));

@@ -127,6 +127,8 @@ cudaError_t launch_stft_fast(const PlanDev &plan, const TrackDesc *d_tracks, int
 
 // two frames per CTA in packed f32x2 arithmetic, n_fft == 16384 (handles every frame itself: edges, 16-bit PCM)
 bool stft_big_supported(const PlanDev &plan);
+// float2 slots of its shared-memory buffer (compact magnitudes + mel partial sums must fit)
+int stft_big_buffer_slots(int n_fft);
 cudaError_t launch_stft_big(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
                             int sm_count, cudaStream_t st);
 

@@ -96,11 +96,12 @@ struct MelOps<float2> {
     static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 };
 
+// (g0, gs): this warp takes groups g0, g0 + gs, ... -- (0, 1) when one warp owns the whole frame
 template <typename V>
-__device__ __forceinline__ void mel_walk(const MelView &mv, const V *mag, V *part, int lane) {
+__device__ __forceinline__ void mel_walk(const MelView &mv, const V *mag, V *part, int lane, int g0 = 0, int gs = 1) {
     using O = MelOps<V>;
     const int n_slots = mv.n_groups * 32;
-    for (int g = 0; g < mv.n_groups; g++) {
+    for (int g = g0; g < mv.n_groups; g += gs) {
         const uint2 gh = mv.grp[g];
         const float4 *wq = reinterpret_cast<const float4 *>(mv.base + gh.y) + lane;
         const V *mq = mag + mv.start[g * 32 + lane];
@@ -118,7 +119,7 @@ __device__ __forceinline__ void mel_walk(const MelView &mv, const V *mag, V *par
         part[g * 32 + lane] = rise;
         part[n_slots + g * 32 + lane] = fall;
     }
-    if (lane == 0) part[2 * n_slots] = O::zero();  // the padding slot of the gather (the tile is reused by the transposes)
+    if (lane == 0 && g0 == 0) part[2 * n_slots] = O::zero();  // the padding slot of the gather (the tile is reused by the transposes)
 }
 
 // band 32 r + lane: sum of its partial sums in the schedule's order (the padding rows add the always-zero slot)

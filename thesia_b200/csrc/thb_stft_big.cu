@@ -104,8 +104,11 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
     __shared__ float red_max[kThreads / 32], red_nmin[kThreads / 32];
     // After the real split (and a barrier) the FFT buffer is reused: |X[k]| of both frames goes to float2 slot k, the mel
     // partial sums follow at slot NC + 64.
-    float2 *cmag = reinterpret_cast<float2 *>(buf);            // compact |X[k]| of both frames, bins 0 .. NC (+ 31 read past)
-    float2 *cpart = cmag + kNC + 64;                            // mel partial sums, one per piece
+    // compact |X[k]| of both frames at float2 slot kMagBase + k (the bin-major walk may start up to 15 bins before bin 0 and
+    // reach past bin NC on zero weights), then the mel partial sums
+    float2 *cmag = reinterpret_cast<float2 *>(buf) + k2048::kMagBase;
+    const bool bin_major = MEL && p.mi_blob != nullptr;
+    float2 *cpart = cmag + (bin_major ? ((p.mi_max_reach + 2) & ~1) : kNC + 64);
     auto mag_at = [&](int k) -> float2 & { return cmag[k]; };
     auto part_at = [&](int q) -> float2 & { return cpart[q]; };
 
@@ -116,8 +119,8 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
         for (int i = t; i < 2 * kNC / 4; i += kThreads)
             reinterpret_cast<float4 *>(wsm)[i] = __ldg(reinterpret_cast<const float4 *>(p.big_wpad) + i);
     }
-    // (the mel walk reads up to 31 bins past a piece with weight 0: idxn(8192 + 31) = 8479 is inside the buffer, and
-    // what it finds there is left-over FFT data, finite whenever the frame is)
+    // (the mel walks read a few bins before bin 0 / past bin NC with weight 0: those slots are inside the buffer, and what
+    // they find there is left-over FFT data, finite whenever the frame is)
     __syncthreads();
     const int half = p.win / 2;
     const float2 w_own = __ldg(&p.twiddle[t]);  // W_n_fft^t (real split, 512-thread variant)
@@ -408,9 +411,61 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
                 for (int j = 0; j <= kJ; j++) split(j, unused0, unused1);
             }
             __syncthreads();
-            if (MEL) {
-                // ---- sparse mel: a warp walks 32 pieces (<= 32 consecutive bins of one band each) in lock step ----
-                // ---- sparse mel: a warp walks 32 pieces (<= 32 consecutive bins of one band each) in lock step ----
+            if (MEL && bin_major) {
+                // ---- sparse mel, bin-major (the schedule of the n_fft 2048 kernels, thb_host.hpp MelItems, read from global
+                // memory): every |X[k]| is read once and multiplied by a (rise, fall) weight pair; the lanes of a half warp
+                // start on sixteen different residues mod 16, so the float2 reads are conflict-free; the warps share the groups
+                const k2048::MelView mv(p.mi_blob);
+                {
+                    // mel_walk (thb_stft2048.cuh) with the schedule in L2 instead of shared memory: the group headers of
+                    // this warp are fetched together, and all weights of a group are in registers before the first use,
+                    // so a group costs one L2 round trip, not one per step
+                    constexpr int kNW = kThreads / 32, kMaxT2 = 9;   // T <= kMelPieceMax + 3, even
+                    const int n_slots = mv.n_groups * 32;
+                    for (int g = warp; g < mv.n_groups; g += kNW) {
+                        const uint2 gh = __ldg(mv.grp + g);
+                        const int st = __ldg(mv.start + g * 32 + lane);
+                        const float4 *wq = reinterpret_cast<const float4 *>(mv.base + gh.y) + lane;
+                        const int T2 = static_cast<int>(gh.x) >> 1;
+                        float4 wv[kMaxT2];
+#pragma unroll
+                        for (int i = 0; i < kMaxT2; i++) wv[i] = i < T2 ? __ldg(wq + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float2 *mq = cmag + st;
+                        f2 rise = make_float2(0.f, 0.f), fall = rise;
+#pragma unroll
+                        for (int i = 0; i < kMaxT2; i++) {
+                            if (i < T2) {
+                                const float2 m0 = mq[2 * i], m1 = mq[2 * i + 1];
+                                rise = pfma(m0, bc(wv[i].x), rise);
+                                fall = pfma(m0, bc(wv[i].y), fall);
+                                rise = pfma(m1, bc(wv[i].z), rise);
+                                fall = pfma(m1, bc(wv[i].w), fall);
+                            }
+                        }
+                        cpart[g * 32 + lane] = rise;
+                        cpart[n_slots + g * 32 + lane] = fall;
+                    }
+                    if (t == 0) cpart[2 * n_slots] = make_float2(0.f, 0.f);   // the padding slot of the gather
+                }
+                __syncthreads();
+                for (int r = warp; 32 * r < mv.n_mel; r += kThreads / 32) {
+                    const int m = 32 * r + lane;
+                    const f2 acc = k2048::mel_band<float2>(mv, cpart, r, lane);
+                    if (m >= mv.n_mel) continue;
+                    const float a0 = kDbPerLog2Amp * lg2_ftz(acc.x), a1 = kDbPerLog2Amp * lg2_ftz(acc.y);
+                    orow_a[m] = a0;
+                    lmax = fmaxf(lmax, a0);
+                    lnmin = fmaxf(lnmin, -a0);
+                    if (has_b) {
+                        orow_b[m] = a1;
+                        lmax = fmaxf(lmax, a1);
+                        lnmin = fmaxf(lnmin, -a1);
+                    }
+                }
+                __syncthreads();
+            } else if (MEL) {
+                // ---- sparse mel, band-major fallback (banks the bin-major schedule does not cover): a warp walks 32 pieces
+                // (<= 31 consecutive bins of one band each) in lock step ----
                 const int n_groups = (p.big_n_pieces + 31) >> 5;
                 for (int g = warp; g < n_groups; g += kThreads / 32) {
                     const int q = 32 * g + lane;
@@ -483,10 +538,16 @@ size_t big_smem_bytes(const PlanDev &p, bool ws = false) {
 
 }  // namespace
 
+int stft_big_buffer_slots(int n_fft) { return 2 * buf_elems(n_fft / 512); }
+
 bool stft_big_supported(const PlanDev &p) {
     if ((p.n_fft != 1024 && p.n_fft != 4096 && p.n_fft != 8192 && p.n_fft != 16384) || !p.big_wpad || !p.big_tw) return false;
-    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > 2 * buf_elems(big_r1(p)) - (p.n_fft / 2 + 64)))
+    if (p.n_mel && (!p.big_pieces || !p.big_pptr || !p.big_w || p.big_n_pieces > 2 * buf_elems(big_r1(p)) - (p.n_fft / 2 + 64 + k2048::kMagBase)))
         return false;   // compact magnitudes + one partial sum per piece share the FFT buffer
+    if (p.n_mel && p.mi_blob &&
+        (p.mi_min_start < -(k2048::kMagBase - 1) ||
+         k2048::kMagBase + ((p.mi_max_reach + 2) & ~1) + 2 * p.mi_groups * 32 + 1 > 2 * buf_elems(big_r1(p))))
+        return false;   // (the plan builder only keeps a bin-major schedule that fits: see thb_api.cu)
     return big_smem_bytes(p, true) <= 226 * 1024 || big_smem_bytes(p) <= 226 * 1024;
 }
 
