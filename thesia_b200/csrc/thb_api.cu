@@ -869,20 +869,6 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             it.d_pcm = static_cast<const float *>(it.staging);
         }
     }
-    if (any_host) {
-        // the staging buffers exist once ctx->stream reaches this point; the copies then run stage by stage on the
-        // copy stream, each stage followed by its event
-        CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->h2d_ev, 0));
-        for (int c = 1; c <= n_stages; c++) {
-            for (size_t i = 0; i < n; i++)
-                if (items[i].chunk == c)
-                    CK(cudaMemcpyAsync(items[i].staging, tracks[i].pcm, (items[i].i16 ? 2 : 4) * tracks[i].len,
-                                       cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(cudaEventRecord(ctx->stage_ev[c - 1], ctx->copy_stream));
-        }
-    }
-
     // ---- descriptors, one array per plan group ----
     // THB_STFT_KERNEL = generic | fast | pair pins one implementation (A/B measurements); default: best
     const char *force = getenv("THB_STFT_KERNEL");
@@ -994,6 +980,23 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     }
     rc = arena_commit(ctx);
     if (rc) return rc;
+    // The PCM copies are queued only now, AFTER the descriptor upload: that small host-to-device copy on ctx->stream
+    // shares the DMA queue with them, and queued behind 14 GB of PCM it held every kernel back until the last stage had
+    // landed (measured: the whole 20 ms of kernel time ran after the copies instead of under them).
+    if (any_host) {
+        // the staging buffers exist once ctx->stream reaches this point; the copies then run stage by stage on the
+        // copy stream, each stage followed by its event
+        CK(cudaEventRecord(ctx->h2d_ev, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->h2d_ev, 0));
+        for (int c = 1; c <= n_stages; c++) {
+            for (size_t i = 0; i < n; i++)
+                if (items[i].chunk == c)
+                    CK(cudaMemcpyAsync(items[i].staging, tracks[i].pcm, (items[i].i16 ? 2 : 4) * tracks[i].len,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->stage_ev[c - 1], ctx->copy_stream));
+        }
+    }
+
     if (max_pair_tiles > ctx->rescue_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_rescue_items) cudaFree(ctx->d_rescue_items);
