@@ -149,3 +149,45 @@ def test_spectrogram_tile_geometry_matches_oracle(orc):
         for lx, ly, tx, ty in ((0, 0, 0, 0), (0, 0, 3, 0), (3, 1, 1, 0), (9, 4, 0, 0), (40, 70, 0, 0), (2, 0, 10 ** 6, 0),
                                (0, 0, W // 512, H // 512), (1, 1, (W // 2) // 512, 0), (0, 3, 5, 1)):
             assert spectrogram_tile_geometry(H, W, lx, ly, tx, ty) == orc.spectrogram_tile_geometry(H, W, lx, ly, tx, ty)
+
+
+# ---- randomized sweeps: the product's host arithmetic (C ABI, no device) against the oracle's restatement ----
+def test_random_settings_framing_frames_bins_and_ranges(orc):
+    """2 000 random (win_ms, sr, t_overlap, f_overlap) settings: hop / win / n_fft (spectrogram.rs:57-98, round-half-away in
+    f64), frame counts, hz_range_to_idx and tile geometry must equal the oracle's integer for integer."""
+    from thesia_b200.analysis import spectrogram_tile_geometry
+    rng = np.random.default_rng(20261017)
+    srs = [8000, 11025, 16000, 22050, 24000, 32000, 44100, 48000, 88200, 96000, 176400, 192000]
+    checked = 0
+    for _ in range(2000):
+        sr = int(rng.choice(srs))
+        win_ms = float(rng.choice([rng.uniform(0.5, 200.0), rng.integers(1, 200), 2048 / 48.0, 1000.0 * 1024 / sr]))
+        t_ov, f_ov = int(rng.choice([1, 2, 3, 4, 8, 16, 32])), int(rng.choice([1, 1, 1, 2, 4]))
+        want = orc.framing_params(win_ms, sr, t_ov, f_ov)
+        got = thb.SpecSetting(win_ms, t_ov, f_ov).calc_framing_params(sr)
+        assert got == want, (win_ms, sr, t_ov, f_ov)
+        hop, win, n_fft = got
+        if hop == 0 or win < 3:
+            continue
+        n = int(rng.integers(2, 5_000_000))
+        assert thb.n_frames(n, win, hop) == orc.n_frames(n, win, hop)
+        nb = int(rng.integers(1, 4000))
+        max_sr = int(rng.choice(srs))
+        for scale in (0, 1):
+            assert thb.hz_range_to_idx(scale, (0.0, max_sr / 2), sr, nb) == orc.hz_range_to_idx(scale, 0.0, max_sr / 2, sr, nb)
+        H, W = int(rng.integers(1, 9000)), int(rng.integers(1, 700000))
+        lx, ly = int(rng.integers(0, 14)), int(rng.integers(0, 10))
+        tx, ty = int(rng.integers(0, 1 + (W >> lx) // 512 + 1)), int(rng.integers(0, 1 + (H >> ly) // 512 + 1))
+        assert spectrogram_tile_geometry(H, W, lx, ly, tx, ty) == orc.spectrogram_tile_geometry(H, W, lx, ly, tx, ty)
+        checked += 1
+    assert checked > 1500
+
+
+def test_mel_banks_bit_exact_over_sample_rates(orc):
+    """calc_mel_fb_default over every sample rate x n_fft the kernels specialise for: the whole bank, bit for bit."""
+    for sr in (8000, 16000, 22050, 44100, 48000, 96000, 192000):
+        for n_fft in (512, 1024, 2048, 4096, 8192, 16384):
+            if n_fft < sr // 100:     # windows shorter than 10 ms never occur with the reference's settings range
+                continue
+            got = thb.calc_mel_fb_default(sr, n_fft)
+            assert np.array_equal(got, orc.mel_fb_default(sr, n_fft)), (sr, n_fft)
