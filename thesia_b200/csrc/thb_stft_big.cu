@@ -421,29 +421,41 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
                     // this warp are fetched together, and all weights of a group are in registers before the first use,
                     // so a group costs one L2 round trip, not one per step
                     constexpr int kNW = kThreads / 32, kMaxT2 = 9;   // T <= kMelPieceMax + 3, even
+                    constexpr int kBatch = 4;                        // group headers fetched together
                     const int n_slots = mv.n_groups * 32;
-                    for (int g = warp; g < mv.n_groups; g += kNW) {
-                        const uint2 gh = __ldg(mv.grp + g);
-                        const int st = __ldg(mv.start + g * 32 + lane);
-                        const float4 *wq = reinterpret_cast<const float4 *>(mv.base + gh.y) + lane;
-                        const int T2 = static_cast<int>(gh.x) >> 1;
-                        float4 wv[kMaxT2];
+                    for (int gb = warp; gb < mv.n_groups; gb += kBatch * kNW) {
+                        uint2 gh[kBatch];
+                        int st[kBatch];
 #pragma unroll
-                        for (int i = 0; i < kMaxT2; i++) wv[i] = i < T2 ? __ldg(wq + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float2 *mq = cmag + st;
-                        f2 rise = make_float2(0.f, 0.f), fall = rise;
-#pragma unroll
-                        for (int i = 0; i < kMaxT2; i++) {
-                            if (i < T2) {
-                                const float2 m0 = mq[2 * i], m1 = mq[2 * i + 1];
-                                rise = pfma(m0, bc(wv[i].x), rise);
-                                fall = pfma(m0, bc(wv[i].y), fall);
-                                rise = pfma(m1, bc(wv[i].z), rise);
-                                fall = pfma(m1, bc(wv[i].w), fall);
-                            }
+                        for (int b = 0; b < kBatch; b++) {
+                            const int g = gb + b * kNW;
+                            gh[b] = g < mv.n_groups ? __ldg(mv.grp + g) : make_uint2(0u, 0u);
+                            st[b] = g < mv.n_groups ? __ldg(mv.start + g * 32 + lane) : 0;
                         }
-                        cpart[g * 32 + lane] = rise;
-                        cpart[n_slots + g * 32 + lane] = fall;
+#pragma unroll
+                        for (int b = 0; b < kBatch; b++) {
+                            const int g = gb + b * kNW;
+                            if (g >= mv.n_groups) break;
+                            const float4 *wq = reinterpret_cast<const float4 *>(mv.base + gh[b].y) + lane;
+                            const int T2 = static_cast<int>(gh[b].x) >> 1;
+                            float4 wv[kMaxT2];
+#pragma unroll
+                            for (int i = 0; i < kMaxT2; i++) wv[i] = i < T2 ? __ldg(wq + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float2 *mq = cmag + st[b];
+                            f2 rise = make_float2(0.f, 0.f), fall = rise;
+#pragma unroll
+                            for (int i = 0; i < kMaxT2; i++) {
+                                if (i < T2) {
+                                    const float2 m0 = mq[2 * i], m1 = mq[2 * i + 1];
+                                    rise = pfma(m0, bc(wv[i].x), rise);
+                                    fall = pfma(m0, bc(wv[i].y), fall);
+                                    rise = pfma(m1, bc(wv[i].z), rise);
+                                    fall = pfma(m1, bc(wv[i].w), fall);
+                                }
+                            }
+                            cpart[g * 32 + lane] = rise;
+                            cpart[n_slots + g * 32 + lane] = fall;
+                        }
                     }
                     if (t == 0) cpart[2 * n_slots] = make_float2(0.f, 0.f);   // the padding slot of the gather
                 }
