@@ -462,7 +462,18 @@ __global__ void __launch_bounds__(kThreads, R1 == 2 ? 16 : (R1 == 8 ? 4 : (R1 ==
                 __syncthreads();
                 for (int r = warp; 32 * r < mv.n_mel; r += kThreads / 32) {
                     const int m = 32 * r + lane;
-                    const f2 acc = k2048::mel_band<float2>(mv, cpart, r, lane);
+                    // mel_band (thb_stft2048.cuh) with the slot ids in L2: eight ids are fetched together, then summed in
+                    // the schedule's order
+                    const uint2 rd = __ldg(mv.rounds + r);
+                    const uint16_t *row = mv.goff + rd.y * 32 + lane;
+                    f2 acc = make_float2(0.f, 0.f);
+                    for (uint32_t j0 = 0; j0 < rd.x; j0 += 8) {
+                        uint16_t id[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) id[j] = j0 + j < rd.x ? __ldg(row + 32 * (j0 + j)) : static_cast<uint16_t>(2 * mv.n_groups * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) acc = padd(acc, cpart[id[j]]);   // the padding slot holds zero
+                    }
                     if (m >= mv.n_mel) continue;
                     const float a0 = kDbPerLog2Amp * lg2_ftz(acc.x), a1 = kDbPerLog2Amp * lg2_ftz(acc.y);
                     orow_a[m] = a0;
