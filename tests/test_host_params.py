@@ -191,3 +191,12 @@ def test_mel_banks_bit_exact_over_sample_rates(orc):
                 continue
             got = thb.calc_mel_fb_default(sr, n_fft)
             assert np.array_equal(got, orc.mel_fb_default(sr, n_fft)), (sr, n_fft)
+
+
+def test_integration_doc_declares_every_entry_point():
+    """INTEGRATION.md's Rust extern "C" blocks name every function of include/thesia_b200.h, and nothing else."""
+    import re
+    header = (ROOT / "include" / "thesia_b200.h").read_text()
+    declared = set(re.findall(r"\b(thb_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (thb_[a-z0-9_]+)", (ROOT / "INTEGRATION.md").read_text()))
+    assert declared == bound, declared ^ bound
