@@ -396,3 +396,38 @@ def test_spectrogram_tile_resampler_against_pillow(orc):
             worst = max(worst, err)
             assert err <= 1.5, (lx, ly, tx, ty, err)   # measured: <= 0.5 for one resampled axis, <= 1.05 for two
     assert worst > 0.0   # (the two are not the same code: a 0 here would mean the test compares something with itself)
+
+
+def test_oracle_building_blocks_against_numpy_and_scipy(orc):
+    """Independent restatements of the oracle's building blocks: the periodic Hann window (scipy), numpy's 'reflect' padding
+    incl. pads longer than the signal (utils.rs:111-137 cycles with period 2N - 2, which is what numpy does), pad-then-frame
+    framing, the dB rule and the waveform envelope."""
+    import scipy.signal
+    rng = np.random.default_rng(12)
+    for n in (4, 7, 320, 1764, 1920, 2048):
+        ref = scipy.signal.windows.hann(n, sym=False)
+        assert np.abs(orc.hann(n, False).astype(np.float64) - ref).max() <= 5e-7   # the reference evaluates it in f32 (windows.rs:68-83)
+        for n_fft in (n, 2 * n):
+            assert np.abs(orc.normalized_hann(n, n_fft).astype(np.float64) - ref / n_fft).max() <= 5e-7 / n_fft
+    for n, left, right in ((3, 3, 4), (2, 5, 5), (5, 1, 0), (10, 25, 31), (100, 99, 99), (100, 150, 7), (7, 0, 40)):
+        x = rng.standard_normal(n).astype(np.float32)
+        assert np.array_equal(orc.pad_reflect(x, left, right), np.pad(x, (left, right), mode="reflect")), (n, left, right)
+    for n, win, hop in ((1000, 64, 16), (1001, 64, 17), (50, 64, 16), (5, 8, 6), (4097, 2048, 512)):
+        x = rng.standard_normal(n).astype(np.float32)
+        padded = np.pad(x, win // 2, mode="reflect")
+        T = 1 + (padded.size - win) // hop
+        want = np.stack([padded[t * hop:t * hop + win] for t in range(T)])
+        assert orc.n_frames(n, win, hop) == T
+        assert np.array_equal(orc.stft_frames(x, win, hop), want), (n, win, hop)
+    v = np.abs(rng.standard_normal(1000)).astype(np.float32)
+    v[::97] = 0.0
+    with np.errstate(divide="ignore"):
+        want = (np.log10(v.astype(np.float64)) * 20.0)
+    got = orc.dB_from_amp_inplace(v.copy()).astype(np.float64)
+    assert np.array_equal(np.isneginf(got), np.isneginf(want)) and np.abs(np.where(np.isneginf(want), 0, got - np.where(np.isneginf(want), 0, want))).max() <= 2e-5
+    w = rng.standard_normal(5000).astype(np.float32)
+    b = orc.encode_waveform_tile(w, 1, 5, 0)
+    vals = np.frombuffer(b, np.float32, offset=24).reshape(-1, 3)
+    blk = w[:(w.size // 32) * 32].reshape(-1, 32)
+    assert np.array_equal(vals[:blk.shape[0], 0], blk.min(axis=1)) and np.array_equal(vals[:blk.shape[0], 1], blk.max(axis=1))
+    assert np.abs(vals[:blk.shape[0], 2] - blk.mean(axis=1, dtype=np.float64)).max() <= 1e-6
