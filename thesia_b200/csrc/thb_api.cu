@@ -190,6 +190,26 @@ bool is_device_ptr(const void *p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Stream-ordered scratch memory that goes back to the pool when the scope ends, whatever the exit path.
+struct Scratch {
+    thb_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(thb_ctx *c) : ctx(c) {}
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    template <typename T>
+    cudaError_t alloc(T **p, size_t bytes) {
+        void *q = nullptr;
+        const cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 1, ctx->stream);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = static_cast<T *>(q);
+        return e;
+    }
+    ~Scratch() {
+        for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
+    }
+};
+
 // ---- measurement hooks -------------------------------------------------------------------------
 struct ProfScope {
     thb_ctx *ctx;
@@ -1538,12 +1558,13 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
         max_h = std::max<unsigned>(max_h, static_cast<unsigned>(work[k].g.height));
         max_tmp_h = std::max(max_tmp_h, tmp_h);
     }
+    Scratch scratch(ctx);
     uint16_t *d_tmp = nullptr;
     uint8_t *d_out = nullptr;
     uchar4 *d_cm = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_tmp), sizeof(uint16_t) * tmp_total + 16, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), out_total + 16, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_cm), colormap_bytes, ctx->stream));
+    CK(scratch.alloc(&d_tmp, sizeof(uint16_t) * tmp_total + 16));
+    CK(scratch.alloc(&d_out, out_total + 16));
+    CK(scratch.alloc(&d_cm, colormap_bytes));
     CK(cudaMemcpyAsync(d_cm, colormap_rgba, colormap_bytes, cudaMemcpyHostToDevice, ctx->stream));
     size_t tmp_off = 0, out_off = 0;
     for (size_t k = 0; k < m; k++) {
@@ -1582,9 +1603,6 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
         CK(cudaMemcpyAsync(reqs[work[k].req].out + 40, d_out + out_off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         out_off += bytes;
     }
-    CK(cudaFreeAsync(d_tmp, ctx->stream));
-    CK(cudaFreeAsync(d_out, ctx->stream));
-    CK(cudaFreeAsync(d_cm, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -1683,16 +1701,17 @@ int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *
     if (rc) return rc;
     thb::TrackDesc *d_desc = nullptr;
     thb::TrackDesc *h = arena_push<thb::TrackDesc>(ctx, n, &d_desc);
-    std::vector<void *> staging(n, nullptr);
+    Scratch scratch(ctx);
     long long max_len = 0;
     for (size_t i = 0; i < n; i++) {
         const thb_track &t = channels[i];
         const size_t esz = t.pcm_format == THB_PCM_I16 ? 2 : 4;
         const void *d_pcm = t.pcm;
         if (t.len && !is_device_ptr(t.pcm)) {
-            CK(cudaMallocAsync(&staging[i], esz * t.len + 64, ctx->stream));
-            CK(cudaMemcpyAsync(staging[i], t.pcm, esz * t.len, cudaMemcpyHostToDevice, ctx->stream));
-            d_pcm = staging[i];
+            void *st = nullptr;
+            CK(scratch.alloc(&st, esz * t.len + 64));
+            CK(cudaMemcpyAsync(st, t.pcm, esz * t.len, cudaMemcpyHostToDevice, ctx->stream));
+            d_pcm = st;
         }
         memset(&h[i], 0, sizeof(thb::TrackDesc));
         h[i].pcm = static_cast<const float *>(d_pcm);
@@ -1705,9 +1724,9 @@ int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *
     const size_t chunks = static_cast<size_t>(thb::stats_chunks(max_len));
     double *d_part_ss = nullptr;
     float *d_part_mx = nullptr, *d_out = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_part_ss), sizeof(double) * n * chunks, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_part_mx), sizeof(float) * n * chunks, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_out), sizeof(float) * 2 * n, ctx->stream));
+    CK(scratch.alloc(&d_part_ss, sizeof(double) * n * chunks));
+    CK(scratch.alloc(&d_part_mx, sizeof(float) * n * chunks));
+    CK(scratch.alloc(&d_out, sizeof(float) * 2 * n));
     {
         ProfScope ps(ctx, "channel_stats", 2 * static_cast<int>((n + 65534) / 65535));
         cudaError_t e = thb::launch_channel_stats(d_desc, static_cast<int>(n), max_len, d_part_ss, d_part_mx, d_out, d_out + n, ctx->stream);
@@ -1715,11 +1734,6 @@ int thb_channel_stats(thb_ctx *ctx, const thb_track *channels, size_t n, float *
     }
     CK(cudaMemcpyAsync(sum_squares, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(abs_max, d_out + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    for (size_t i = 0; i < n; i++)
-        if (staging[i]) CK(cudaFreeAsync(staging[i], ctx->stream));
-    CK(cudaFreeAsync(d_part_ss, ctx->stream));
-    CK(cudaFreeAsync(d_part_mx, ctx->stream));
-    CK(cudaFreeAsync(d_out, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -1789,7 +1803,7 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
     if (rc) return rc;
     thb::GainDesc *d_desc = nullptr;
     thb::GainDesc *h = arena_push<thb::GainDesc>(ctx, n, &d_desc);
-    std::vector<void *> to_free;
+    Scratch scratch(ctx);
     struct Back { void *host; const void *dev; size_t bytes; };
     std::vector<Back> backs;
     long long max_len_active = 0, max_len_copy = 0;
@@ -1799,8 +1813,7 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
         const void *d_in = c.pcm;
         if (c.len && !is_device_ptr(c.pcm)) {
             void *p = nullptr;
-            CK(cudaMallocAsync(&p, esz * c.len + 64, ctx->stream));
-            to_free.push_back(p);
+            CK(scratch.alloc(&p, esz * c.len + 64));
             CK(cudaMemcpyAsync(p, c.pcm, esz * c.len, cudaMemcpyHostToDevice, ctx->stream));
             d_in = p;
         }
@@ -1808,8 +1821,7 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
             *dev = user;
             if (user && c.len && !is_device_ptr(user)) {
                 void *p = nullptr;
-                CK(cudaMallocAsync(&p, 4 * c.len + 64, ctx->stream));
-                to_free.push_back(p);
+                CK(scratch.alloc(&p, 4 * c.len + 64));
                 backs.push_back({user, p, 4 * static_cast<size_t>(c.len)});
                 *dev = static_cast<float *>(p);
             }
@@ -1834,9 +1846,9 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
     double *d_part = nullptr;
     thb::GainOut *d_outs = nullptr;
     unsigned *d_peak = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_part), sizeof(double) * n * chunks, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_outs), sizeof(thb::GainOut) * n, ctx->stream));
-    CK(cudaMallocAsync(reinterpret_cast<void **>(&d_peak), sizeof(unsigned) * n_groups, ctx->stream));
+    CK(scratch.alloc(&d_part, sizeof(double) * n * chunks));
+    CK(scratch.alloc(&d_outs, sizeof(thb::GainOut) * n));
+    CK(scratch.alloc(&d_peak, sizeof(unsigned) * n_groups));
     CK(cudaMemsetAsync(d_outs, 0, sizeof(thb::GainOut) * n, ctx->stream));
     CK(cudaMemsetAsync(d_peak, 0, sizeof(unsigned) * n_groups, ctx->stream));
     const int per_launch = 65535;
@@ -1862,10 +1874,6 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
     std::vector<unsigned> h_peak(n_groups);
     CK(cudaMemcpyAsync(h_outs.data(), d_outs, sizeof(thb::GainOut) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_peak.data(), d_peak, sizeof(unsigned) * n_groups, cudaMemcpyDeviceToHost, ctx->stream));
-    for (void *p : to_free) CK(cudaFreeAsync(p, ctx->stream));
-    CK(cudaFreeAsync(d_part, ctx->stream));
-    CK(cudaFreeAsync(d_outs, ctx->stream));
-    CK(cudaFreeAsync(d_peak, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     auto as_float = [](unsigned bits) { float f; memcpy(&f, &bits, 4); return f; };
     for (size_t k = 0; k < n; k++) {
