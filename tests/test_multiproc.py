@@ -16,6 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+import thesia_b200 as thb  # noqa: E402
 from thesia_b200 import sharding  # noqa: E402
 from thesia_b200.analysis import SpecSetting, FreqScale  # noqa: E402
 from thesia_b200.synth import LOUD, ZERO_GAP, synth_pcm  # noqa: E402
@@ -126,3 +127,39 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
             seen[(i, ch)][fb:fb + piece.shape[0]] = True
     assert all(v.all() for v in seen.values())
     assert want[1] == 0.0  # the LOUD track drives max_dB into the min(max, 0) clamp
+
+
+def test_random_plans_cover_every_frame_and_carry_every_sample(orc):
+    """300 random jobs (channel counts, lengths, settings, world sizes 1..8): every frame is computed exactly once, a unit's
+    PCM slice holds every sample its frames read -- checked against the oracle's own reflect index, sample by sample at the
+    unit's first and last frame -- and the load is balanced to within one unit.  Also the BASELINE shapes: C3 deals 16
+    channels to each of 8 ranks, C2's single 1-hour file is cut into 8 frame ranges."""
+    rng = np.random.default_rng(77)
+    for _ in range(300):
+        world = int(rng.integers(1, 9))
+        sr = int(rng.choice([8000, 16000, 44100, 48000, 96000]))
+        s = thb.SpecSetting(float(rng.choice([10.0, 40.0, 2048 / 48.0, 170.0])), int(rng.choice([1, 2, 4, 8, 16])), 1, thb.FreqScale.Mel)
+        hop, win, _ = s.calc_framing_params(sr)
+        chans = [(i, c, sr, int(rng.integers(2, 3_000_000))) for i in range(int(rng.integers(1, 7))) for c in range(int(rng.integers(1, 3)))]
+        ranks = sharding.plan(chans, lambda _sr: s.calc_framing_params(_sr), world)
+        assert len(ranks) == world
+        for (i, ch, _, n) in chans:
+            units = sorted((u for r in ranks for u in r if (u.id, u.ch) == (i, ch)), key=lambda u: u.frame_begin)
+            pos = 0
+            for u in units:
+                assert u.frame_begin == pos and u.full_len == n and 0 <= u.pcm_lo <= u.pcm_hi <= n
+                pos += u.frame_count
+                for f in (u.frame_begin, u.frame_begin + u.frame_count - 1) if u.frame_count else ():
+                    taps = (f * hop - win // 2, f * hop - win // 2 + win - 1)
+                    idx = [orc.reflect_index(t, n) for t in taps] + [orc.reflect_index(t, n) for t in range(taps[0], min(taps[0] + 3, taps[1] + 1))]
+                    assert all(u.pcm_lo <= k < u.pcm_hi for k in idx), (n, win, hop, f, idx, u)
+            assert pos == sharding.n_frames(n, win, hop) == thb.n_frames(n, win, hop)
+        loads = [sum(u.cost for u in r) for r in ranks]
+        assert max(loads) - min(loads) <= max([u.cost for r in ranks for u in r] + [0])
+    c3 = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    ranks = sharding.plan([(t, c, 48000, 28_800_000) for t in range(64) for c in range(2)], lambda sr: c3.calc_framing_params(sr), 8)
+    assert [len(r) for r in ranks] == [16] * 8 and all(u.frame_count == 56251 for r in ranks for u in r)
+    c2 = thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128)
+    ranks = sharding.plan([(0, 0, 48000, 172_800_000)], lambda sr: c2.calc_framing_params(sr), 8)
+    assert [len(r) for r in ranks] == [1] * 8 and sum(u.frame_count for r in ranks for u in r) == 675001
+    assert all(u.pcm_hi - u.pcm_lo <= 172_800_000 // 8 + 2 * 2048 for r in ranks for u in r)
