@@ -12,10 +12,12 @@
  *  - every function returns 0 (THB_OK) or a negative thb_status; thb_last_error() gives text.
  *    The Rust shim maps non-zero to panic!/anyhow::Error (the reference unwrap()s here:
  *    stft.rs:47, release profile panic = "abort").
- *  - thb_spec_batch / thb_update_spec_imgs / thb_minmax_global / thb_spec_to_img assume one
- *    caller at a time per ctx (the reference serialises them on its "write-lock-worker" thread,
- *    interface.rs:12-56).  thb_waveform_tile / thb_waveform_level are thread-safe (the reference
- *    serves tiles from concurrent IPC threads, lib.rs:343-367).
+ *  - Every entry point is thread-safe.  The analysis calls (thb_spec_batch, thb_update_spec_imgs,
+ *    thb_minmax_global, thb_spec_to_img, release, ...) take the context exclusively, as the reference
+ *    serialises them on its "write-lock-worker" thread (interface.rs:12-56).  The tile readers
+ *    (thb_waveform_tile, thb_spectrogram_tile, thb_spectrogram_tile_batch) take it SHARED and each call
+ *    runs on its own stream: concurrent tile calls overlap on the device, as the reference serves tiles
+ *    from concurrent IPC threads under read locks (lib.rs:343-389).
  *  - `pcm` pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).
  *    Host memory from thb_host_alloc() is pinned and copies from it are asynchronous.
  *  - There is no CPU fallback: without a CUDA device thb_ctx_create() fails with THB_ERR_CUDA.
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define THB_ABI_VERSION 3
+#define THB_ABI_VERSION 4
 
 typedef enum thb_status {
     THB_OK = 0,
@@ -186,6 +188,17 @@ int thb_spec_to_img(thb_ctx *ctx, uint64_t id, uint32_t ch, uint64_t i0, uint64_
  * neither the dB range nor max_sr moved (mod.rs:194-203); NULL = every track. */
 int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length, uint32_t max_sr,
                          const uint64_t *only_ids, size_t n_only, float *min_dB, float *max_dB);
+/* With min_dB == max_dB == NULL thb_update_spec_imgs only QUEUES its work (reduce, all-reduce, quantise) on the ctx
+ * stream and returns: a host that re-analyses in a loop keeps the device busy back to back.  thb_range_get waits for
+ * the stream and returns the (min_dB, max_dB) of the last update.
+ * MULTI-GPU CONTRACT: thb_update_spec_imgs and thb_minmax_global issue exactly ONE collective each, whatever
+ * `only_ids` holds; every rank of the communicator must make the same sequence of these two calls.  When only the
+ * quantise step is needed for an already reduced range (the reference's `ids_need_update` branch with an unchanged
+ * range, mod.rs:194-203, or set_colormap_length, mod.rs:123-131), thb_update_spec_imgs_range does it with the
+ * caller's (min_dB, max_dB) and NO collective, so ranks with different track lists may call it independently. */
+int thb_range_get(thb_ctx *ctx, float *min_dB, float *max_dB);
+int thb_update_spec_imgs_range(thb_ctx *ctx, float min_dB, float max_dB, uint32_t colormap_length, uint32_t max_sr,
+                               const uint64_t *only_ids, size_t n_only);
 /* TrackManager::get_spectrogram (mod.rs:133-135): copy image (H, W = T) to the host */
 int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t cap,
                  uint64_t *height, uint64_t *width);
@@ -234,6 +247,13 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
  * u32 0, then per bin f32 min, f32 max, f32 mean (little endian).  `out` is HOST memory. */
 int thb_waveform_tile(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level,
                       uint32_t tile_index, uint8_t *out, size_t cap, size_t *written);
+/* Host PCM handed to thb_waveform_tile stays on the device under the key (pcm pointer, len, revision) -- the key of the
+ * reference's own tile cache (render_tiles.rs:124-169) -- filled granule by granule with exactly the samples tile calls
+ * touch, so a later tile of the same channel does not cross PCIe again.  A changed channel must come with a new
+ * revision (as in the reference) or a new pointer.  Bounded by the environment variable THB_PCM_CACHE_MB (default
+ * 4096; 0 turns the cache off), least recently used first. */
+int thb_pcm_cache_stats(thb_ctx *ctx, uint64_t *entries, uint64_t *bytes, uint64_t *hits, uint64_t *misses);
+int thb_pcm_cache_clear(thb_ctx *ctx);
 /* every tile of one level, concatenated in tile order (what a full redraw at that zoom asks for) */
 int thb_waveform_level(thb_ctx *ctx, const float *pcm, uint64_t len, uint64_t revision, uint32_t level,
                        uint8_t *out, size_t cap, size_t *written);

@@ -109,6 +109,8 @@ SIGNATURES = {
     "thb_minmax_global": (_i, [_vp, _f32, _P(_f32), _P(_f32)]),
     "thb_spec_to_img": (_i, [_vp, _u64, _u32, _u64, _u64, _f32, _f32, _u32, _vp, _u64]),
     "thb_update_spec_imgs": (_i, [_vp, _f32, _u32, _u32, _P(_u64), C.c_size_t, _P(_f32), _P(_f32)]),
+    "thb_range_get": (_i, [_vp, _P(_f32), _P(_f32)]),
+    "thb_update_spec_imgs_range": (_i, [_vp, _f32, _f32, _u32, _u32, _P(_u64), C.c_size_t]),
     "thb_img_read": (_i, [_vp, _u64, _u32, _vp, _u64, _P(_u64), _P(_u64)]),
     "thb_img_read_batch": (_i, [_vp, C.c_size_t, _P(_u64), _P(_u32), _P(_vp), _P(_u64)]),
     "thb_img_put": (_i, [_vp, _u64, _u32, _vp, _u64, _u64]),
@@ -118,6 +120,8 @@ SIGNATURES = {
                                   _P(C.c_size_t)]),
     "thb_spectrogram_tile_batch": (_i, [_vp, _vp, C.c_size_t, _u64, _P(SpecTileReq), C.c_size_t]),
     "thb_waveform_tile": (_i, [_vp, _vp, _u64, _u64, _u32, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),
+    "thb_pcm_cache_stats": (_i, [_vp, _P(_u64), _P(_u64), _P(_u64), _P(_u64)]),
+    "thb_pcm_cache_clear": (_i, [_vp]),
     "thb_waveform_level": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, C.c_size_t, _P(C.c_size_t)]),
     "thb_waveform_level_batch": (_i, [_vp, _P(Track), C.c_size_t, _u64, _u32, _P(_vp), _P(C.c_size_t),
                                       _P(C.c_size_t), _P(_vp)]),
@@ -155,7 +159,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.thb_abi_version() != 3:
+        if l.thb_abi_version() != 4:
             raise RuntimeError("libthesia_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -305,18 +305,41 @@ class Context:
                                     out.ctypes.data, out.size), self._h)
         return out
 
+    @staticmethod
+    def _ids(only_ids):
+        if only_ids is None:
+            return None, 0
+        lst = list(only_ids)
+        return (C.c_uint64 * max(len(lst), 1))(*lst), len(lst)
+
     def update_spec_imgs(self, dB_range: float, colormap_length: int, max_sr: int = 0,
-                         only_ids: Optional[Iterable[int]] = None) -> Tuple[float, float]:
+                         only_ids: Optional[Iterable[int]] = None, wait: bool = True) -> Optional[Tuple[float, float]]:
+        """thb_update_spec_imgs (one collective when a communicator is attached).  wait=False only queues the
+        work on the stream (no host round trip): read the range later with range_get()."""
         a, b = C.c_float(), C.c_float()
-        ids = None
-        n_ids = 0
-        if only_ids is not None:
-            lst = list(only_ids)
-            n_ids = len(lst)
-            ids = (C.c_uint64 * max(n_ids, 1))(*lst)
-        check(lib().thb_update_spec_imgs(self._h, dB_range, colormap_length, max_sr, ids, n_ids, C.byref(a),
-                                         C.byref(b)), self._h)
+        ids, n_ids = self._ids(only_ids)
+        check(lib().thb_update_spec_imgs(self._h, dB_range, colormap_length, max_sr, ids, n_ids,
+                                         C.byref(a) if wait else None, C.byref(b) if wait else None), self._h)
+        return (a.value, b.value) if wait else None
+
+    def update_spec_imgs_range(self, dB_range: Tuple[float, float], colormap_length: int, max_sr: int = 0,
+                               only_ids: Optional[Iterable[int]] = None) -> None:
+        """thb_update_spec_imgs_range: the quantise step alone with an already reduced (min_dB, max_dB); no collective."""
+        ids, n_ids = self._ids(only_ids)
+        check(lib().thb_update_spec_imgs_range(self._h, dB_range[0], dB_range[1], colormap_length, max_sr, ids, n_ids), self._h)
+
+    def range_get(self) -> Tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        check(lib().thb_range_get(self._h, C.byref(a), C.byref(b)), self._h)
         return a.value, b.value
+
+    def pcm_cache_stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        check(lib().thb_pcm_cache_stats(self._h, *[C.byref(x) for x in v]), self._h)
+        return dict(zip(("entries", "bytes", "hits", "misses"), (x.value for x in v)))
+
+    def pcm_cache_clear(self) -> None:
+        check(lib().thb_pcm_cache_clear(self._h), self._h)
 
     def img_read(self, id: int, ch: int) -> np.ndarray:
         h, w = C.c_uint64(), C.c_uint64()
@@ -655,6 +678,9 @@ class TrackManager:
 
     # -- mod.rs:168-230
     def _update_spec_imgs(self, tracklist: TrackList, force_update_all: bool) -> set:
+        # The ONE collective of an update (when a communicator is attached): every rank makes it, whatever its own
+        # track list needs afterwards; the quantise step below then uses the reduced range and no collective, so
+        # ranks whose `ids_need_update` differ cannot fall out of step.
         mn, mx = self.ctx.minmax_global(self.dB_range)
         need_update_all = force_update_all
         if self.max_dB != mx:
@@ -676,7 +702,7 @@ class TrackManager:
         if ids_need_update:
             if need_update_all:
                 self._img_keys.clear()
-            self.ctx.update_spec_imgs(self.dB_range, self.colormap_length, self.max_sr,
-                                      None if need_update_all else sorted(ids_need_update))
+            self.ctx.update_spec_imgs_range((self.min_dB, self.max_dB), self.colormap_length, self.max_sr,
+                                            None if need_update_all else sorted(ids_need_update))
             self._img_keys.update(k for k in self._spec_keys if k[0] in ids_need_update)
         return ids_need_update

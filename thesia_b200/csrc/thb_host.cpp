@@ -166,8 +166,9 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
     }
 }
 
-MelItems mel_items(const MelBank &b) {
+MelItems mel_items(const MelBank &b, uint32_t t_multiple) {
     MelItems it;
+    const uint32_t tm = t_multiple < 2 ? 2 : t_multiple;  // the walk takes two steps per float4 of weights
     it.n_mel = b.n_mel;
     const uint32_t F = b.n_freq, M = b.n_mel;
     // ---- per bin: segment id and its two weights (rise of band seg, fall of band seg - 1) ----
@@ -251,7 +252,7 @@ MelItems mel_items(const MelBank &b) {
         uint32_t T = maxL;
         bool matched = false;
         for (uint32_t e = 0; e <= kSlack && !matched; e++) {
-            T = (maxL + e + 1) & ~1u;  // even: the walk takes two steps per float4 of weights
+            T = (maxL + e + tm - 1) / tm * tm;
             std::fill(owner, owner + 32, -1);
             bool seen[32];
             std::function<bool(int)> aug = [&](int i) -> bool {
@@ -281,7 +282,7 @@ MelItems mel_items(const MelBank &b) {
             for (int sl = 0; sl < 32; sl++)
                 if (owner[sl] >= 0) slot_sel[owner[sl]] = sl;
         } else {  // give up on conflict freedom for this group: no lead, halves in order
-            T = (maxL + 1) & ~1u;
+            T = (maxL + tm - 1) / tm * tm;
             for (uint32_t i = 0; i < n; i++) slot_sel[i] = -1;
         }
         // Lane inside the half warp: the lane whose index equals the segment id mod 16 when it is free, so that
@@ -362,12 +363,27 @@ MelItems mel_items(const MelBank &b) {
     for (uint32_t m = 0; m < M; m++)
         for (uint32_t i = it.piece_ptr[m]; i < it.piece_ptr[m + 1]; i++)
             it.goff[(static_cast<size_t>(it.gbase[m / 32]) + (i - it.piece_ptr[m])) * 32 + m % 32] = static_cast<uint16_t>(it.piece_ids[i]);
+    // rows of four byte offsets (one 16-byte load serves four list entries)
+    it.gk4.assign(n_rounds, 0);
+    it.gbase4.assign(n_rounds, 0);
+    uint32_t rows4 = 0;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        it.gk4[r] = (it.gk[r] + 3) / 4;
+        it.gbase4[r] = rows4;
+        rows4 += it.gk4[r];
+    }
+    it.goff4.assign(static_cast<size_t>(rows4) * 128, it.zero_slot * 8u);
+    for (uint32_t m = 0; m < M; m++)
+        for (uint32_t i = it.piece_ptr[m]; i < it.piece_ptr[m + 1]; i++) {
+            const uint32_t j = i - it.piece_ptr[m];
+            it.goff4[(static_cast<size_t>(it.gbase4[m / 32]) + j / 4) * 128 + (m % 32) * 4 + j % 4] = it.piece_ids[i] * 8u;
+        }
     it.valid = true;
     return it;
 }
 
 std::vector<uint32_t> MelItems::blob() const {
-    std::vector<uint32_t> o(8, 0);
+    std::vector<uint32_t> o(12, 0);
     auto align4 = [&]() {
         while (o.size() & 3) o.push_back(0);
     };
@@ -393,6 +409,15 @@ std::vector<uint32_t> MelItems::blob() const {
     o[5] = static_cast<uint32_t>(o.size());
     for (size_t i = 0; i + 1 < goff.size() + 1; i += 2)
         o.push_back(static_cast<uint32_t>(goff[i]) | (static_cast<uint32_t>(i + 1 < goff.size() ? goff[i + 1] : 0) << 16));
+    align4();
+    o[8] = static_cast<uint32_t>(o.size());  // {rows of four, first row of four} per round
+    for (size_t r = 0; r < gk4.size(); r++) {
+        o.push_back(gk4[r]);
+        o.push_back(gbase4[r]);
+    }
+    align4();
+    o[9] = static_cast<uint32_t>(o.size());
+    o.insert(o.end(), goff4.begin(), goff4.end());
     align4();
     o[7] = static_cast<uint32_t>(o.size());
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(w.data());

@@ -63,6 +63,10 @@ struct MelItems {
     std::vector<uint32_t> piece_ids;  // slots
     std::vector<uint32_t> gk, gbase;  // [ceil(n_mel / 32)]
     std::vector<uint16_t> goff;       // [sum(gk) * 32]
+    // the same gather lists for the n_fft == 2048 kernels: per round ceil(gk / 4) rows of 32 lanes x 4 BYTE offsets
+    // (slot * 8: float2 slots of the frame-pair kernel; the scalar kernel halves them), padded with the zero slot
+    std::vector<uint32_t> gk4, gbase4;  // [rounds]: rows of 4, first row
+    std::vector<uint32_t> goff4;        // [sum(gk4) * 32 * 4]
     uint32_t zero_slot = 0;
     size_t w_index(uint32_t g, uint32_t t, uint32_t lane) const {
         return woff[g] + static_cast<size_t>(t / 2) * 128 + 4 * static_cast<size_t>(lane) + 2 * (t & 1);
@@ -73,7 +77,10 @@ struct MelItems {
     // off_goff, zero_slot, off_w} then the arrays (see blob())
     std::vector<uint32_t> blob() const;
 };
-MelItems mel_items(const MelBank &b);
+// t_multiple: every group's step count is a multiple of it (the walks take two steps per float4 of weights; padding
+// steps carry zero weights and add +0).  4 would spare the n_fft == 2048 walk its two-step tail but costs the default
+// banks (10 - 11 groups of 2 - 12 steps) 12 - 14 extra steps per frame pair: measured on the host, not adopted.
+MelItems mel_items(const MelBank &b, uint32_t t_multiple = 2);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

@@ -59,6 +59,8 @@ struct MelView {
     const int32_t *start;  // [n_groups * 32]
     const uint2 *rounds;   // {K, first row} per 32 bands
     const uint16_t *goff;  // rows of 32 slot ids
+    const uint2 *rounds4;  // {rows of four, first row of four} per 32 bands
+    const uint4 *goff4;    // rows of 32 lanes x 4 byte offsets (float2 slots)
     __device__ __forceinline__ explicit MelView(const uint32_t *b) : base(b) {
         n_groups = static_cast<int>(b[0]);
         n_mel = static_cast<int>(b[1]);
@@ -66,6 +68,8 @@ struct MelView {
         start = reinterpret_cast<const int32_t *>(b + b[3]);
         rounds = reinterpret_cast<const uint2 *>(b + b[4]);
         goff = reinterpret_cast<const uint16_t *>(b + b[5]);
+        rounds4 = reinterpret_cast<const uint2 *>(b + b[8]);
+        goff4 = reinterpret_cast<const uint4 *>(b + b[9]);
     }
 };
 
@@ -130,6 +134,72 @@ __device__ __forceinline__ V mel_band(const MelView &mv, const V *part, int r, i
     const uint16_t *row = mv.goff + rd.y * 32 + lane;
     V acc = O::zero();
     for (uint32_t j = 0; j < rd.x; j++) acc = O::add(acc, part[row[32 * j]]);
+    return acc;
+}
+
+// ---- the same walk and gather with leaner bookkeeping: pointers advance instead of being recomputed, four steps per
+// trip plus one optional two-step tail, four gather entries per 16-byte load of byte offsets.  The operations and their
+// order are those of mel_walk / mel_band (padding entries add the always-zero slot), so the results are the same bit
+// for bit.
+template <typename V>
+__device__ __forceinline__ void mel_walk4(const MelView &mv, const V *mag, V *part, int lane) {
+    using O = MelOps<V>;
+    const int n_slots = mv.n_groups * 32;
+    const float4 *wlane = reinterpret_cast<const float4 *>(mv.base) + lane;
+    V *prow = part + lane;
+#pragma unroll 1
+    for (int g = 0; g < mv.n_groups; g++) {
+        const uint2 gh = mv.grp[g];
+        const float4 *wq = wlane + (gh.y >> 2);
+        const V *mq = mag + mv.start[g * 32 + lane];
+        const int T4 = static_cast<int>(gh.x) >> 2;
+        V rise = O::zero(), fall = O::zero();
+#pragma unroll 1
+        for (int t = 0; t < T4; t++) {
+            const float4 w0 = wq[0], w1 = wq[32];
+            const V m0 = mq[0], m1 = mq[1], m2 = mq[2], m3 = mq[3];
+            wq += 64;
+            mq += 4;
+            rise = O::fma(m0, w0.x, rise);
+            fall = O::fma(m0, w0.y, fall);
+            rise = O::fma(m1, w0.z, rise);
+            fall = O::fma(m1, w0.w, fall);
+            rise = O::fma(m2, w1.x, rise);
+            fall = O::fma(m2, w1.y, fall);
+            rise = O::fma(m3, w1.z, rise);
+            fall = O::fma(m3, w1.w, fall);
+        }
+        if (gh.x & 2u) {  // step counts are even
+            const float4 w0 = wq[0];
+            const V m0 = mq[0], m1 = mq[1];
+            rise = O::fma(m0, w0.x, rise);
+            fall = O::fma(m0, w0.y, fall);
+            rise = O::fma(m1, w0.z, rise);
+            fall = O::fma(m1, w0.w, fall);
+        }
+        prow[0] = rise;
+        prow[n_slots] = fall;
+        prow += 32;
+    }
+    if (lane == 0) part[2 * n_slots] = O::zero();  // the padding slot of the gather (the tile is reused by the transposes)
+}
+
+template <typename V>
+__device__ __forceinline__ V mel_band4(const MelView &mv, const V *part, int r, int lane) {
+    using O = MelOps<V>;
+    constexpr int kShift = sizeof(V) == 8 ? 0 : 1;  // the table holds float2 byte offsets
+    const uint2 rd = mv.rounds4[r];
+    const uint4 *row = mv.goff4 + rd.y * 32 + lane;
+    const unsigned char *pb = reinterpret_cast<const unsigned char *>(part);
+    V acc = O::zero();
+#pragma unroll 1
+    for (uint32_t j = 0; j < rd.x; j++) {
+        const uint4 o = row[32 * j];
+        acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.x >> kShift)));
+        acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.y >> kShift)));
+        acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.z >> kShift)));
+        acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.w >> kShift)));
+    }
     return acc;
 }
 

@@ -54,10 +54,18 @@ __device__ __forceinline__ PairSmem carve(unsigned char *raw, int tile_f2) {
 // HS > 0: hop == 64 HS, so frame B's row n1 is frame A's row n1 + HS and 32 + HS loads serve both frames.
 // HS < 0: frames may start on any 4-byte boundary (odd hop such as the 44.1 kHz default's 441, odd channel start):
 // the same samples through 4-byte loads, everything after the loads is identical.
-template <bool MEL, int NW, bool I16, int HS>
+// L2 prefetch of a byte range of global memory (one instruction, no register destination, no completion to wait for)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *addr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+}
+
+// flags: bit 0 = while a tile is computed, pull the PCM of this CTA's NEXT tile into L2 (the loads of a frame pair
+// then hit L2 instead of HBM: the pair's 40 loads sit at the head of a long dependent chain)
+// M4: the lean mel walk / gather (mel_walk4 / mel_band4; same results bit for bit)
+template <bool MEL, int NW, bool I16, int HS, bool M4>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
-                                                                        long long n_items, RescueList rescue) {
+                                                                        long long n_items, RescueList rescue, int flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kTile = 8 * NW;
 
@@ -98,6 +106,30 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
         const long long f_end = min(f_begin + kTile, d.n_frames);
         float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
         bool flagged = false;
+        if ((flags & 1) && lane == 0) {
+            const long long nxt = item + gridDim.x;
+            if (nxt < n_items) {
+                const long long t2 = nxt / tiles_per_track, i2 = nxt - t2 * tiles_per_track;
+                const TrackDesc *d2 = tracks + t2;
+                const long long nf2 = __ldg(&d2->n_frames), fb2 = i2 * kTile;
+                if (fb2 < nf2) {
+                    constexpr int esz = I16 ? 2 : 4;
+                    const long long fe2 = min(fb2 + kTile, nf2);
+                    // samples [s0, s1) of the slice that the tile's frames read; this warp takes its 1 / NW of them
+                    long long s0 = (__ldg(&d2->frame_begin) + fb2) * p.hop - half - p.pad_left - __ldg(&d2->pcm_offset);
+                    long long s1 = s0 + (fe2 - fb2 - 1) * p.hop + 2048;
+                    s0 = max(s0, 0ll);
+                    s1 = min(s1, __ldg(&d2->slice_len));
+                    const long long per = ((s1 - s0 + NW - 1) / NW + 31) & ~31ll;
+                    const long long a = s0 + per * warp, b = min(a + per, s1);
+                    if (b > a) {
+                        const unsigned long long base = __ldg(reinterpret_cast<const unsigned long long *>(&d2->pcm));
+                        const unsigned long long lo = (base + a * esz) & ~15ull, hi = (base + b * esz) & ~15ull;  // never past the slice
+                        if (hi > lo) prefetch_l2_bulk(reinterpret_cast<const void *>(lo), static_cast<unsigned>(hi - lo));
+                    }
+                }
+            }
+        }
 
         for (long long fa = f_begin + 2 * warp; fa < f_end; fa += 2 * NW) {
             const long long fb = fa + 1;
@@ -260,11 +292,12 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                mel_walk<float2>(mv, mag, part, lane);
+                if constexpr (M4) mel_walk4<float2>(mv, mag, part, lane);
+                else mel_walk<float2>(mv, mag, part, lane);
                 __syncwarp();
                 for (int r = 0; 32 * r < mv.n_mel; r++) {
                     const int m = 32 * r + lane;
-                    const f2 acc = mel_band<float2>(mv, part, r, lane);
+                    const f2 acc = M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane);
                     if (m >= mv.n_mel) continue;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
@@ -305,16 +338,19 @@ int pair_warps() {
     return (w == 8 || w == 10 || w == 12) ? w : 12;
 }
 
-template <bool MEL, int NW, bool I16, int HS = 0>
+template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true>
 cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
                       cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
-    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS>;
+    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS, M4>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
     const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
-    kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks, n_items, rescue);
+    // THB_PAIR_PREFETCH=0 turns the next-tile L2 prefetch off (A/B runs)
+    const char *pe = getenv("THB_PAIR_PREFETCH");
+    const int flags = (pe && atoi(pe) == 0) ? 0 : 1;
+    kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks, n_items, rescue, flags);
     return cudaGetLastError();
 }
 
@@ -349,6 +385,9 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
     const char *se = getenv("THB_PAIR_SHARE");
     const bool share = !(se && atoi(se) == 0) && nw == 12;
     if (share && plan.hop == 512) {
+        // THB_MEL4=0: the mel walk / gather with remainder code and 16-bit slot ids (A/B runs; same results)
+        const char *m4 = getenv("THB_MEL4");
+        if (plan.n_mel && m4 && atoi(m4) == 0) return launch_nw<true, 12, false, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         if (plan.n_mel) return launch_nw<true, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }

@@ -323,6 +323,8 @@ private:
     }
     // mod.rs:168-230
     std::set<uint64_t> update_spec_imgs(const TrackList &tracklist, bool force_update_all) {
+        // the ONE collective of an update (when a communicator is attached): every rank makes it, whatever its own track
+        // list needs afterwards; the quantise step below uses the reduced range and no collective
         float mn = 0.0f, mx = 0.0f;
         check(thb_minmax_global(ctx_.get(), dB_range, &mn, &mx), ctx_.get());
         bool need_update_all = force_update_all;
@@ -348,8 +350,8 @@ private:
         if (!ids_need_update.empty()) {
             if (need_update_all) spec_imgs_.clear();
             const std::vector<uint64_t> only(ids_need_update.begin(), ids_need_update.end());
-            check(thb_update_spec_imgs(ctx_.get(), dB_range, colormap_length, max_sr, need_update_all ? nullptr : only.data(),
-                                       need_update_all ? 0 : only.size(), nullptr, nullptr),
+            check(thb_update_spec_imgs_range(ctx_.get(), min_dB, max_dB, colormap_length, max_sr, need_update_all ? nullptr : only.data(),
+                                             need_update_all ? 0 : only.size()),
                   ctx_.get());
             for (const IdCh &k : specs_)
                 if (ids_need_update.count(k.first)) spec_imgs_.insert(k);

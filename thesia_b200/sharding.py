@@ -1,9 +1,10 @@
 """Work split of the analysis path across the GPUs of one box.
 
 Units are (id, ch) channels -- the reference already treats them independently (mod.rs:152-163).
-Channels are dealt greedily by sample count; a file longer than a rank's fair share is split by
-FRAME RANGE: each part gets the PCM slice its frames touch (a (win - hop)-sample halo plus the
-reflected samples at true file ends), so no halo exchange happens on the device.  The only
+The frames of all channels form one line, cut into one contiguous span per rank; a file that
+straddles a cut (C2: one 1-hour file on N GPUs) is split there by FRAME RANGE: each part gets the
+PCM slice its frames touch (a (win - hop)-sample halo plus the reflected samples at true file
+ends), so no halo exchange happens on the device, and a rank never holds two parts of one file.  The only
 collective of the path is the 2-float max all-reduce inside thb_minmax_global.
 """
 from __future__ import annotations
@@ -65,30 +66,62 @@ def split_frames(id: int, ch: int, sr: int, full_len: int, win: int, hop: int, p
     return out
 
 
+def frame_weight(n_fft: int) -> int:
+    """Relative cost of one frame (the kernels are FFT-bound: ~ n_fft log2 n_fft)."""
+    return max(1, n_fft * max(1, n_fft.bit_length() - 1))
+
+
 def plan(channels: Sequence[Tuple[int, int, int, int]], framing, world_size: int) -> List[List[Unit]]:
     """channels: (id, ch, sr, n_samples); framing(sr) -> (hop, win, n_fft).
-    Returns, per rank, the units it computes.  Deterministic, identical on every rank."""
-    units: List[Unit] = []
-    total_frames = 0
+    Returns, per rank, the units it computes.  Deterministic, identical on every rank.
+
+    The frames of all channels, in the order given, form one line weighted by their cost; rank r takes the
+    r-th of `world_size` equal spans of it.  A channel that straddles a span boundary is split there by frame
+    range (at an even frame, so that the frame-pair kernel keeps whole pairs).  Consequences the device store
+    relies on (it is keyed by (id, ch)): a rank holds AT MOST ONE unit of any channel, and that unit is one
+    contiguous frame range -- two parts of a file can never meet on one rank."""
     per = []
+    total = 0
     for (i, ch, sr, n) in channels:
-        hop, win, _ = framing(sr)
+        hop, win, n_fft = framing(sr)
         t = n_frames(n, win, hop)
-        per.append((i, ch, sr, n, hop, win, t))
-        total_frames += t
-    fair = max(1, -(-total_frames // world_size))
-    for (i, ch, sr, n, hop, win, t) in per:
-        # split only files that exceed one rank's fair share (C2: one 1-hour file on N GPUs)
-        parts = -(-t // fair) if t > fair else 1
-        units.extend(split_frames(i, ch, sr, n, win, hop, parts))
-    # longest-processing-time-first onto the least loaded rank
-    order = sorted(range(len(units)), key=lambda k: (-units[k].cost, units[k].id, units[k].ch, units[k].frame_begin))
-    load = [0] * world_size
+        w = frame_weight(int(n_fft))
+        per.append((i, ch, sr, n, hop, win, t, w))
+        total += t * w
     ranks: List[List[Unit]] = [[] for _ in range(world_size)]
-    for k in order:
-        r = min(range(world_size), key=lambda q: (load[q], q))
-        ranks[r].append(units[k])
-        load[r] += units[k].cost
-    for r in ranks:
-        r.sort(key=lambda u: (u.id, u.ch, u.frame_begin))
+    if total == 0:
+        return ranks
+    # cut points of the weighted line: rank r owns [r * total / W, (r + 1) * total / W)
+    cuts = [(r * total) // world_size for r in range(world_size + 1)]
+    pos = 0
+    r = 0
+    for (i, ch, sr, n, hop, win, t, w) in per:
+        begin = 0
+        while begin < t:
+            while r + 1 < world_size and pos >= cuts[r + 1]:
+                r += 1
+            # frames of this channel that still fit the span of rank r
+            room = cuts[r + 1] - pos if r + 1 < world_size else (t - begin) * w
+            cnt = min(t - begin, max(1, -(-room // w)))
+            if begin + cnt < t:
+                # not the channel's tail: keep the cut on an even frame
+                cnt = cnt + 1 if (begin + cnt) & 1 else cnt
+                cnt = min(cnt, t - begin)
+            lo, hi = needed_samples(begin, cnt, win, hop, n)
+            ranks[r].append(Unit(i, ch, sr, n, begin, cnt, lo, hi))
+            begin += cnt
+            pos += cnt * w
+    # one contiguous unit per (id, ch) and rank: merge neighbours that the even-frame rounding left on one rank
+    for q in range(world_size):
+        merged: List[Unit] = []
+        for u in ranks[q]:
+            m = merged[-1] if merged else None
+            if m and (m.id, m.ch) == (u.id, u.ch) and m.frame_begin + m.frame_count == u.frame_begin:
+                hop, win, _ = framing(u.sr)
+                cnt = m.frame_count + u.frame_count
+                lo, hi = needed_samples(m.frame_begin, cnt, win, hop, u.full_len)
+                merged[-1] = Unit(u.id, u.ch, u.sr, u.full_len, m.frame_begin, cnt, lo, hi)
+            else:
+                merged.append(u)
+        ranks[q] = merged
     return ranks
