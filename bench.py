@@ -231,6 +231,243 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+
+# -------------------------------------------------------------------------------------------------
+def strong_scaling(args, torch, dist, thb, ctx, pcm_weak, n, rank, world, local_rank, dev, stream) -> dict:
+    """The fixed jobs dealt over the ranks by thesia_b200.sharding.plan:
+       c3: the 128-channel batch of configs[2] by channel (units = (id, ch), mod.rs:152-163);
+       c2: the single 1-hour file of configs[1] by FRAME RANGE (stft.rs:100-113 is the reference's frames-parallel leg),
+           every rank holding only the PCM slice its frames touch.
+    Timed like `value` (queued steps, CUDA events on the launching stream, max over ranks).  In the same run rank 0
+    also runs each whole job alone on its GPU (no communicator): `efficiency` = that time / (N x sharded time), and --
+    for N > 1 -- every rank checks its shard against that one-GPU result bit for bit (dB rows, u16 images, range)."""
+    from thesia_b200 import sharding
+
+    steps, warm = max(args.steps, 5), max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def gather(x: float):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [x]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def timed(c, tracks, setting, max_sr, k, w):
+        for _ in range(w):
+            c.spec_batch(tracks, setting)
+            c.update_spec_imgs(DB_RANGE, CMAP_LEN, max_sr, wait=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            c.spec_batch(tracks, setting)
+            c.update_spec_imgs(DB_RANGE, CMAP_LEN, max_sr, wait=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    def breakdown(c, tracks, setting, max_sr, kname):
+        c.profile_enable(True)
+        c.profile_reset()
+        for _ in range(3):
+            c.spec_batch(tracks, setting)
+            c.update_spec_imgs(DB_RANGE, CMAP_LEN, max_sr, wait=False)
+        torch.cuda.synchronize()
+        k_ms = (c.profile_get(kname)[0] + c.profile_get(kname + "_edges")[0]) / 3
+        img_ms = c.profile_get("spec_to_img")[0] / 3
+        red_ms = c.profile_get("minmax_reduce")[0] / 3
+        c.profile_enable(False)
+        return k_ms, img_ms, red_ms
+
+    def job(name, channels, setting, sr, pcm_of, hours):
+        """channels: [(id, ch, sr, n_samples)]; pcm_of(id, ch) -> device tensor of the whole channel."""
+        framing = setting.calc_framing_params
+        plan = sharding.plan(channels, framing, world)
+        units = plan[rank]
+        tracks = ctx.prepare_tracks([dict(pcm=pcm_of(u.id, u.ch)[u.pcm_lo:u.pcm_hi], id=u.id, ch=u.ch, sr=u.sr, full_len=u.full_len,
+                                          pcm_offset=u.pcm_lo, frame_begin=u.frame_begin, frame_count=u.frame_count) for u in units])
+        ctx.release_all()
+        barrier()
+        ms = timed(ctx, tracks, setting, sr, steps, warm)
+        barrier()
+        ms_all = gather(ms)
+        k_ms, img_ms, red_ms = breakdown(ctx, tracks, setting, sr, "stft_mel_db")
+        rng = ctx.range_get()
+        k_all, red_all = gather(k_ms), gather(red_ms)
+        # one GPU, whole job, no communicator: rank 0 while the others wait
+        solo_ms, solo_rng = (max(ms_all) if world == 1 else None), None
+        solo = None
+        if rank == 0 and world > 1:
+            solo = thb.Context(local_rank, stream.cuda_stream)
+            whole = solo.prepare_tracks([dict(pcm=pcm_of(i, ch), id=i, ch=ch, sr=s_) for (i, ch, s_, _) in channels])
+            solo_ms = timed(solo, whole, setting, sr, steps, warm)
+            solo_rng = solo.range_get()
+        check = None
+        if world > 1:
+            check = shard_check(torch, dist, ctx, solo, units, channels, framing, rank, dev, rng, solo_rng)
+        if solo is not None:
+            solo.close()
+        barrier()
+        ctx.release_all()
+        worst = max(ms_all)
+        rec = {"job": name, "units_per_rank": [len(p) for p in plan], "frames_per_rank": [sum(u.frame_count for u in p) for p in plan],
+               "ms_per_step": worst, "value": hours / (worst * 1e-3), "unit": UNIT,
+               "rank_ms": {"min": min(ms_all), "max": worst},
+               "stft_kernel_ms": {"min": min(k_all), "max": max(k_all), "skew": max(k_all) - min(k_all)},
+               "spec_to_img_ms": img_ms, "minmax_allreduce_ms": {"min": min(red_all), "max": max(red_all)},
+               "one_gpu_ms_same_run": None, "efficiency": None, "limiter": None, "check": check, "dB_range": list(rng)}
+        sm = torch.tensor([solo_ms if solo_ms is not None else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(sm, src=0)
+        one = float(sm.item())
+        rec["one_gpu_ms_same_run"] = one
+        rec["efficiency"] = one / (world * worst) if worst > 0 else None
+        ideal = one / world
+        over = worst - ideal
+        rec["limiter"] = (f"{1e3 * over:.0f} us per step over the ideal {1e3 * ideal:.0f} us: all-reduce scope (the wait for the slowest "
+                          f"rank + NCCL) {1e3 * max(red_all):.0f} us, STFT-kernel skew between ranks {1e3 * (max(k_all) - min(k_all)):.0f} us, "
+                          f"the rest launch gaps / tails of the smaller grids")
+        return rec
+
+    out = {"note": "fixed total work split over the ranks; `scaling` of the headline stays weak (the driver computes its efficiency)"}
+    # c3: 128 channels x 10 min (the weak batch of rank 0 IS this job: tracks 0..63)
+    setting3 = thb.SpecSetting(WIN_MS, T_OVERLAP, 1, thb.FreqScale.Mel, N_MEL)
+    n_ch = pcm_weak.shape[0]
+    chans3 = [(c // N_CH, c % N_CH, SR, n) for c in range(n_ch)]
+    if rank == 0:
+        pcm3 = {(c // N_CH, c % N_CH): pcm_weak[c, :n] for c in range(n_ch)}
+    else:
+        mine = sharding.plan(chans3, setting3.calc_framing_params, world)[rank]
+        buf = torch.empty((len(mine), (n + 63) // 64 * 64), dtype=torch.float32, device=dev)
+        pcm3 = {}
+        for k, u in enumerate(mine):
+            ctx.synth_pcm(buf[k, :n], SR, u.id, u.ch, track_flags(u.id))
+            pcm3[(u.id, u.ch)] = buf[k, :n]
+        ctx.synchronize()
+    out["c3"] = job("C3: 64 stereo tracks x 10 min, mel 128, hop 512 -- sharded by channel", chans3, setting3, SR,
+                    lambda i, ch: pcm3[(i, ch)], n_ch * (n / SR) / 3600.0)
+    # c2: one 1-hour mono file, hop 256, mel 128 -- sharded by frame range
+    n2 = SR * 3600 if args.scale >= 1.0 else SR * 120
+    setting2 = thb.SpecSetting(WIN_MS, 8, 1, thb.FreqScale.Mel, N_MEL)
+    file2 = torch.empty((n2 + 63) // 64 * 64, dtype=torch.float32, device=dev)
+    ctx.synth_pcm(file2[:n2], SR, 7, 0, 0)
+    ctx.synchronize()
+    out["c2"] = job("C2: one 1-hour 48 kHz mono file, mel 128, hop 256 -- sharded by frame range", [(7, 0, SR, n2)], setting2, SR,
+                    lambda i, ch: file2[:n2], (n2 / SR) / 3600.0)
+    del file2
+    return out
+
+
+def shard_check(torch, dist, ctx, solo, units, channels, framing, rank, dev, rng, solo_rng) -> str:
+    """Every rank compares what it computed for its shard with the one-GPU run of the whole job on rank 0: same dB range,
+    and -- for up to two of its units -- the same dB rows and u16 image columns, bit for bit (tools/multi_gpu_check.py's
+    assertion, from inside the bench run).  Raises on a mismatch."""
+    world = dist.get_world_size()
+    r = torch.tensor(list(solo_rng) if rank == 0 else [0.0, 0.0], dtype=torch.float32, device=dev)
+    dist.broadcast(r, src=0)
+    assert tuple(float(x) for x in r.tolist()) == tuple(np.float32(x) for x in rng), (rank, rng, r.tolist())
+    # each rank names the head of its first unit and the tail of its last one (the cuts of a frame-range split);
+    # rank 0 serves those rows of the one-GPU result
+    W = 30000
+    mine = []
+    if units:
+        a, b = units[0], units[-1]
+        mine.append((a.id, a.ch, a.frame_begin, min(a.frame_count, W)))
+        tail = (b.id, b.ch, b.frame_begin + max(0, b.frame_count - W), min(b.frame_count, W))
+        if tail != mine[0]:
+            mine.append(tail)
+    names = [None] * world
+    dist.all_gather_object(names, mine)
+    checked = 0
+    cache = {}
+    for src_rank, lst in enumerate(names):
+        for (i, ch, fb, fc) in lst:
+            shape = torch.zeros(2, dtype=torch.int64, device=dev)
+            spec = img = None
+            if rank == 0:
+                if (i, ch) not in cache:
+                    cache.clear()
+                    cache[(i, ch)] = (solo.spec_read(i, ch), solo.img_read(i, ch))
+                spec = cache[(i, ch)][0][fb:fb + fc]
+                img = cache[(i, ch)][1][:, fb:fb + fc]
+                shape[0], shape[1] = spec.shape[1], img.shape[0]
+            dist.broadcast(shape, src=0)
+            B, H = int(shape[0]), int(shape[1])
+            t_spec = torch.from_numpy(np.ascontiguousarray(spec)).to(dev) if rank == 0 else torch.empty((fc, B), dtype=torch.float32, device=dev)
+            t_img = torch.from_numpy(np.ascontiguousarray(img).view(np.int16)).to(dev) if rank == 0 else torch.empty((H, fc), dtype=torch.int16, device=dev)
+            dist.broadcast(t_spec, src=0)
+            dist.broadcast(t_img, src=0)
+            if rank == src_rank:
+                u = next(x for x in units if (x.id, x.ch) == (i, ch))
+                got = ctx.spec_read(i, ch)[fb - u.frame_begin:fb - u.frame_begin + fc]
+                gimg = ctx.img_read(i, ch)[:, fb - u.frame_begin:fb - u.frame_begin + fc]
+                assert np.array_equal(got, t_spec.cpu().numpy(), equal_nan=True), f"rank {rank}: dB rows of ({i}, {ch}) differ from one GPU"
+                assert np.array_equal(gimg.view(np.int16), t_img.cpu().numpy()), f"rank {rank}: image of ({i}, {ch}) differs from one GPU"
+            checked += 1
+    return f"{checked} shard units over {world} ranks: dB rows, u16 images and the dB range bit-equal to the one-GPU run"
+
+
+def other_configs(torch, thb, ctx, pcm, n, peak_fp32, hbm_gbs) -> list:
+    """Kernel times of BASELINE.json's other configurations on one GPU (PCM resident; the library's per-kernel CUDA
+    events), the rows of DESIGN.md's per-configuration table (tools/design_table.py renders them)."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import configs_bench as cb
+    cb.FP32_PEAK_TFLOPS, cb.HBM_GBS = peak_fp32, hbm_gbs
+    recs = []
+    t0 = time.perf_counter()
+    Mel, Lin = thb.FreqScale.Mel, thb.FreqScale.Linear
+    ctx.release_all()
+    cb.stft_case(ctx, "C1 linear 2048/512, 2 113 529 samples mono", 1, 2113529 / 48000.0, 48000, 2048 / 48.0, 4, Lin, 0, 3, recs.append)
+    cb.stft_case(ctx, "C2 mel128 2048/256, 1 h mono", 1, 3600, 48000, 2048 / 48.0, 8, Mel, 128, 3, recs.append)
+    cb.stft_case(ctx, "C2 mel-default(347) 2048/256, 1 h mono", 1, 3600, 48000, 2048 / 48.0, 8, Mel, 0, 3, recs.append)
+    cb.stft_case(ctx, "C3' default setting 40 ms/4 (1920/480/2048, mel 347), 32 ch x 10 min", 32, 600, 48000, 40.0, 4, Mel, 0, 3, recs.append)
+    cb.stft_case(ctx, "C4 linear 16384/1024 @96 kHz, one 15-min track", 1, 900, 96000, 16384 / 96.0, 16, Lin, 0, 2, recs.append)
+    cb.stft_case(ctx, "C4 mel-default(1621) 16384/1024 @96 kHz, one 15-min track", 1, 900, 96000, 16384 / 96.0, 16, Mel, 0, 2, recs.append)
+    cb.stft_case(ctx, "default setting @16 kHz (640/160/1024, mel default), 32 ch x 10 min", 32, 600, 16000, 40.0, 4, Mel, 0, 2, recs.append)
+    cb.stft_case(ctx, "default setting @8 kHz (320/80/512, mel default), 32 ch x 10 min", 32, 600, 8000, 40.0, 4, Mel, 0, 2, recs.append)
+    # C5 (levels 9 and 15) + f3 + f4 on C3's own PCM, f2 on 16 of its channels
+    cb.envelope_case(ctx, pcm.shape[0], n / SR, SR, 3, recs.append, levels=(9, 15), pcm=pcm)
+    cb.tile_case(ctx, 16, n / SR, SR, 3, recs.append, levels=((0, 0),), pcm=pcm)
+    recs.append({"config": "(time spent on this table)", "seconds": time.perf_counter() - t0})
+    return recs
+
+
+def tile_latency_us(thb, ctx, n) -> dict:
+    """get_waveform_tile is one tile per call from the host's channel (lib.rs:343-367): latency of thb_waveform_tile with
+    pageable HOST PCM, first call (the tile's samples cross PCIe) and repeated (the channel's device copy is reused),
+    against the CPU port's encode_waveform_tile on the same tile."""
+    from oracle import orc
+    wav = orc.synth_pcm(n, SR, 9, 0, 0)
+    out = {}
+    for level in (9, 15):
+        ctx.pcm_cache_clear()
+        tile = 3 if level == 9 else 0
+        t0 = time.perf_counter()
+        got = ctx.waveform_tile(wav, 1, level, tile)
+        cold = time.perf_counter() - t0
+        reps = 50
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.waveform_tile(wav, 1, level, tile)
+        warm = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(5):
+            want = orc.encode_waveform_tile(wav, 1, level, tile)
+        cpu = (time.perf_counter() - t0) / 5
+        a = np.frombuffer(got, np.float32, offset=24).reshape(-1, 3)
+        b = np.frombuffer(want, np.float32, offset=24).reshape(-1, 3)
+        assert got[:24] == want[:24] and np.array_equal(a[:, :2], b[:, :2])
+        out[f"level{level}"] = {"samples_in_tile": min(n, 1024 << level), "gpu_first_call_us": 1e6 * cold, "gpu_repeat_us": 1e6 * warm,
+                                "cpu_port_us": 1e6 * cpu, "note": "python ctypes call overhead (two calls: size query + tile) included on the GPU side"}
+    ctx.pcm_cache_clear()
+    return out
+
+
 # -------------------------------------------------------------------------------------------------
 def run_b200(args) -> None:
     import torch
@@ -258,7 +495,12 @@ def run_b200(args) -> None:
     hop, win, n_fft = setting.calc_framing_params(SR)
     T = thb.n_frames(n, win, hop)
 
-    stream = torch.cuda.current_stream()
+    # The library launches on the stream it is given.  torch's default stream has handle 0, which the C ABI reads as
+    # "create your own stream" -- and torch.cuda.Event on the default stream would then time nothing the library does.
+    # So: one explicit torch stream, made current (synthetic PCM, NCCL ordering, events) and handed to the library.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = thb.Context(local_rank, stream.cuda_stream)
     if world > 1:
         obj = [thb.Context.comm_unique_id() if rank == 0 else None]
@@ -278,8 +520,10 @@ def run_b200(args) -> None:
     tracks_dev = ctx.prepare_tracks([dict(pcm=pcm[c, :n], id=c // N_CH, ch=c % N_CH, sr=SR) for c in range(n_ch_total)])
 
     def step_resident():
+        # both calls only queue work on the stream (PCM resident, no host outputs, range read after the loop):
+        # the host runs ahead and the device works back to back, as a re-analysis loop of the host program would
         ctx.spec_batch(tracks_dev, setting)
-        return ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR)
+        ctx.update_spec_imgs(DB_RANGE, CMAP_LEN, SR, wait=False)
 
     def barrier():
         if world > 1:
@@ -299,9 +543,10 @@ def run_b200(args) -> None:
     launches0 = ctx.launch_count()
     e0.record(stream)
     for _ in range(args.steps):
-        mn, mx = step_resident()
+        step_resident()
     e1.record(stream)
     torch.cuda.synchronize()
+    mn, mx = ctx.range_get()
     clocks = sampler.stop()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -333,11 +578,22 @@ def run_b200(args) -> None:
             traffic = json.loads(tp.read_text()).get("stft_mel_db_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # FP32 roof of the part at the clock it actually ran at: SMs x 128 lanes x 2 flop x SM clock
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    peak_fp32 = sm_count * 256 * sm_mhz * 1e6 / 1e12
+    fp32_tflops = alg_flops / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
     roofline = {
         "kernel": "stft_mel_db", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at full size, read from "
+                          "profiles/roofline_traffic.json (captured under ncu in a separate run, not measured by this one)",
+        # what ncu says binds the kernel (profiles/): FP32 pipe + issue slots + shared-memory wavefronts, not HBM --
+        # `bound`/`frac` above keep the contract's HBM figure, these two give the roof that actually limits it
+        "limiter_per_ncu": "fp32 pipe / issue slots (HBM traffic is 1.006x algorithmic and far below the roof)",
+        "frac_fp32": fp32_tflops / peak_fp32, "peak_fp32_tflops": peak_fp32, "sm_mhz_for_fp32_peak": sm_mhz,
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
-        "achieved_fp32_tflops": alg_flops / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0,
+        "achieved_fp32_tflops": fp32_tflops,
         "share_of_step": (k_ms / ms_total) if ms_total > 0 else None,
         "launches_per_step": k_launches / max(args.steps, 1),
         "edge_kernels_ms_per_step": edge_ms / max(args.steps, 1),
@@ -346,6 +602,21 @@ def run_b200(args) -> None:
         if img_ms > 0 else None,
         "minmax_allreduce_avg_ms": red_ms / max(args.steps, 1),
     }
+
+    # ---- strong scaling: the FIXED jobs of BASELINE configs[2] / configs[1] dealt over the N ranks ----
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling(args, torch, dist, thb, ctx, pcm, n, rank, world, local_rank, dev, stream)
+
+    # ---- the other BASELINE configurations, kernel times only (N == 1) ----
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and args.scale >= 1.0:
+        configs = other_configs(torch, thb, ctx, pcm, n, peak_fp32, peaks["hbm_gbs"])
+
+    # ---- the per-tile seam: one thb_waveform_tile call against the CPU port, host PCM ----
+    tile_latency = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        tile_latency = tile_latency_us(thb, ctx, n)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
     e2e = None
@@ -463,7 +734,7 @@ def run_b200(args) -> None:
                        "l2": "inputs (14.75 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "dB_range": [mn, mx]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_i16": e2e_i16, "clocks": clocks,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "strong": strong, "configs": configs, "tile_latency_us": tile_latency,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -481,6 +752,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and args.scale >= 1.0:
         args.warmup = 3  # timing rule: W >= 3

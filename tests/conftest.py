@@ -35,3 +35,12 @@ def orc():
     from oracle import orc as _orc
     _orc.build()
     return _orc
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """the measured margins of every GPU parity case (tests/parity_util.py) -> gpurun_out/parity_margins.json"""
+    try:
+        import parity_util
+        parity_util.dump_margins()
+    except Exception:
+        pass

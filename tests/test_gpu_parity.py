@@ -42,46 +42,7 @@ def _scale(orc, fs):
     return orc.MEL if fs == thb.FreqScale.Mel else orc.LINEAR
 
 
-def check_spec(orc, gpu_db, wav, sr, setting: thb.SpecSetting, tag=""):
-    an = orc.Analyzer(sr, setting.win_ms, setting.t_overlap, setting.f_overlap, _scale(orc, setting.freq_scale),
-                      setting.n_mel)
-    truth_db, truth_amp = an.calc_spec_truth(wav, want_amp=True, n_threads=8)
-    f32_db = an.calc_spec(wav, n_threads=8)
-    assert gpu_db.shape == truth_db.shape, (tag, gpu_db.shape, truth_db.shape)
-    g = gpu_db.astype(np.float64)
-    neg = np.isneginf(truth_db)
-    assert not np.isnan(g).any(), f"{tag}: NaN in GPU output"
-    P = truth_amp ** 2
-    # all-zero input frames: every bin must be exactly -inf (0 -> -inf, decibel.rs:193)
-    silent = P.max(axis=1) == 0.0
-    assert np.all(np.isneginf(g[silent])), f"{tag}: silent frames must be -inf"
-    assert not np.isposinf(g).any()
-    with np.errstate(over="ignore", invalid="ignore"):
-        Pg = np.where(np.isneginf(g), 0.0, 10.0 ** (g / 10.0))
-    floor = FLOOR * P.max(axis=1, keepdims=True)
-    rel = np.abs(Pg - P) / np.maximum(np.maximum(P, floor), 1e-300)
-    rel[silent] = 0.0
-    worst_pow = float(rel.max()) if rel.size else 0.0
-    above = (P > floor) & ~neg
-    with np.errstate(invalid="ignore"):
-        ddb = np.where(~neg, np.abs(g - np.where(neg, 0.0, truth_db)), 0.0)
-        ddb32 = np.where(~neg, np.abs(f32_db.astype(np.float64) - np.where(neg, 0.0, truth_db)), 0.0)
-    worst_db = float(ddb[above].max()) if above.any() else 0.0
-    assert worst_pow <= POW_RTOL, f"{tag}: power rel err {worst_pow:.3g}"
-    assert worst_db <= DB_TOL, f"{tag}: dB err above floor {worst_db:.3g}"
-    # below the floor an f32 FFT's error is ABSOLUTE (set by the frame's energy, not by the bin): compare the
-    # amplitude error normalised by the frame's peak amplitude with the reference-like f32 oracle's own worst
-    peak = np.sqrt(P.max(axis=1, keepdims=True))
-    live = (peak[:, 0] > 0)
-    if live.any():
-        with np.errstate(over="ignore", invalid="ignore"):
-            amp_g = np.where(np.isneginf(g), 0.0, 10.0 ** (g / 20.0))
-            amp_o = np.where(np.isneginf(f32_db), 0.0, 10.0 ** (f32_db.astype(np.float64) / 20.0))
-        eg = (np.abs(amp_g - truth_amp)[live] / peak[live]).max()
-        eo = (np.abs(amp_o - truth_amp)[live] / peak[live]).max()
-        # + 1.5e-6: an f32 dB value near -150 dB is itself quantised to 8.8e-7 relative in amplitude
-        assert eg <= 3.0 * eo + 1.5e-6, f"{tag}: amplitude err / frame peak {eg:.3g} vs f32 oracle {eo:.3g}"
-    return worst_pow, worst_db
+from parity_util import MARGINS, check_spec  # noqa: E402,F401
 
 
 # ---------------------------------------------------------------------------------------------
@@ -378,6 +339,42 @@ def test_spec_parity(ctx, orc, case):
     mn, mx = ctx.spec_minmax(1, 0)
     assert (mn, mx) == orc.find_min_max(db), tag
     print(tag, "worst power rel %.3g, worst dB %.3g" % worst)
+
+
+@pytest.mark.parametrize("setting,sr", [(thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128), 48000),
+                                        (thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear), 48000),
+                                        (thb.SpecSetting(), 44100), (thb.SpecSetting(), 16000),
+                                        (thb.SpecSetting(16384 / 96.0, 16, 1, thb.FreqScale.Linear), 96000)],
+                         ids=["mel128-2048", "lin-2048", "default-44k1", "default-16k", "lin-16384"])
+def test_genuinely_f32_pcm(ctx, orc, setting, sr):
+    """Every other parity input is the i16-quantised synthetic signal (what a 16-bit decoder hands over).  f32 files
+    (and the f32 output of gain / resampling stages) are not on that grid: Gaussian noise + an irrational-frequency tone
+    with full 24-bit mantissas, a short stretch of denormals, a stretch of -0.0 and single samples at the f32 extremes of
+    ordinary audio.  Same bars as the quantised cases; no NaN anywhere (0 * x, flushed denormals), and the frames that see
+    nothing but -0.0 are exactly -inf."""
+    rng = np.random.default_rng(4242)
+    n = 6 * sr
+    t = np.arange(n, dtype=np.float64)
+    x = (0.3 * np.sin(2 * np.pi * (997.0 * np.sqrt(2.0)) * t / sr) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    # denormals (and zeros): a stretch SHORTER than any window here, so that every frame that sees it also sees ordinary
+    # samples -- a frame of nothing but denormals is below what f32 arithmetic resolves (window x sample underflows in
+    # the reference's own f32 path too), whatever the hardware does with them
+    x[sr:sr + 300] = np.float32(1e-41) * rng.integers(-3, 4, 300).astype(np.float32)
+    x[2 * sr:2 * sr + 9000] = np.float32(-0.0)
+    x[3 * sr + 5] = np.float32(0.99999994)
+    x[3 * sr + 6] = np.float32(-1.0)
+    x[4 * sr:4 * sr + 64] = np.float32(1.1754944e-38)                                  # smallest normal
+    db = ctx.calc_spec(x, sr, setting, id=9, ch=0)
+    assert not np.isnan(db).any()
+    check_spec(orc, db, x, sr, setting, "f32-" + "-".join(str(v) for v in setting.calc_framing_params(sr)) +
+               ("-mel" if setting.freq_scale == thb.FreqScale.Mel else "-lin"))
+    # frames that see nothing but -0.0 are silent: exactly -inf, as the reference's 0 -> -inf rule gives (decibel.rs:193)
+    hop, win, n_fft = setting.calc_framing_params(sr)
+    f0 = (2 * sr + win) // hop + 1
+    f1 = (2 * sr + 9000 - win) // hop - 1
+    if f1 > f0:
+        assert np.isneginf(db[f0:f1]).all()
+    ctx.release(9, 0)
 
 
 @pytest.mark.parametrize("n", [2, 3, 5, 100, 1919, 1920, 1921, 2048, 2400])

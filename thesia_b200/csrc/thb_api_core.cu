@@ -192,11 +192,11 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     d.mi_words = d.mi_groups = d.mi_min_start = d.mi_max_reach = 0;
     d.mi_blob = nullptr;
     std::vector<uint32_t> mi_blob;
-    if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
+    if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
         // (the large-FFT kernel walks the same bin-major schedule out of global memory)
         const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
         if (mi.valid) mi_blob = mi.blob();
-        if (d.n_fft != 2048 && mi.valid) {
+        if (d.n_fft > 2048 && mi.valid) {
             // the large-FFT kernel keeps magnitudes (16 lead slots + reach) and two partial sums per slot in its FFT buffer
             const long long need = 16 + ((static_cast<long long>(mi.max_reach) + 2) & ~1ll) + 2ll * mi.n_groups * 32 + 1;
             if (mi.min_start < -15 || need > thb::stft_big_buffer_slots(d.n_fft)) mi_blob.clear();  // band-major fallback
@@ -283,25 +283,28 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     d.fast_wpad = nullptr;
     d.fast_tw = nullptr;
     std::vector<float> wpad, ftw;
-    if (d.n_fft == 2048) {
-        // tables of the warp-per-frame kernel (thb_stft_fast.cu)
-        wpad.assign(2048, 0.0f);
+    if (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512) {
+        // tables of the warp-register kernels (thb_stft_fast.cu / thb_stft_pair.cu: R1 = 32; thb_stft_warp.cu: R1 = 16 / 8):
+        // the frame is NC = 32 R1 complex points = R1 x 32
+        const int r1 = d.n_fft / 64, ncx = d.n_fft / 2;
+        wpad.assign(d.n_fft, 0.0f);
         for (int a = 0; a < d.win; a++) wpad[a + d.pad_left] = 0.5f * win[a];
-        ftw.resize(2 * (31 * 32 + 16 * 32));
+        ftw.resize(2 * ((r1 - 1) * 32 + 16 * 32));
         const double tau = 6.283185307179586476925286766559;
-        for (int k1 = 1; k1 < 32; k1++)
+        for (int k1 = 1; k1 < r1; k1++)
             for (int lane = 0; lane < 32; lane++) {
-                const double a = -tau * static_cast<double>((lane * k1) % 1024) / 1024.0;
+                const double a = -tau * static_cast<double>((lane * k1) % ncx) / static_cast<double>(ncx);
                 ftw[2 * ((k1 - 1) * 32 + lane)] = static_cast<float>(std::cos(a));
                 ftw[2 * ((k1 - 1) * 32 + lane) + 1] = static_cast<float>(std::sin(a));
             }
         for (int j = 0; j < 16; j++)
             for (int lane = 0; lane < 32; lane++) {
-                const int k_own = (lane ? lane : 32) + 32 * (31 - j);
-                float c = tw[2 * (k_own % 2048)], s = tw[2 * (k_own % 2048) + 1];
-                if (k_own == 1024) { c = -1.0f; s = 0.0f; }
-                ftw[2 * (31 * 32 + j * 32 + lane)] = c;
-                ftw[2 * (31 * 32 + j * 32 + lane) + 1] = s;
+                const int k1 = lane % r1;
+                const int k_own = (k1 ? k1 : r1) + r1 * (31 - j);
+                float c = tw[2 * (k_own % d.n_fft)], s = tw[2 * (k_own % d.n_fft) + 1];
+                if (k_own == ncx) { c = -1.0f; s = 0.0f; }
+                ftw[2 * ((r1 - 1) * 32 + j * 32 + lane)] = c;
+                ftw[2 * ((r1 - 1) * 32 + j * 32 + lane) + 1] = s;
             }
         if ((rc = upload(ctx, pl.get(), wpad, &d.fast_wpad))) return rc;
         const float *ftwp = nullptr;

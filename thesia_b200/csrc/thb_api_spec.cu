@@ -170,6 +170,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
     const char *force = getenv("THB_STFT_KERNEL");
     const bool want_pair = !force || !strcmp(force, "pair"), want_fast = want_pair || !strcmp(force, "fast");
     const bool want_big = !force || !strcmp(force, "big");
+    const bool want_warp = !force || !strcmp(force, "warp");  // n_fft 1024 / 512: thb_stft_warp.cu
     struct Launch {
         const Plan *plan;
         thb::TrackDesc *d_desc;  // every channel of the group, whole frame range
@@ -211,7 +212,9 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             L.max_frames = std::max(L.max_frames, h[j].n_frames);
         }
         const thb::PlanDev &pd = L.plan->dev;
-        if (want_pair && thb::stft_pair_supported(pd) && thb::stft_fast_supported(pd)) {
+        const bool use_pair = want_pair && thb::stft_pair_supported(pd) && thb::stft_fast_supported(pd);
+        const bool use_warp = want_warp && thb::stft_warp_supported(pd);
+        if (use_pair || use_warp) {
             std::vector<thb::TrackDesc> pairs, edges;
             const long long W = pd.win, H = pd.hop, half = W / 2, padl = pd.pad_left;
             for (size_t j = 0; j < g.second.size(); j++) {
@@ -220,7 +223,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 auto ceil_div = [](long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; };
                 long long lo = std::max({fb, ceil_div(half, H), ceil_div(f.pcm_offset + half + padl, H)});
                 long long hi = fe - 1;
-                const long long c2 = f.full_len - W + half, c4 = f.pcm_offset + f.slice_len - 2048 + half + padl;
+                const long long c2 = f.full_len - W + half, c4 = f.pcm_offset + f.slice_len - pd.n_fft + half + padl;
                 hi = (c2 < 0 || c4 < 0) ? -1 : std::min({hi, c2 / H, c4 / H});
                 long long cnt = hi >= lo ? hi - lo + 1 : 0;
                 // the frame-pair kernel loads sample pairs: 8-byte aligned float2, or 4-byte aligned i16 pairs
@@ -232,7 +235,8 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 // kernel, through its one-load-per-sample variant
                 const bool usable = aligned || (addr & (esz - 1)) == 0;
                 if (usable && !aligned && cnt >= 2) L.pair_unaligned = true;
-                cnt = usable ? (cnt & ~1ll) : 0;
+                // (the n_fft 2048 frame-pair kernel wants whole pairs; the n_fft 1024 / 512 kernel masks its own tail)
+                cnt = usable ? (use_pair ? (cnt & ~1ll) : cnt) : 0;
                 if (cnt < 2) {
                     if (f.n_frames) edges.push_back(f);
                     continue;
@@ -268,7 +272,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 thb::TrackDesc *he = arena_push<thb::TrackDesc>(ctx, edges.size(), &L.d_edge);
                 memcpy(he, edges.data(), sizeof(thb::TrackDesc) * edges.size());
             }
-            const long long tf = thb::stft_pair_tile_frames();
+            const long long tf = use_pair ? thb::stft_pair_tile_frames() : thb::stft_warp_tile_frames(pd);
             L.pair_tiles = static_cast<size_t>(L.n_pair) * static_cast<size_t>((L.max_pair_frames + tf - 1) / tf);
             max_pair_tiles = std::max(max_pair_tiles, L.pair_tiles);
         }
@@ -325,24 +329,28 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         if (l.n_pair || l.n_edge) {
             const char *kname = pd.n_mel ? "stft_mel_db" : "stft_lin_db";
             const char *ename = pd.n_mel ? "stft_mel_db_edges" : "stft_lin_db_edges";
+            const bool is2048 = pd.n_fft == 2048;  // else n_fft 1024 / 512: thb_stft_warp.cu, same division of labour
             if (l.n_pair) {
-                const unsigned tf = static_cast<unsigned>(thb::stft_pair_tile_frames());
+                const unsigned tf = static_cast<unsigned>(is2048 ? thb::stft_pair_tile_frames() : thb::stft_warp_tile_frames(pd));
                 const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
                                          static_cast<unsigned>(ctx->rescue_cap), tf,
                                          static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf)};
                 CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
                 {
-                    ProfScope ps(ctx, kname, 1);  // the frame-pair kernel alone: this is the roofline kernel
-                    e = thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream);
+                    ProfScope ps(ctx, kname, 1);  // the packed kernel alone: this is the roofline kernel
+                    e = is2048 ? thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream)
+                               : thb::launch_stft_warp_packed(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream);
                 }
                 if (e == cudaSuccess) {
                     ProfScope ps(ctx, ename, 1);
-                    e = thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
+                    e = is2048 ? thb::launch_stft_fast_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream)
+                               : thb::launch_stft_warp_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
                 }
             }
             if (e == cudaSuccess && l.n_edge) {
                 ProfScope ps(ctx, ename, (l.n_edge + 65534) / 65535);
-                e = thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream);
+                e = is2048 ? thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream)
+                           : thb::launch_stft_warp_scalar(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream);
             }
         } else {
             ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", chunks);

@@ -34,9 +34,10 @@ struct PlanDev {
     const float *mel_w;               // [nnz]
     int max_band_len;
     int mel_nnz;
-    // n_fft == 2048 warp-per-frame path (thb_stft_fast.cu); null otherwise
-    const float *fast_wpad;           // [2048] 0.5 * window centred in the FFT buffer, zeros outside
-    const float2 *fast_tw;            // [31*32] W_1024^(lane*k1) then [16*32] split twiddles
+    // warp-register paths: n_fft == 2048 (thb_stft_fast.cu / thb_stft_pair.cu) and n_fft == 1024 / 512 (thb_stft_warp.cu),
+    // R1 = n_fft / 64; null otherwise
+    const float *fast_wpad;           // [n_fft] 0.5 * window centred in the FFT buffer, zeros outside
+    const float2 *fast_tw;            // [(R1-1)*32] W_(n_fft/2)^(lane*k1) then [16*32] split twiddles
     // warp schedule of the sparse mel product (thb_host.hpp MelItems::blob); mel only, n_fft == 2048
     int mi_words;                     // size of mi_blob in 32-bit words
     int mi_groups, mi_min_start, mi_max_reach;
@@ -140,6 +141,18 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
                              bool pcm_i16, bool unaligned, int sm_count, cudaStream_t st);
 // frames per work item of the frame-pair kernel (a multiple of twice its warps per CTA)
 int stft_pair_tile_frames();
+
+// n_fft == 1024 / 512 in the same warp-register design (thb_stft_warp.cu): the packed kernel over the interior frames of
+// every descriptor (any count; `unaligned` as above), its scalar twin over whole descriptors (file edges, leftovers)
+// and over the rescue list; both agree bit for bit on every frame
+bool stft_warp_supported(const PlanDev &plan);
+int stft_warp_tile_frames(const PlanDev &plan);
+cudaError_t launch_stft_warp_packed(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue,
+                                    bool pcm_i16, bool unaligned, int sm_count, cudaStream_t st);
+cudaError_t launch_stft_warp_scalar(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, long long max_frames,
+                                    int sm_count, cudaStream_t st);
+cudaError_t launch_stft_warp_list(const PlanDev &plan, const TrackDesc *d_tracks, RescueList rescue, int sm_count,
+                                  cudaStream_t st);
 // the scalar kernel over the tiles on a rescue list (persistent grid; a no-op when the list is empty)
 cudaError_t launch_stft_fast_list(const PlanDev &plan, const TrackDesc *d_tracks, RescueList rescue,
                                   int sm_count, cudaStream_t st);

@@ -16,6 +16,7 @@ import torch  # noqa: E402
 
 import thesia_b200 as thb  # noqa: E402
 
+FP32_PEAK_TFLOPS = 1965e6 * 148 * 256 / 1e12  # sm_max_mhz x SMs x 128 lanes x 2 (bench.py overrides it with the measured clock)
 HBM_GBS = 6552.3
 try:
     HBM_GBS = float(json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
@@ -55,18 +56,20 @@ def stft_case(ctx, name, n_ch, seconds, sr, win_ms, t_overlap, scale, n_mel, rep
     rec = {"config": name, "channels": n_ch, "seconds": seconds, "sr": sr, "win": win, "hop": hop, "n_fft": n_fft, "bins": B,
            "frames": n_ch * T, "stft_ms": ms, "audio_hours_per_s": n_ch * seconds / 3600.0 / (ms * 1e-3),
            "Mframes_per_s": n_ch * T / ms / 1e3, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
-           "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS, "fp32_tflops": flops / (ms * 1e-3) / 1e12}
+           "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM_GBS, "fp32_tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_fp32": flops / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS}
     ctx.release_all()
     del pcm
     torch.cuda.empty_cache()
     out(rec)
 
 
-def envelope_case(ctx, n_ch, seconds, sr, reps, out):
+def envelope_case(ctx, n_ch, seconds, sr, reps, out, levels=range(9, 16), pcm=None):
     n = int(sr * seconds)
-    pcm = synth(ctx, n_ch, n, sr)
+    if pcm is None:
+        pcm = synth(ctx, n_ch, n, sr)
     wavs = [pcm[c, :n] for c in range(n_ch)]
-    for level in range(9, 16):
+    for level in levels:
         ctx.waveform_level_batch(wavs, 1, level, want_host=False)
         ctx.synchronize()
         ctx.profile_enable(True)
@@ -115,17 +118,18 @@ def envelope_case(ctx, n_ch, seconds, sr, reps, out):
     torch.cuda.empty_cache()
 
 
-def tile_case(ctx, n_ch, seconds, sr, reps, out):
+def tile_case(ctx, n_ch, seconds, sr, reps, out, levels=((0, 0), (2, 0), (4, 1)), pcm=None):
     """f2: every tile of a level for n_ch mel-default spectrogram images (347 x 56 251 at 10 min), levels 0 / 2 / 4 in x."""
     from thesia_b200.analysis import spectrogram_tile_geometry
     n = int(sr * seconds)
-    pcm = synth(ctx, n_ch, n, sr)
+    if pcm is None:
+        pcm = synth(ctx, n_ch, n, sr)
     setting = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 0)
     ctx.spec_batch([dict(pcm=pcm[c, :n], id=c, ch=0, sr=sr) for c in range(n_ch)], setting, want_host=False)
     ctx.update_spec_imgs(100.0, 258)
     H, W = ctx.img_read(0, 0).shape
     cm = bytes((i * 7 + j * 31) & 255 for i in range(258) for j in range(4))
-    for lx, ly in ((0, 0), (2, 0), (4, 1)):
+    for lx, ly in levels:
         g = spectrogram_tile_geometry(H, W, lx, ly, 0, 0)
         tiles_x, tiles_y = -(-g[0] // 512), -(-g[1] // 512)
         reqs = [(c, 0, lx, ly, tx, ty) for c in range(n_ch) for ty in range(tiles_y) for tx in range(tiles_x)]
@@ -153,7 +157,8 @@ def main():
     ap.add_argument("--c4-seconds", type=int, default=3600, help="shorter C4 tracks (profiling runs)")
     a = ap.parse_args()
     only = set(a.only.split(","))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)   # (the default stream's handle 0 would make the library create its own stream)
     ctx = thb.Context(0, stream.cuda_stream)
     outdir = Path("gpurun_out")
     outdir.mkdir(exist_ok=True)

@@ -35,7 +35,8 @@ def main():
     setting = thb.SpecSetting(a.win_ms, a.t_overlap, 1, fs, a.n_mel if a.scale == "mel" else 0)
     hop, win, n_fft = setting.calc_framing_params(sr)
     T = thb.n_frames(n, win, hop)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)   # (the default stream's handle 0 would make the library create its own stream)
     ctx = thb.Context(0, stream.cuda_stream)
     row = (n + 63) // 64 * 64
     pcm = torch.empty((a.channels, row), dtype=torch.float32, device="cuda")
@@ -47,8 +48,16 @@ def main():
     print(f"{a.channels} ch x {a.seconds} s @ {sr} Hz, win {win} hop {hop} n_fft {n_fft}, {a.scale}, {frames} frames")
     ref = None
     for var in a.variants.split(","):
-        name, _, nw = var.partition(":")
+        # name[:warps][/ENV=VALUE...]   e.g.  pair/THB_PAIR_PREFETCH=0/THB_MEL4=0
+        head, *envs = var.split("/")
+        name, _, nw = head.partition(":")
         os.environ["THB_STFT_KERNEL"] = name
+        os.environ.pop("THB_PAIR_WARPS", None)
+        for k in ("THB_PAIR_PREFETCH", "THB_MEL4", "THB_PAIR_SHARE"):
+            os.environ.pop(k, None)
+        for kv in envs:
+            k, _, v = kv.partition("=")
+            os.environ[k] = v
         if nw:
             os.environ["THB_PAIR_WARPS"] = nw
         ctx.spec_batch(tracks, setting)  # warm-up
@@ -71,7 +80,7 @@ def main():
             fin = np.isfinite(ref) & np.isfinite(out)
             diff = float(np.abs(ref[fin] - out[fin]).max()) if fin.any() else 0.0
         clk = ms * 1e-3 * 1.965e9 * 148 / frames
-        print(f"  {var:<10} {ms:8.3f} ms  {frames / ms / 1e3:8.1f} Mframes/s  {clk:7.1f} clk/frame/SM   max|dB - first| {diff:.2e}")
+        print(f"  {var:<44} {ms:8.3f} ms  {frames / ms / 1e3:8.1f} Mframes/s  {clk:7.1f} clk/frame/SM   max|dB - first| {diff:.2e}")
     ctx.close()
 
 
