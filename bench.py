@@ -630,6 +630,14 @@ def run_b200(args) -> None:
         if numa is not None:
             os.sched_setaffinity(0, numa[1])
             host_affinity = f"NUMA node {numa[0]} of the GPU ({len(numa[1])} CPUs)"
+        elif world > 1:
+            # sysfs reports one node (a VM that hides the topology): give every rank its own slice of the cores, so that
+            # the threads that allocate, touch and feed a rank's pinned buffers at least do not migrate over each other
+            cpus = sorted(affinity_before)
+            per = max(1, len(cpus) // world)
+            mine = set(cpus[local_rank * per:(local_rank + 1) * per]) or set(cpus)
+            os.sched_setaffinity(0, mine)
+            host_affinity = f"no NUMA information: cores {min(mine)}-{max(mine)} of {len(cpus)} by local rank"
         img_bytes = n_ch_total * N_MEL * T * 2
         img_stride = N_MEL * T
         host_img_p = C.c_void_p()
@@ -704,8 +712,40 @@ def run_b200(args) -> None:
         _lib.lib().thb_host_free(host_pcm_p)
         _lib.lib().thb_host_free(host_i16_p)
         _lib.lib().thb_host_free(host_img_p)
+        # what the box's host side delivers to N GPUs AT ONCE with no library in the way: plain pinned cudaMemcpyAsync
+        # (torch) of 1 GiB per rank, every rank at the same time.  e2e cannot beat bytes / this.
+        probe_n = 1 << 30
+        hp = torch.empty(probe_n, dtype=torch.uint8, pin_memory=True)
+        dp = torch.empty(probe_n, dtype=torch.uint8, device=dev)
+        hp.fill_(1)
+        feed = {}
+        for name, fn in (("h2d", lambda: dp.copy_(hp, non_blocking=True)), ("d2h", lambda: hp.copy_(dp, non_blocking=True))):
+            fn()
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            gbs = 3 * probe_n / (time.perf_counter() - t0) / 1e9
+            barrier()
+            g = torch.tensor([gbs], dtype=torch.float64, device=dev)
+            lo, tot = g.clone(), g.clone()
+            if world > 1:
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            feed[name + "_gbs_per_rank_min"] = float(lo.item())
+            feed[name + "_gbs_aggregate"] = float(tot.item())
+        del hp, dp
         os.sched_setaffinity(0, affinity_before)
         e2e["host_affinity"] = host_affinity
+        e2e["host_feed_probe"] = dict(feed, how=f"{world} rank(s) at once, 3 x 1 GiB pinned cudaMemcpyAsync each way, no library")
+        # the floor the host feed sets for one e2e step of this rank: its PCM in, its images out, one after the other
+        # (the images need the global range, which needs every spectrogram, which needs every sample)
+        floor_ms = 1e3 * (h2d_bytes / (feed["h2d_gbs_per_rank_min"] * 1e9) + img_bytes / (feed["d2h_gbs_per_rank_min"] * 1e9))
+        e2e["host_limit_ms_per_step"] = floor_ms
+        e2e["host_limit_value"] = hours_per_step / (floor_ms * 1e-3)
+        e2e["host_limit_gbs"] = feed["h2d_gbs_aggregate"]
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on a bounded sample ----
     cpu = None

@@ -10,7 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 
 #include "../../thesia_b200/host/thesia_host.hpp"
 
@@ -259,6 +261,42 @@ static void test_gpu_flow() {
     }
 }
 
+// get_waveform_tile is served from concurrent IPC threads under read locks (lib.rs:343-389).  The library's tile
+// readers take the context shared and run each call on its own stream: eight host threads asking for tiles of eight
+// channels must finish in clearly less wall-clock time than the same calls made one after the other, and every answer
+// must be the one a single thread gets.  (Host PCM: the channels are uploaded once by the first call, then cached.)
+static void test_tile_readers_overlap() {
+    Context ctx(0);
+    constexpr int kThreads = 8, kCalls = 300;
+    const uint64_t len = 1u << 22;  // level 11: two tiles of 2 M samples each (8 MB per call)
+    std::vector<std::vector<float>> wavs(kThreads, std::vector<float>(len));
+    for (int c = 0; c < kThreads; c++)
+        for (uint64_t i = 0; i < len; i++) wavs[c][i] = static_cast<float>(static_cast<int>((i * 2654435761u + c * 97u) % 20001u) - 10000) / 16384.0f;
+    std::vector<std::vector<uint8_t>> want(kThreads);
+    for (int c = 0; c < kThreads; c++) want[c] = encode_waveform_tile(ctx, wavs[c].data(), len, 1, 11, 1);  // uploads + caches
+    auto work = [&](int c, int *bad) {
+        for (int i = 0; i < kCalls; i++)
+            if (encode_waveform_tile(ctx, wavs[c].data(), len, 1, 11, 1) != want[c]) ++*bad;
+    };
+    int bad = 0;
+    work(0, &bad);  // warm-up
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int c = 0; c < kThreads; c++) work(c, &bad);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::vector<std::thread> ths;
+    std::vector<int> bads(kThreads, 0);
+    for (int c = 0; c < kThreads; c++) ths.emplace_back(work, c, &bads[c]);
+    for (auto &t : ths) t.join();
+    const auto t2 = std::chrono::steady_clock::now();
+    for (int b : bads) bad += b;
+    const double serial = std::chrono::duration<double>(t1 - t0).count(), parallel = std::chrono::duration<double>(t2 - t1).count();
+    std::printf("tile readers: %d x %d calls one after the other %.1f ms (%.1f us / tile), from %d threads %.1f ms (%.1f us / tile): %.2fx\n",
+                kThreads, kCalls, 1e3 * serial, 1e6 * serial / (kThreads * kCalls), kThreads, 1e3 * parallel,
+                1e6 * parallel / (kThreads * kCalls), serial / parallel);
+    EXPECT(bad == 0);
+    EXPECT(parallel < 0.67 * serial);  // a context-wide lock would make the two equal
+}
+
 int main(int argc, char **argv) {
     const std::string mode = argc > 1 ? argv[1] : "--cpu";
     try {
@@ -266,6 +304,7 @@ int main(int argc, char **argv) {
         test_window_and_mel();
         if (mode == "--gpu") {
             test_gpu_flow();
+            test_tile_readers_overlap();
         } else {
             test_no_device_is_loud();
         }

@@ -68,6 +68,11 @@ def check_spec(orc, gpu_db, wav, sr, setting: thb.SpecSetting, tag=""):
     MARGINS[tag or "untagged"] = {"n_fft": int(nfft_), "win": int(win_), "hop": int(hop_), "bins": int(gpu_db.shape[1]),
                                   "power_rel_err_above_floor": sweep, "dB_err_above_1e-5_floor": worst_db,
                                   "f32_oracle_dB_err_above_1e-5_floor": float(ddb32[above].max()) if above.any() else 0.0}
+    # at the survey's floors the reference-like f32 leg itself passes 1e-4 (measured: up to 4.6e-4 at 1e-7 for linear
+    # spectra, gpurun_out/parity_margins.json), so below 1e-5 the bar is the survey's RELATIVE one: the GPU within 2x of
+    # what f32 arithmetic in the reference's own operation order delivers
+    for fl, e in sweep.items():
+        assert e["gpu"] <= 2.0 * e["f32_oracle"] + 1e-5, f"{tag}: power rel err above the {fl} floor {e['gpu']:.3g} vs f32 oracle {e['f32_oracle']:.3g}"
     assert worst_pow <= POW_RTOL, f"{tag}: power rel err {worst_pow:.3g}"
     assert worst_db <= DB_TOL, f"{tag}: dB err above floor {worst_db:.3g}"
     # below the floor an f32 FFT's error is ABSOLUTE (set by the frame's energy, not by the bin): compare the
@@ -83,7 +88,7 @@ def check_spec(orc, gpu_db, wav, sr, setting: thb.SpecSetting, tag=""):
         MARGINS[tag or "untagged"].update({"amp_err_over_frame_peak": {"gpu": float(eg), "f32_oracle": float(eo)},
                                            "ratio_to_f32_oracle": float(eg / eo) if eo > 0 else None})
         # + 1.5e-6: an f32 dB value near -150 dB is itself quantised to 8.8e-7 relative in amplitude
-        assert eg <= 3.0 * eo + 1.5e-6, f"{tag}: amplitude err / frame peak {eg:.3g} vs f32 oracle {eo:.3g}"
+        assert eg <= 2.0 * eo + 1.5e-6, f"{tag}: amplitude err / frame peak {eg:.3g} vs f32 oracle {eo:.3g}"
     return worst_pow, worst_db
 
 

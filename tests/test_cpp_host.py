@@ -25,3 +25,4 @@ def test_cpp_host_mirror_gpu():
     _build()
     r = subprocess.run([str(BIN), "--gpu"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+    print(r.stdout)   # incl. the wall-clock line of the concurrent tile readers (std::thread, no interpreter lock)

@@ -21,7 +21,11 @@ import pytest
 import thesia_b200 as thb
 from thesia_b200.sharding import split_frames
 
+import os
+
 pytestmark = pytest.mark.gpu
+# under compute-sanitizer (tools/gpu_sanitize.sh) the same tests run at a sixth of the size: the tool slows kernels ~50x
+SMALL = os.environ.get("THB_TEST_SMALL") == "1"
 
 DB_TOL = 1e-3
 FLOOR = 1e-5
@@ -72,14 +76,14 @@ def _check_frames_against_oracle(orc, ctx, pcm_dev, n, sr, setting, frames, spec
 
 def test_c2_full_size_properties(ctx, orc):
     import torch
-    sr, n = 48000, 48000 * 3600
+    sr, n = 48000, 48000 * (600 if SMALL else 3600)
     setting = thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128)
     hop, win, _ = setting.calc_framing_params(sr)
     pcm = _device_track(ctx, n, sr, 7)
     ctx.spec_batch([dict(pcm=pcm, id=1, ch=0, sr=sr)], setting)
     whole = ctx.spec_read(1, 0)
     T = thb.n_frames(n, win, hop)
-    assert whole.shape == (T, 128) and T == 675001
+    assert whole.shape == (T, 128) and (SMALL or T == 675001)
     assert np.isfinite(whole).all()
     # frame locality against the oracle
     rng = np.random.default_rng(42)
@@ -158,7 +162,7 @@ def test_c2_full_size_properties(ctx, orc):
 @pytest.mark.parametrize("scale_name", ["linear", "mel"])
 def test_c4_large_fft_full_track(ctx, orc, scale_name):
     import torch
-    sr, n = 96000, 96000 * 600       # 10 min of a C4 track: 56 251 frames of 8193 bins = 1.8 GB of f32 (linear)
+    sr, n = 96000, 96000 * (100 if SMALL else 600)       # 10 min of a C4 track: 56 251 frames of 8193 bins = 1.8 GB of f32 (linear)
     scale = thb.FreqScale.Linear if scale_name == "linear" else thb.FreqScale.Mel
     setting = thb.SpecSetting(16384 / 96.0, 16, 1, scale, 0)
     hop, win, _ = setting.calc_framing_params(sr)

@@ -7,9 +7,13 @@ Stated tolerances (DESIGN.md "Parity"):
     50 dB under the frame's peak; the f32 oracle itself measures 5.9e-5 against this bound).
   * dB     |dB_gpu - dB_truth| <= 1e-3 dB wherever P_truth is above that floor; exactly -inf for
     all-zero frames; below the floor the power bound above applies (absolute), and over ALL bins the
-    amplitude error normalised by the frame's peak amplitude must be no worse than 3x the
+    amplitude error normalised by the frame's peak amplitude must be no worse than 2x the
     reference-like f32 oracle's own worst (+1.5e-6, the f32 quantisation of a dB value): an f32 FFT's error is absolute, set by the
     frame's energy, so a per-bin dB comparison of the deepest bin only measures luck.
+  * at the floors SURVEY.md section 7 asked for (1e-6, 1e-7 of the frame's peak power) the f32 oracle itself is past
+    1e-4 (up to 4.6e-4 at 1e-7 on linear spectra: profiles/r02_parity_margins.json lists every case), so there the bar is
+    the survey's relative one: GPU power error <= 2x the f32 oracle's (+1e-5), at each of 1e-5 / 1e-6 / 1e-7.
+    Every case's measured margins are written to gpurun_out/parity_margins.json (tests/parity_util.py).
   * envelope mean <= 1e-6 absolute; u16 image: bit-exact given the GPU's own dB, <= 1 LSB end to end.
 "truth" = the oracle's f64 leg; "f32 oracle" = its reference-like f32 leg.
 """

@@ -62,7 +62,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *addr, unsigned byte
 // flags: bit 0 = while a tile is computed, pull the PCM of this CTA's NEXT tile into L2 (the loads of a frame pair
 // then hit L2 instead of HBM: the pair's 40 loads sit at the head of a long dependent chain)
 // M4: the lean mel walk / gather (mel_walk4 / mel_band4; same results bit for bit)
-template <bool MEL, int NW, bool I16, int HS, bool M4>
+// PL (HS > 0): the PCM of the warp's NEXT frame pair is prefetched into L1 before the mel stage of the current one
+// (three instructions per pair), so that its 40 loads hit L1 instead of stalling the window multiply on L2 / HBM
+template <bool MEL, int NW, bool I16, int HS, bool M4, bool PL>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
                                                                         long long n_items, RescueList rescue, int flags) {
@@ -289,6 +291,18 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                 lmax = fmaxf(lmax, fmaxf(fmx.x, fmx.y));
                 lnmin = fmaxf(lnmin, fmaxf(fnm.x, fnm.y));
             }
+            if constexpr (PL && HS > 0 && !I16) {
+                // the (32 + HS) x 256-byte rows of the warp's next frame pair are contiguous: lane l touches 128-byte lines
+                // l, l + 32, l + 64 of them -- three instructions put the whole pair into L1 while the mel stage runs
+                const long long fn = fa + 2 * NW;
+                if (fn < f_end) {
+                    const char *base = reinterpret_cast<const char *>(d.pcm + ((d.frame_begin + fn) * p.hop - half - p.pad_left - d.pcm_offset));
+                    constexpr int kLines = (32 + HS) * 2;
+#pragma unroll
+                    for (int i = 0; i * 32 < kLines; i++)
+                        if (i * 32 + lane < kLines) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 128 * (i * 32 + lane)));
+                }
+            }
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
@@ -338,11 +352,11 @@ int pair_warps() {
     return (w == 8 || w == 10 || w == 12) ? w : 12;
 }
 
-template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true>
+template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true, bool PL = false>
 cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
                       cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
-    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS, M4>;
+    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS, M4, PL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
@@ -388,6 +402,9 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
         // THB_MEL4=0: the mel walk / gather with remainder code and 16-bit slot ids (A/B runs; same results)
         const char *m4 = getenv("THB_MEL4");
         if (plan.n_mel && m4 && atoi(m4) == 0) return launch_nw<true, 12, false, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        // THB_PAIR_PL=1: software-pipelined PCM loads (A/B runs)
+        const char *pl = getenv("THB_PAIR_PL");
+        if (plan.n_mel && pl && atoi(pl) == 1) return launch_nw<true, 12, false, 8, true, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         if (plan.n_mel) return launch_nw<true, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }

@@ -1,12 +1,17 @@
 #!/bin/bash
-# compute-sanitizer (memcheck, then racecheck on the shared-memory kernels) over a small subset of the GPU tests
+# compute-sanitizer memcheck over the WHOLE -m gpu suite (the full-size property tests run at reduced sizes under the
+# tool: THB_TEST_SMALL=1), racecheck over the kernels with shared-memory choreography.  Log -> gpurun_out/sanitize_<tag>.log
+TAG=${1:-r02}
 mkdir -p gpurun_out
+export THB_TEST_SMALL=1
 {
-echo "== memcheck"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 --print-limit 5 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-  -k "spectrogram_tile or apply_gain or odd_hop or plan_cache or (large_fft and 4096) or (large_fft and 8192 and Linear) or (spec_parity and (22k05 or 192k or 4096 or C3 or C4-mel))" 2>&1 | tail -12
-echo "== racecheck"
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 99 --print-limit 5 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-  -k "(spec_parity and (22k05 or 96k or C4-mel or C3-mel))" 2>&1 | tail -12
-} > gpurun_out/sanitize.log 2>&1
-tail -30 gpurun_out/sanitize.log | cut -c1-220
+echo "== memcheck: tests -m gpu"
+timeout 3000 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 9 --target-processes all \
+  python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | grep -v "^=========\s*$" | tail -40
+echo "memcheck exit: ${PIPESTATUS[0]}"
+echo "== racecheck: frame-pair / warp / large-FFT kernels, tiles"
+timeout 2400 compute-sanitizer --tool racecheck --error-exitcode 9 \
+  python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "spec_parity or odd_hop or large_fft or genuinely or spectrogram_tile or i16" 2>&1 | tail -25
+echo "racecheck exit: ${PIPESTATUS[0]}"
+} > gpurun_out/sanitize_${TAG}.log 2>&1
+tail -12 gpurun_out/sanitize_${TAG}.log
