@@ -506,12 +506,12 @@ int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB
     return THB_OK;
 }
 
-// which spec_to_img kernel a batch of descriptors may use (thb_kernels.cuh); THB_IMG_TILE=0|1|2 caps it (A/B runs)
+// which spec_to_img kernel a batch of descriptors may use (thb_kernels.cuh); THB_IMG_TILE=0|1|2|3 caps it (A/B runs)
 static int img_tile_mode(const thb::ImgDesc *h, size_t n) {
-    int mode = 2;
+    int mode = 3;
     for (size_t i = 0; i < n; i++) {
         if ((h[i].pitch & 1) || (reinterpret_cast<uintptr_t>(h[i].img) & 3)) return 0;
-        if ((h[i].B & 3) || (h[i].i0 & 3) || (reinterpret_cast<uintptr_t>(h[i].spec) & 15)) mode = 1;
+        if ((h[i].B & 3) || (h[i].i0 & 3) || (reinterpret_cast<uintptr_t>(h[i].spec) & 15)) mode = std::min(mode, 1);
     }
     if (const char *e = getenv("THB_IMG_TILE")) mode = std::min(mode, atoi(e));
     return mode < 0 ? 0 : mode;

@@ -126,13 +126,39 @@ __device__ __forceinline__ uint32_t quantise_dB(float v, float dB_min, float spa
     return (r != r) ? 0u : static_cast<uint32_t>(fminf(fmaxf(r, 0.0f), 65535.0f));  // clamp, `as u16`; NaN -> 0
 }
 
+// The same quantiser with the division by the (launch-uniform) span replaced by Markstein's sequence on its correctly
+// rounded reciprocal y = RN(1 / span):
+//     q0 = RN(a y);  r0 = a - span q0 (exact, one FMA);  q1 = RN(q0 + r0 y)       -> q1 is a faithful quotient
+//     r1 = a - span q1 (exact);                           q  = RN(q1 + r1 y)       -> q == RN(a / span)
+// (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, "division with an FMA": with y the correctly
+// rounded reciprocal and q1 faithful, the last step yields the correctly rounded quotient when nothing over- or
+// underflows.)  One FMUL + four FFMA instead of __fdiv_rn's reciprocal refinement + range check + slow path, and the
+// pixel is still the reference's bit for bit.  The caller guarantees 2^-60 < span < 2^60 (else the plain kernel runs);
+// |a| >= 1e30 (incl. +-inf, NaN) takes a y alone: far outside the image range, it clamps -- or stays NaN -- exactly like
+// the true quotient.  round(): trunc + compare, exact for every x that survives the clamp to [0, 65535]
+// (x < 0 ends at <= 0, NaN at 0 through fmaxf, like f32::round followed by the reference's clamp and `as u16`).
+__device__ __forceinline__ uint32_t quantise_dB_rcp(float v, float dB_min, float span, float y, float u16_span, float min_value_f) {
+    const float a = __fsub_rn(v, dB_min);
+    const float q0 = __fmul_rn(a, y);
+    const float r0 = __fmaf_rn(-span, q0, a);
+    const float q1 = __fmaf_rn(r0, y, q0);
+    const float r1 = __fmaf_rn(-span, q1, a);
+    const float q2 = __fmaf_rn(r1, y, q1);
+    const float zero_to_one = fabsf(a) < 1e30f ? q2 : q0;
+    const float scaled = __fadd_rn(__fmul_rn(zero_to_one, u16_span), min_value_f);
+    const float t = truncf(scaled);
+    const float r = (__fsub_rn(scaled, t) >= 0.5f) ? __fadd_rn(t, 1.0f) : t;
+    return static_cast<uint32_t>(fminf(fmaxf(r, 0.0f), 65535.0f));
+}
+
 // 128 (bins) x 128 (frames) tiles: a thread quantises 4 consecutive bins of 2 consecutive frames at a time (two
 // 16-byte loads when VEC), packs the two frames of a bin into one 32-bit word and parks it in a shared tile whose
 // columns are XOR-swizzled by the lane, so both the transposing stores and the row reads are conflict-free; image
 // rows leave as 128-byte warp stores.
 constexpr int kBigT = 128, kBigB = 128;
 
-template <bool VEC>
+// RCP: quantise_dB_rcp (the launcher checks the span)
+template <bool VEC, bool RCP>
 __global__ void __launch_bounds__(256) spec_to_img_tile_kernel(const ImgDesc *__restrict__ descs,
                                                                 const float *__restrict__ range, float min_value_f,
                                                                 float u16_span) {
@@ -144,6 +170,9 @@ __global__ void __launch_bounds__(256) spec_to_img_tile_kernel(const ImgDesc *__
     const float dB_min = range[0], dB_max = range[1];
     const bool all_zero = (dB_min == dB_max) && (dB_max == -CUDART_INF_F);
     const float span = __fsub_rn(dB_max, dB_min);
+    // RCP needs an ordinary span; anything else (a zero, huge or non-finite range) takes the plain division
+    const bool use_rcp = RCP && span > 8.6736174e-19f && span < 1.1529215e+18f;
+    const float y = use_rcp ? __frcp_rn(span) : 0.0f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = r0 + 4 * lane;      // first image row of this lane's 4 bins
     const int bin = d.i0 + row;
@@ -171,8 +200,14 @@ __global__ void __launch_bounds__(256) spec_to_img_tile_kernel(const ImgDesc *__
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t a = ok[0][j] ? quantise_dB(v[0][j], dB_min, span, u16_span, min_value_f) : 0u;
-            const uint32_t b = ok[1][j] ? quantise_dB(v[1][j], dB_min, span, u16_span, min_value_f) : 0u;
+            uint32_t a, b;
+            if (use_rcp) {
+                a = ok[0][j] ? quantise_dB_rcp(v[0][j], dB_min, span, y, u16_span, min_value_f) : 0u;
+                b = ok[1][j] ? quantise_dB_rcp(v[1][j], dB_min, span, y, u16_span, min_value_f) : 0u;
+            } else {
+                a = ok[0][j] ? quantise_dB(v[0][j], dB_min, span, u16_span, min_value_f) : 0u;
+                b = ok[1][j] ? quantise_dB(v[1][j], dB_min, span, u16_span, min_value_f) : 0u;
+            }
             tile[4 * lane + j][fp ^ lane] = a | (b << 16);
         }
     }
@@ -239,16 +274,19 @@ cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, i
     uint32_t min_value = static_cast<uint32_t>(r);
     if (min_value < 1) min_value = 1;
     const float u16_span = static_cast<float>(65535u - min_value);
-    // tile_mode: 0 = small tiles (any layout), 1 = big tiles, 2 = big tiles with 16-byte loads
+    // tile_mode: 0 = small tiles (any layout), 1 = big tiles, 2 = big tiles with 16-byte loads, 3 = as 2 with the
+    // reciprocal-based exact quotient
     const unsigned gx = static_cast<unsigned>(tile_mode ? (max_T + kBigT - 1) / kBigT : (max_T + kTileT - 1) / kTileT);
     const unsigned gy = static_cast<unsigned>(tile_mode ? (max_H + kBigB - 1) / kBigB : (max_H + kTileB - 1) / kTileB);
     for (int t0 = 0; t0 < n; t0 += 65535) {
         const int nt = n - t0 < 65535 ? n - t0 : 65535;
         dim3 grid(gx, gy, static_cast<unsigned>(nt));
-        if (tile_mode == 2)
-            spec_to_img_tile_kernel<true><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        if (tile_mode == 3)
+            spec_to_img_tile_kernel<true, true><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+        else if (tile_mode == 2)
+            spec_to_img_tile_kernel<true, false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
         else if (tile_mode == 1)
-            spec_to_img_tile_kernel<false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
+            spec_to_img_tile_kernel<false, false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
         else
             spec_to_img_kernel<<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
         cudaError_t e = cudaGetLastError();

@@ -349,7 +349,7 @@ int pair_warps() {
     // THB_PAIR_WARPS = 8 | 10 | 12 (tuning knob; registers per thread follow from it)
     const char *e = getenv("THB_PAIR_WARPS");
     const int w = e ? atoi(e) : 12;
-    return (w == 8 || w == 10 || w == 12) ? w : 12;
+    return (w == 8 || w == 10 || w == 12 || w == 14 || w == 16) ? w : 12;
 }
 
 template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true, bool PL = false>
@@ -397,7 +397,7 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
     }
     // THB_PAIR_SHARE=0 turns the shared-load variants off (A/B runs)
     const char *se = getenv("THB_PAIR_SHARE");
-    const bool share = !(se && atoi(se) == 0) && nw == 12;
+    const bool share = !(se && atoi(se) == 0) && nw >= 12;
     if (share && plan.hop == 512) {
         // THB_MEL4=0: the mel walk / gather with remainder code and 16-bit slot ids (A/B runs; same results)
         const char *m4 = getenv("THB_MEL4");
@@ -405,6 +405,9 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
         // THB_PAIR_PL=1: software-pipelined PCM loads (A/B runs)
         const char *pl = getenv("THB_PAIR_PL");
         if (plan.n_mel && pl && atoi(pl) == 1) return launch_nw<true, 12, false, 8, true, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        // THB_PAIR_WARPS=14 | 16: more warps on fewer registers (144 / 128: the DFT state spills) -- occupancy experiment
+        if (plan.n_mel && nw == 14) return launch_nw<true, 14, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+        if (plan.n_mel && nw == 16) return launch_nw<true, 16, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         if (plan.n_mel) return launch_nw<true, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
