@@ -99,18 +99,24 @@ void prof_collect(thb_ctx *ctx) {
 
 // ---- descriptor arena --------------------------------------------------------------------------
 int arena_begin(thb_ctx *ctx, size_t need) {
-    CK(cudaEventSynchronize(ctx->arena_ev));  // previous upload has been consumed by the copy engine
-    if (need > ctx->arena_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
-        if (ctx->d_arena) cudaFree(ctx->d_arena);
-        ctx->h_arena = ctx->d_arena = nullptr;
+    ctx->arena_idx = (ctx->arena_idx + 1) % thb_ctx::kArenas;
+    thb_ctx::Arena &a = ctx->arenas[ctx->arena_idx];
+    if (!a.ev) CK(cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(a.ev));  // the upload made from this mirror four calls ago has been consumed by the copy engine
+    if (need > a.cap) {
+        CK(cudaStreamSynchronize(ctx->stream));  // a queued kernel may still read the device copy
+        if (a.h) cudaFreeHost(a.h);
+        if (a.d) cudaFree(a.d);
+        a.h = a.d = nullptr;
+        a.cap = 0;
         size_t cap = 1 << 16;
         while (cap < need) cap <<= 1;
-        CK(cudaMallocHost(&ctx->h_arena, cap));
-        CK(cudaMalloc(&ctx->d_arena, cap));
-        ctx->arena_cap = cap;
+        CK(cudaMallocHost(reinterpret_cast<void **>(&a.h), cap));
+        CK(cudaMalloc(reinterpret_cast<void **>(&a.d), cap));
+        a.cap = cap;
     }
+    ctx->h_arena = a.h;
+    ctx->d_arena = a.d;
     ctx->arena_used = 0;
     return THB_OK;
 }
@@ -118,7 +124,7 @@ int arena_commit(thb_ctx *ctx) {
     if (ctx->arena_used) {
         CK(cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, ctx->arena_used, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaEventRecord(ctx->arena_ev, ctx->stream));
+    CK(cudaEventRecord(ctx->arenas[ctx->arena_idx].ev, ctx->stream));
     return THB_OK;
 }
 
@@ -427,7 +433,6 @@ int thb_ctx_create(int device, void *cuda_stream, thb_ctx **out) {
         ctx->own_stream = true;
     }
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->arena_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->h2d_ev, cudaEventDisableTiming);
     cudaMalloc(&ctx->d_send, sizeof(float) * 2);
     cudaMalloc(&ctx->d_range, sizeof(float) * 2);
@@ -469,9 +474,11 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     if (ctx->d_range) cudaFree(ctx->d_range);
     if (ctx->d_range_tmp) cudaFree(ctx->d_range_tmp);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
-    if (ctx->d_arena) cudaFree(ctx->d_arena);
-    if (ctx->arena_ev) cudaEventDestroy(ctx->arena_ev);
+    for (thb_ctx::Arena &a : ctx->arenas) {
+        if (a.h) cudaFreeHost(a.h);
+        if (a.d) cudaFree(a.d);
+        if (a.ev) cudaEventDestroy(a.ev);
+    }
     if (ctx->h2d_ev) cudaEventDestroy(ctx->h2d_ev);
     for (cudaEvent_t ev : ctx->stage_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -126,10 +126,19 @@ struct thb_ctx {
     float *d_range_tmp = nullptr;
     float *h_pinned = nullptr;  // small pinned scratch (64 floats)
 
-    // descriptor arena: pinned host mirror + device copy, re-used call after call (writers only)
-    unsigned char *h_arena = nullptr, *d_arena = nullptr;
-    size_t arena_cap = 0, arena_used = 0;
-    cudaEvent_t arena_ev = nullptr;
+    // descriptor arenas: pinned host mirror + device copy (writers only).  A ring of four: a call fills the next one
+    // while the uploads of the previous calls may still be queued behind their kernels, so a host that queues steps
+    // back to back (thb_update_spec_imgs without a host round trip) is never held up by its own previous step.
+    static constexpr int kArenas = 4;
+    struct Arena {
+        unsigned char *h = nullptr, *d = nullptr;
+        size_t cap = 0;
+        cudaEvent_t ev = nullptr;  // recorded after the upload: the pinned mirror may be rewritten once it has passed
+    };
+    Arena arenas[kArenas];
+    int arena_idx = 0;
+    unsigned char *h_arena = nullptr, *d_arena = nullptr;  // the current one
+    size_t arena_used = 0;
     cudaEvent_t h2d_ev = nullptr;
     std::vector<cudaEvent_t> stage_ev;  // one per H2D pipeline stage of thb_spec_batch
 

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Worker of tests/test_gpu_multi.py (run under torch.distributed.run, one rank per GPU, NCCL).
 
-Every rank analyses its shard (channels dealt by sample count, the long file split by FRAME RANGE with the PCM
-slice its frames touch), then thb_update_spec_imgs reduces the global dB range with the library's one
+Every rank analyses its shard (thesia_b200.sharding.plan: one contiguous span of the frame line per rank, a file that
+straddles a cut split by FRAME RANGE with the PCM slice its frames touch), then thb_update_spec_imgs reduces the global dB range with the library's one
 ncclAllReduce(max) of {max, -min}.  Rank 0 also runs the whole job alone on its GPU (no communicator) and every
 rank compares: identical global range, identical dB values and u16 images for each of its shards.
 """
@@ -47,7 +47,8 @@ def main():
         tracks = []
         for k, u in enumerate(units):
             w = wavs[(u.id, u.ch)]
-            tracks.append(dict(pcm=np.ascontiguousarray(w[u.pcm_lo:u.pcm_hi]), id=1000 * u.id + k, ch=u.ch, sr=SR,
+            # (the plan gives a rank at most one unit of any channel, so the file's own id is a valid key)
+            tracks.append(dict(pcm=np.ascontiguousarray(w[u.pcm_lo:u.pcm_hi]), id=u.id, ch=u.ch, sr=SR,
                                full_len=u.full_len, pcm_offset=u.pcm_lo, frame_begin=u.frame_begin,
                                frame_count=u.frame_count))
         ctx.spec_batch(tracks, setting)
