@@ -401,7 +401,7 @@ def shard_check(torch, dist, ctx, solo, units, channels, framing, rank, dev, rng
             t_spec = torch.from_numpy(np.ascontiguousarray(spec)).to(dev) if rank == 0 else torch.empty((fc, B), dtype=torch.float32, device=dev)
             t_img = torch.from_numpy(np.ascontiguousarray(img).view(np.int16)).to(dev) if rank == 0 else torch.empty((H, fc), dtype=torch.int16, device=dev)
             dist.broadcast(t_spec, src=0)
-            dist.broadcast(t_img, src=0)
+            dist.broadcast(t_img.view(torch.uint8), src=0)   # (NCCL has no 16-bit integer type: the same bytes as u8)
             if rank == src_rank:
                 u = next(x for x in units if (x.id, x.ch) == (i, ch))
                 got = ctx.spec_read(i, ch)[fb - u.frame_begin:fb - u.frame_begin + fc]

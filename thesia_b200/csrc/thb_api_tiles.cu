@@ -217,9 +217,11 @@ static int get_tile_axis(thb_ctx *ctx, cudaStream_t st, uint32_t in_size, uint64
     d->precision = a.precision;
     d->first = UINT32_MAX;
     d->end = 0;
+    d->identity = a.n > 0;
     for (uint32_t o = 0; o < a.n; o++) {
         d->first = std::min(d->first, a.start[o]);
         d->end = std::max(d->end, a.start[o] + a.size[o]);
+        if (a.size[o] != 1 || a.start[o] != a.start[0] + o || a.w_t[o] != (int32_t(1) << a.precision)) d->identity = false;
     }
     CK(cudaMalloc(reinterpret_cast<void **>(&d->start), sizeof(unsigned) * a.n));
     CK(cudaMalloc(reinterpret_cast<void **>(&d->size), sizeof(unsigned) * a.n));
@@ -340,6 +342,8 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
         t.py = ays[k]->precision;
         t.tmp = d_tmp + tmp_off;
         t.out = d_out + out_off;
+        t.identity = axs[k]->identity && ays[k]->identity ? 1u : 0u;
+        t.x_first = axs[k]->first;
         tmp_off += (static_cast<size_t>(t.tmp_h) * t.width + 7) & ~size_t(7);
         out_off += static_cast<size_t>(t.width) * t.height * 4;
     }

@@ -156,6 +156,7 @@ struct thb_ctx {
         unsigned *start = nullptr, *size = nullptr;
         int *w = nullptr;
         unsigned n = 0, window = 0, precision = 0, first = 0, end = 0;
+        bool identity = false;  // every output pixel is one input pixel with weight 2^precision, starts consecutive
         AxisDev() = default;
         AxisDev(const AxisDev &) = delete;
         AxisDev &operator=(const AxisDev &) = delete;

@@ -109,6 +109,8 @@ struct TileDesc {
     unsigned px, py;          // fixed-point precisions
     uint16_t *tmp;            // (tmp_h, width)
     uint8_t *out;             // (height, width) RGBA, rows reversed
+    unsigned identity;        // both axes copy (one tap of weight 2^precision, consecutive starts): level 0 in x and y
+    unsigned x_first;         // identity: first image column of the tile
 };
 
 // sample `idx` of a channel's slice as f32: 16-bit PCM converts as s / 32768 (exact)

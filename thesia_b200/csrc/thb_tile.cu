@@ -28,6 +28,7 @@ constexpr int kTileRows = 8;
 
 __global__ void __launch_bounds__(kTileThreads) tile_horiz_kernel(const TileDesc *__restrict__ descs) {
     const TileDesc &d = descs[blockIdx.z];
+    if (d.identity) return;  // tile_identity_kernel's
     const unsigned width = d.width, tmp_h = d.tmp_h;
     const unsigned x = blockIdx.x * kTileThreads + threadIdx.x;
     const unsigned y0 = blockIdx.y * kTileRows;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_horiz_kernel(const TileDesc
 __global__ void __launch_bounds__(kTileThreads) tile_vert_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
                                                                  unsigned colors) {
     const TileDesc &d = descs[blockIdx.z];
+    if (d.identity) return;  // tile_identity_kernel's
     const unsigned width = d.width, height = d.height;
     const unsigned x = blockIdx.x * kTileThreads + threadIdx.x;
     const unsigned y0 = blockIdx.y * kTileRows;
@@ -85,6 +87,61 @@ __global__ void __launch_bounds__(kTileThreads) tile_vert_kernel(const TileDesc 
     }
 }
 
+// Level 0 in x and y: both resize passes are copies (one tap of weight 2^precision per output pixel: the fixed-point
+// convolution returns the input value exactly), so the tile is colormap[index(img[y_first + y][x_first + x])] written
+// with its rows reversed -- one pass, 2 bytes read and 4 written per pixel, no intermediate.  A thread takes two
+// neighbouring pixels of kIdRows rows (8-byte stores; 4-byte loads when the source happens to be aligned).
+constexpr int kIdRows = 4;
+__global__ void __launch_bounds__(kTileThreads) tile_identity_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
+                                                                     unsigned colors) {
+    __shared__ uchar4 cm[1024];
+    const TileDesc &d = descs[blockIdx.z];
+    if (!d.identity) return;
+    const unsigned width = d.width, height = d.height;
+    const unsigned x = 2 * (blockIdx.x * kTileThreads + threadIdx.x);
+    const unsigned y0 = blockIdx.y * kIdRows;
+    if (y0 >= height) return;
+    const bool cm_smem = colors <= 1024;
+    if (cm_smem) {
+        for (unsigned i = threadIdx.x; i < colors; i += kTileThreads) cm[i] = __ldg(colormap + i);
+        __syncthreads();
+    }
+    if (x >= width) return;
+    const unsigned rows = min(static_cast<unsigned>(kIdRows), height - y0);
+    const bool two = x + 1 < width;
+    const uint16_t *src = d.img + static_cast<size_t>(d.y_first + y0) * d.pitch + d.x_first + x;
+    uchar4 *out = reinterpret_cast<uchar4 *>(d.out);
+    const unsigned scale = colors - 1;
+    auto look = [&](unsigned v) -> uchar4 {
+        // render_tiles.rs:339-346: (value * (color_count - 1) + u16::MAX / 2) / u16::MAX
+        const unsigned ci = colors <= 1 ? 0u : static_cast<unsigned>((static_cast<unsigned long long>(v) * scale + 32767ull) / 65535ull);
+        return cm_smem ? cm[ci] : __ldg(colormap + ci);
+    };
+#pragma unroll
+    for (int r = 0; r < kIdRows; r++) {
+        if (static_cast<unsigned>(r) >= rows) break;
+        const uint16_t *s = src + static_cast<size_t>(r) * d.pitch;
+        unsigned v0, v1 = 0;
+        if (two && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
+            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(s));
+            v0 = w & 0xffffu;
+            v1 = w >> 16;
+        } else {
+            v0 = __ldg(s);
+            if (two) v1 = __ldg(s + 1);
+        }
+        uchar4 *o = out + static_cast<size_t>(height - 1 - (y0 + r)) * width + x;
+        const uchar4 c0 = look(v0);
+        if (two && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+            const uchar4 c1 = look(v1);
+            *reinterpret_cast<uint2 *>(o) = make_uint2(*reinterpret_cast<const unsigned *>(&c0), *reinterpret_cast<const unsigned *>(&c1));
+        } else {
+            o[0] = c0;
+            if (two) o[1] = look(v1);
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned max_w, unsigned max_h, unsigned max_tmp_h,
@@ -93,8 +150,13 @@ cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned ma
     const unsigned gx = (max_w + kTileThreads - 1) / kTileThreads;
     for (int c0 = 0; c0 < n; c0 += 65535) {
         const unsigned nc = static_cast<unsigned>(n - c0 < 65535 ? n - c0 : 65535);
-        tile_horiz_kernel<<<dim3(gx, (max_tmp_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0);
+        // (each kernel returns at once for the descriptors of the other kind)
+        tile_identity_kernel<<<dim3((max_w + 2 * kTileThreads - 1) / (2 * kTileThreads), (max_h + kIdRows - 1) / kIdRows, nc), kTileThreads, 0, st>>>(
+            d_descs + c0, d_colormap, colors);
         cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        tile_horiz_kernel<<<dim3(gx, (max_tmp_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0);
+        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         tile_vert_kernel<<<dim3(gx, (max_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0, d_colormap, colors);
         e = cudaGetLastError();

@@ -13,7 +13,8 @@ import thesia_b200 as thb
 from thesia_b200 import _lib
 
 sr, n, nch, nmel = 48000, 48000 * 600, 128, 128
-ctx = thb.Context(0, torch.cuda.current_stream().cuda_stream)
+_st = torch.cuda.Stream(); torch.cuda.set_stream(_st)
+ctx = thb.Context(0, _st.cuda_stream)
 s = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, nmel)
 hop, win, _ = s.calc_framing_params(sr)
 T = thb.n_frames(n, win, hop)

@@ -1,7 +1,8 @@
 import time, torch, numpy as np, sys
 sys.path.insert(0, '.')
 import thesia_b200 as thb
-ctx = thb.Context(0, torch.cuda.current_stream().cuda_stream)
+_st = torch.cuda.Stream(); torch.cuda.set_stream(_st)
+ctx = thb.Context(0, _st.cuda_stream)
 sr, n, nch = 48000, 48000*600, 128
 pcm = torch.empty((nch, n), dtype=torch.float32, device='cuda')
 for c in range(nch): ctx.synth_pcm(pcm[c], sr, c//2, c%2, 0)
