@@ -200,7 +200,9 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     std::vector<uint32_t> mi_blob;
     if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
         // (the large-FFT kernel walks the same bin-major schedule out of global memory)
-        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
+        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
+        // THB_MEL_DIRECT=0|1 pins the mel schedule of the n_fft <= 2048 kernels (A/B runs); default: the cheaper one
+        if (const char *e = getenv("THB_MEL_DIRECT")) mi.use_direct = mi.valid && d.n_fft <= 2048 && atoi(e) != 0;
         if (mi.valid) mi_blob = mi.blob();
         if (d.n_fft > 2048 && mi.valid) {
             // the large-FFT kernel keeps magnitudes (16 lead slots + reach) and two partial sums per slot in its FFT buffer
@@ -209,7 +211,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         }
     }
     if (!mi_blob.empty()) {
-        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel));
+        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
         d.mi_words = static_cast<int>(mi_blob.size());
         d.mi_groups = static_cast<int>(mi.n_groups);
         d.mi_min_start = mi.min_start;
@@ -569,7 +571,7 @@ int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t
 int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t stats[4]) {
     if (!out || !stats || n_fft < 4) return THB_ERR_INVALID;
     const thb::MelBank mb = thb::mel_bank(sr, n_fft, n_mel);
-    const thb::MelItems mi = thb::mel_items(mb);
+    const thb::MelItems mi = thb::mel_items(mb, 2, n_fft <= 2048);
     stats[0] = mi.valid ? 1u : 0u;
     stats[1] = mi.n_groups;
     stats[2] = stats[3] = 0;
@@ -600,6 +602,23 @@ int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *
                 if (off / 8 != mi.zero_slot) b4.push_back(off / 8);
             }
             if (a != b4) return THB_ERR_INTERNAL;
+        }
+    // the band-major schedule (n_fft <= 2048) must spell the same matrix: lane l of round r walks bins k0 + i with weight w[i][l]
+    for (size_t r = 0; r < mi.direct_L.size(); r++)
+        for (uint32_t l = 0; l < 32; l++) {
+            const size_t m = 32 * r + l;
+            for (uint32_t i = 0; i < mi.direct_L[r]; i++) {
+                const float w = mi.direct_w[mi.direct_woff[r] + static_cast<size_t>(i) * 32 + l];
+                const int64_t k = static_cast<int64_t>(mi.direct_k0[m < M ? m : 0]) + i;
+                if (m >= M) {
+                    if (w != 0.0f) return THB_ERR_INTERNAL;
+                    continue;
+                }
+                const float want = (k >= static_cast<int64_t>(mb.k0[m]) && k < static_cast<int64_t>(mb.k0[m] + (mb.ptr[m + 1] - mb.ptr[m])))
+                                       ? mb.w[mb.ptr[m] + static_cast<size_t>(k - mb.k0[m])] : 0.0f;
+                if (w != want) return THB_ERR_INTERNAL;
+            }
+            if (m < M && mi.direct_L[r] < mb.ptr[m + 1] - mb.ptr[m]) return THB_ERR_INTERNAL;
         }
     for (uint32_t g = 0; g < mi.n_groups; g++) {
         if (mi.T[g] % 2) return THB_ERR_INTERNAL;

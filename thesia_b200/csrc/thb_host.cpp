@@ -166,7 +166,7 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
     }
 }
 
-MelItems mel_items(const MelBank &b, uint32_t t_multiple) {
+MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
     MelItems it;
     const uint32_t tm = t_multiple < 2 ? 2 : t_multiple;  // the walk takes two steps per float4 of weights
     it.n_mel = b.n_mel;
@@ -378,12 +378,44 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple) {
             const uint32_t j = i - it.piece_ptr[m];
             it.goff4[(static_cast<size_t>(it.gbase4[m / 32]) + j / 4) * 128 + (m % 32) * 4 + j % 4] = it.piece_ids[i] * 8u;
         }
+    // ---- the band-major schedule and the choice between the two ----
+    if (!with_direct) {
+        it.valid = true;
+        return it;
+    }
+    it.direct_L.assign(n_rounds, 0);
+    it.direct_woff.assign(n_rounds, 0);
+    it.direct_k0.assign(static_cast<size_t>(n_rounds) * 32, 0);
+    uint32_t direct_steps = 0;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        uint32_t L = 0;
+        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
+        L = (L + 1) & ~1u;  // two steps per trip
+        it.direct_L[r] = L;
+        it.direct_woff[r] = static_cast<uint32_t>(it.direct_w.size());
+        it.direct_w.resize(it.direct_w.size() + static_cast<size_t>(L) * 32, 0.0f);
+        direct_steps += L;
+        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) {
+            it.direct_k0[m] = static_cast<int32_t>(b.k0[m]);
+            for (uint32_t i = b.ptr[m]; i < b.ptr[m + 1]; i++)
+                it.direct_w[it.direct_woff[r] + static_cast<size_t>(i - b.ptr[m]) * 32 + (m - 32 * r)] = b.w[i];
+            it.max_reach = std::max<uint32_t>(it.max_reach, b.k0[m] + L - 1);
+        }
+    }
+    // instructions per frame (pair), from the kernels' SASS: bin-major = 36 per group + 4.75 per step + per round
+    // 12 + 13 per row of four; band-major = 10 per round + 3.5 per step
+    uint32_t steps = 0, rows_of4 = 0;
+    for (uint32_t g = 0; g < it.n_groups; g++) steps += it.T[g];
+    for (uint32_t r = 0; r < n_rounds; r++) rows_of4 += it.gk4[r];
+    const double cost_bin = 36.0 * it.n_groups + 4.75 * steps + 12.0 * n_rounds + 13.0 * rows_of4;
+    const double cost_band = 10.0 * n_rounds + 3.5 * direct_steps;
+    it.use_direct = cost_band < cost_bin;
     it.valid = true;
     return it;
 }
 
 std::vector<uint32_t> MelItems::blob() const {
-    std::vector<uint32_t> o(12, 0);
+    std::vector<uint32_t> o(16, 0);
     auto align4 = [&]() {
         while (o.size() & 3) o.push_back(0);
     };
@@ -418,6 +450,24 @@ std::vector<uint32_t> MelItems::blob() const {
     align4();
     o[9] = static_cast<uint32_t>(o.size());
     o.insert(o.end(), goff4.begin(), goff4.end());
+    align4();
+    o[10] = use_direct ? 1u : 0u;
+    o[11] = static_cast<uint32_t>(o.size());  // {steps, absolute word offset of the round's weights} per round
+    const size_t dr_at = o.size();
+    for (size_t r = 0; r < direct_L.size(); r++) {
+        o.push_back(direct_L[r]);
+        o.push_back(direct_woff[r]);
+    }
+    align4();
+    o[12] = static_cast<uint32_t>(o.size());
+    for (int32_t v : direct_k0) o.push_back(static_cast<uint32_t>(v));
+    align4();
+    o[13] = static_cast<uint32_t>(o.size());
+    {
+        const uint32_t *dp = reinterpret_cast<const uint32_t *>(direct_w.data());
+        o.insert(o.end(), dp, dp + direct_w.size());
+    }
+    for (size_t r = 0; r < direct_L.size(); r++) o[dr_at + 2 * r + 1] += o[13];
     align4();
     o[7] = static_cast<uint32_t>(o.size());
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(w.data());

@@ -67,6 +67,14 @@ struct MelItems {
     // (slot * 8: float2 slots of the frame-pair kernel; the scalar kernel halves them), padded with the zero slot
     std::vector<uint32_t> gk4, gbase4;  // [rounds]: rows of 4, first row
     std::vector<uint32_t> goff4;        // [sum(gk4) * 32 * 4]
+    // Band-major alternative for banks of NARROW bands (the default banks: 257 - 404 bands of 2 - 50 bins): lane l of
+    // round r owns band 32 r + l and walks its own bins, direct_L[r] steps (the longest band of the round; shorter ones
+    // run on zero weights): no partial sums, no gather.  direct_w is step-major per round ([step][lane], coalesced).
+    // use_direct says which schedule costs fewer instructions for this bank (cost model in thb_host.cpp).
+    std::vector<uint32_t> direct_L, direct_woff;  // [rounds]
+    std::vector<int32_t> direct_k0;               // [rounds * 32] first bin of the lane's band
+    std::vector<float> direct_w;
+    bool use_direct = false;
     uint32_t zero_slot = 0;
     size_t w_index(uint32_t g, uint32_t t, uint32_t lane) const {
         return woff[g] + static_cast<size_t>(t / 2) * 128 + 4 * static_cast<size_t>(lane) + 2 * (t & 1);
@@ -80,7 +88,8 @@ struct MelItems {
 // t_multiple: every group's step count is a multiple of it (the walks take two steps per float4 of weights; padding
 // steps carry zero weights and add +0).  4 would spare the n_fft == 2048 walk its two-step tail but costs the default
 // banks (10 - 11 groups of 2 - 12 steps) 12 - 14 extra steps per frame pair: measured on the host, not adopted.
-MelItems mel_items(const MelBank &b, uint32_t t_multiple = 2);
+// with_direct: also build the band-major schedule (n_fft <= 2048 kernels) and choose between the two
+MelItems mel_items(const MelBank &b, uint32_t t_multiple = 2, bool with_direct = false);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

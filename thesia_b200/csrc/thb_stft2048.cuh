@@ -61,6 +61,9 @@ struct MelView {
     const uint16_t *goff;  // rows of 32 slot ids
     const uint2 *rounds4;  // {rows of four, first row of four} per 32 bands
     const uint4 *goff4;    // rows of 32 lanes x 4 byte offsets (float2 slots)
+    int direct;            // the band-major schedule is the cheaper one for this bank: mel_direct instead of walk + gather
+    const uint2 *drounds;  // {steps, word offset of the round's weights} per 32 bands
+    const int32_t *dk0;    // [rounds * 32] first bin of the lane's band
     __device__ __forceinline__ explicit MelView(const uint32_t *b) : base(b) {
         n_groups = static_cast<int>(b[0]);
         n_mel = static_cast<int>(b[1]);
@@ -70,6 +73,9 @@ struct MelView {
         goff = reinterpret_cast<const uint16_t *>(b + b[5]);
         rounds4 = reinterpret_cast<const uint2 *>(b + b[8]);
         goff4 = reinterpret_cast<const uint4 *>(b + b[9]);
+        direct = static_cast<int>(b[10]);
+        drounds = reinterpret_cast<const uint2 *>(b + b[11]);
+        dk0 = reinterpret_cast<const int32_t *>(b + b[12]);
     }
 };
 
@@ -199,6 +205,27 @@ __device__ __forceinline__ V mel_band4(const MelView &mv, const V *part, int r, 
         acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.y >> kShift)));
         acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.z >> kShift)));
         acc = O::add(acc, *reinterpret_cast<const V *>(pb + (o.w >> kShift)));
+    }
+    return acc;
+}
+
+// Band-major mel product for banks of narrow bands (MelItems::use_direct): lane l owns band 32 r + l and walks its own
+// bins in ascending order, rd.x steps (the round's longest band; shorter bands run on zero weights).
+template <typename V>
+__device__ __forceinline__ V mel_direct(const MelView &mv, const V *mag, int r, int lane) {
+    using O = MelOps<V>;
+    const uint2 rd = mv.drounds[r];
+    const float *w = reinterpret_cast<const float *>(mv.base + rd.y) + lane;
+    const V *mq = mag + mv.dk0[32 * r + lane];
+    V acc = O::zero();
+#pragma unroll 1
+    for (uint32_t i = 0; i < rd.x; i += 2) {
+        const float w0 = w[0], w1 = w[32];
+        const V m0 = mq[0], m1 = mq[1];
+        w += 64;
+        mq += 2;
+        acc = O::fma(m0, w0, acc);
+        acc = O::fma(m1, w1, acc);
     }
     return acc;
 }

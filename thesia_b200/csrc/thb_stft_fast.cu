@@ -277,11 +277,13 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                mel_walk4<float>(mv, mag, part, lane);
-                __syncwarp();
+                if (!mv.direct) {
+                    mel_walk4<float>(mv, mag, part, lane);
+                    __syncwarp();
+                }
                 for (int r = 0; 32 * r < mv.n_mel; r++) {
                     const int m = 32 * r + lane;
-                    const float acc = mel_band4<float>(mv, part, r, lane);
+                    const float acc = mv.direct ? mel_direct<float>(mv, mag, r, lane) : mel_band4<float>(mv, part, r, lane);
                     if (m >= mv.n_mel) continue;
                     // exact zero stays -inf; db_off only shifts finite values
                     const float db = fmaf(kDbPerLog2Amp, lg2_ftz(acc), db_off);

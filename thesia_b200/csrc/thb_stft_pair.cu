@@ -306,12 +306,15 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                if constexpr (M4) mel_walk4<float2>(mv, mag, part, lane);
-                else mel_walk<float2>(mv, mag, part, lane);
-                __syncwarp();
+                if (!mv.direct) {
+                    if constexpr (M4) mel_walk4<float2>(mv, mag, part, lane);
+                    else mel_walk<float2>(mv, mag, part, lane);
+                    __syncwarp();
+                }
                 for (int r = 0; 32 * r < mv.n_mel; r++) {
                     const int m = 32 * r + lane;
-                    const f2 acc = M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane);
+                    const f2 acc = mv.direct ? mel_direct<float2>(mv, mag, r, lane)
+                                             : (M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane));
                     if (m >= mv.n_mel) continue;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;

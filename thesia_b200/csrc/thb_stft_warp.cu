@@ -605,8 +605,10 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                 for (int g = 0; g < G; g++) {
                     const long long fg = f0 + static_cast<long long>(FPG) * g;
                     if (fg >= f_end) break;
-                    mel_walk4<V>(mv, mag0 + g * mag_stride, part, lane);
-                    __syncwarp();
+                    if (!mv.direct) {
+                        mel_walk4<V>(mv, mag0 + g * mag_stride, part, lane);
+                        __syncwarp();
+                    }
                     float *row0 = d.out + fg * p.n_bins;
                     float *row1 = d.out + min(fg + 1, f_end - 1) * p.n_bins;
                     const bool has1 = kPacked && fg + 1 < f_end;
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                     const float g_off = __shfl_sync(0xffffffffu, db_off, g * R1);
                     for (int r = 0; 32 * r < mv.n_mel; r++) {
                         const int m = 32 * r + lane;
-                        const V acc = mel_band4<V>(mv, part, r, lane);
+                        const V acc = mv.direct ? mel_direct<V>(mv, mag0 + g * mag_stride, r, lane) : mel_band4<V>(mv, part, r, lane);
                         if (m >= mv.n_mel) continue;
                         if constexpr (kPacked) {
                             const float2 db = O::muls(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), kDbPerLog2Amp);

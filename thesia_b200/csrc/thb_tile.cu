@@ -90,54 +90,58 @@ __global__ void __launch_bounds__(kTileThreads) tile_vert_kernel(const TileDesc 
 // Level 0 in x and y: both resize passes are copies (one tap of weight 2^precision per output pixel: the fixed-point
 // convolution returns the input value exactly), so the tile is colormap[index(img[y_first + y][x_first + x])] written
 // with its rows reversed -- one pass, 2 bytes read and 4 written per pixel, no intermediate.  A thread takes two
-// neighbouring pixels of kIdRows rows (8-byte stores; 4-byte loads when the source happens to be aligned).
-constexpr int kIdRows = 4;
+// neighbouring pixels of kIdRows rows and strides over the tile's width (8-byte stores; 4-byte loads when the source
+// happens to be aligned); a CTA covers kIdRows whole rows of one tile.
+constexpr int kIdRows = 8;
 __global__ void __launch_bounds__(kTileThreads) tile_identity_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
                                                                      unsigned colors) {
-    __shared__ uchar4 cm[1024];
-    const TileDesc &d = descs[blockIdx.z];
+    const TileDesc &d = descs[blockIdx.y];
     if (!d.identity) return;
     const unsigned width = d.width, height = d.height;
-    const unsigned x = 2 * (blockIdx.x * kTileThreads + threadIdx.x);
-    const unsigned y0 = blockIdx.y * kIdRows;
+    const unsigned y0 = blockIdx.x * kIdRows;
     if (y0 >= height) return;
-    const bool cm_smem = colors <= 1024;
-    if (cm_smem) {
-        for (unsigned i = threadIdx.x; i < colors; i += kTileThreads) cm[i] = __ldg(colormap + i);
-        __syncthreads();
-    }
-    if (x >= width) return;
     const unsigned rows = min(static_cast<unsigned>(kIdRows), height - y0);
-    const bool two = x + 1 < width;
-    const uint16_t *src = d.img + static_cast<size_t>(d.y_first + y0) * d.pitch + d.x_first + x;
+    const size_t pitch = d.pitch;
+    const uint16_t *src0 = d.img + static_cast<size_t>(d.y_first + y0) * pitch + d.x_first;
     uchar4 *out = reinterpret_cast<uchar4 *>(d.out);
     const unsigned scale = colors - 1;
-    auto look = [&](unsigned v) -> uchar4 {
+    // the colormap (about 1 KB) is read through L1: no per-block staging, no barrier
+    auto look = [&](unsigned v) -> unsigned {
         // render_tiles.rs:339-346: (value * (color_count - 1) + u16::MAX / 2) / u16::MAX
-        const unsigned ci = colors <= 1 ? 0u : static_cast<unsigned>((static_cast<unsigned long long>(v) * scale + 32767ull) / 65535ull);
-        return cm_smem ? cm[ci] : __ldg(colormap + ci);
+        const unsigned ci = colors <= 1 ? 0u : (v * scale + 32767u) / 65535u;   // < 2^32: v, scale < 2^16
+        return __ldg(reinterpret_cast<const unsigned *>(colormap) + ci);
     };
+    const bool big_map = colors > 65536u;  // (index arithmetic above needs colors - 1 < 2^16; larger maps take 64 bits)
+    for (unsigned x = 2 * threadIdx.x; x < width; x += 2 * kTileThreads) {
+        const bool two = x + 1 < width;
 #pragma unroll
-    for (int r = 0; r < kIdRows; r++) {
-        if (static_cast<unsigned>(r) >= rows) break;
-        const uint16_t *s = src + static_cast<size_t>(r) * d.pitch;
-        unsigned v0, v1 = 0;
-        if (two && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
-            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(s));
-            v0 = w & 0xffffu;
-            v1 = w >> 16;
-        } else {
-            v0 = __ldg(s);
-            if (two) v1 = __ldg(s + 1);
-        }
-        uchar4 *o = out + static_cast<size_t>(height - 1 - (y0 + r)) * width + x;
-        const uchar4 c0 = look(v0);
-        if (two && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
-            const uchar4 c1 = look(v1);
-            *reinterpret_cast<uint2 *>(o) = make_uint2(*reinterpret_cast<const unsigned *>(&c0), *reinterpret_cast<const unsigned *>(&c1));
-        } else {
-            o[0] = c0;
-            if (two) o[1] = look(v1);
+        for (int r = 0; r < kIdRows; r++) {
+            if (static_cast<unsigned>(r) >= rows) break;
+            const uint16_t *s = src0 + static_cast<size_t>(r) * pitch + x;
+            unsigned v0, v1 = 0;
+            if (two && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
+                const unsigned w = __ldg(reinterpret_cast<const unsigned *>(s));
+                v0 = w & 0xffffu;
+                v1 = w >> 16;
+            } else {
+                v0 = __ldg(s);
+                if (two) v1 = __ldg(s + 1);
+            }
+            unsigned c0, c1 = 0;
+            if (big_map) {
+                c0 = __ldg(reinterpret_cast<const unsigned *>(colormap) + static_cast<unsigned>((static_cast<unsigned long long>(v0) * scale + 32767ull) / 65535ull));
+                if (two) c1 = __ldg(reinterpret_cast<const unsigned *>(colormap) + static_cast<unsigned>((static_cast<unsigned long long>(v1) * scale + 32767ull) / 65535ull));
+            } else {
+                c0 = look(v0);
+                if (two) c1 = look(v1);
+            }
+            unsigned *o = reinterpret_cast<unsigned *>(out + static_cast<size_t>(height - 1 - (y0 + r)) * width + x);
+            if (two && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+                *reinterpret_cast<uint2 *>(o) = make_uint2(c0, c1);
+            } else {
+                o[0] = c0;
+                if (two) o[1] = c1;
+            }
         }
     }
 }
@@ -151,8 +155,7 @@ cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned ma
     for (int c0 = 0; c0 < n; c0 += 65535) {
         const unsigned nc = static_cast<unsigned>(n - c0 < 65535 ? n - c0 : 65535);
         // (each kernel returns at once for the descriptors of the other kind)
-        tile_identity_kernel<<<dim3((max_w + 2 * kTileThreads - 1) / (2 * kTileThreads), (max_h + kIdRows - 1) / kIdRows, nc), kTileThreads, 0, st>>>(
-            d_descs + c0, d_colormap, colors);
+        tile_identity_kernel<<<dim3((max_h + kIdRows - 1) / kIdRows, nc), kTileThreads, 0, st>>>(d_descs + c0, d_colormap, colors);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         tile_horiz_kernel<<<dim3(gx, (max_tmp_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0);

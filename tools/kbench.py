@@ -53,13 +53,15 @@ def main():
         name, _, nw = head.partition(":")
         os.environ["THB_STFT_KERNEL"] = name
         os.environ.pop("THB_PAIR_WARPS", None)
-        for k in ("THB_PAIR_PREFETCH", "THB_MEL4", "THB_PAIR_SHARE"):
+        for k in ("THB_PAIR_PREFETCH", "THB_MEL4", "THB_PAIR_SHARE", "THB_PAIR_PL", "THB_MEL_DIRECT"):
             os.environ.pop(k, None)
         for kv in envs:
             k, _, v = kv.partition("=")
             os.environ[k] = v
         if nw:
             os.environ["THB_PAIR_WARPS"] = nw
+        base = ctx
+        ctx = thb.Context(0, stream.cuda_stream)  # a fresh plan cache: some switches act when a plan is built
         ctx.spec_batch(tracks, setting)  # warm-up
         ctx.synchronize()
         ctx.profile_enable(True)
@@ -72,6 +74,8 @@ def main():
         ctx.profile_enable(False)
         ms /= a.reps  # the scope covers every launch of one spec_batch call
         out = ctx.spec_read(0, 0)
+        ctx.close()
+        ctx = base
         if ref is None:
             ref = out
             diff = 0.0
