@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define THB_ABI_VERSION 4
+#define THB_ABI_VERSION 5
 
 typedef enum thb_status {
     THB_OK = 0,
@@ -170,6 +170,15 @@ int thb_release_all(thb_ctx *ctx);
  * for those sample rates -- what TrackManager does after remove_tracks / set_setting (mod.rs:96-99,110-112) -- and
  * reports how many are left. */
 int thb_plans_prepare(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n);
+/* Diagnostic: which STFT kernel family thb_spec_batch runs for (setting, sr) -- a plan whose tables outgrow a fast
+ * kernel's shared memory silently takes a slower one, and the tests pin the expected family of every BASELINE
+ * configuration.  *family: THB_KERNEL_GENERIC .. THB_KERNEL_WARP; *mel_schedule: 0 linear, 1 bin-major, 2 band-major. */
+#define THB_KERNEL_GENERIC 0u  /* thb_stft_generic.cu */
+#define THB_KERNEL_FAST 1u     /* n_fft 2048, scalar warp-per-frame only */
+#define THB_KERNEL_PAIR 2u     /* n_fft 2048, packed frame pairs + scalar twin */
+#define THB_KERNEL_BIG 3u      /* n_fft 1024 / 4096 / 8192 / 16384, one frame pair per CTA */
+#define THB_KERNEL_WARP 4u     /* n_fft 1024 / 512, packed frame pairs + scalar twin */
+int thb_plan_kernel(thb_ctx *ctx, const thb_setting *setting, uint32_t sr, uint32_t *family, uint32_t *mel_schedule);
 int thb_plans_retain(thb_ctx *ctx, const thb_setting *setting, const uint32_t *srs, size_t n, size_t *n_left);
 
 /* ---- TrackManager::update_spec_imgs (mod.rs:168-230) ----------------------------------------

@@ -177,3 +177,33 @@ def test_spectrogram_tiles_from_concurrent_threads(ctx, orc):
         th.join()
     assert not bad, bad[:4]
     ctx.release_all()
+
+
+def test_every_baseline_configuration_runs_on_its_fast_kernel(ctx):
+    """A plan whose tables outgrow a kernel's shared memory silently falls back to a slower kernel (it happened once,
+    when a second mel schedule was stored next to the first: 6x).  Pin the family and the mel schedule of BASELINE's
+    configurations and of the reference's default setting at its fixture rates."""
+    F = thb.FreqScale
+    PAIR, BIG, WARP = 2, 3, 4
+    cases = [
+        (thb.SpecSetting(2048 / 48.0, 4, 1, F.Linear), 48000, PAIR, 0),          # C1
+        (thb.SpecSetting(2048 / 48.0, 8, 1, F.Mel, 128), 48000, PAIR, 1),        # C2: wide bands -> bin-major
+        (thb.SpecSetting(2048 / 48.0, 8, 1, F.Mel, 0), 48000, PAIR, None),       # C2, default bank
+        (thb.SpecSetting(2048 / 48.0, 4, 1, F.Mel, 128), 48000, PAIR, 1),        # C3
+        (thb.SpecSetting(), 48000, PAIR, None),                                  # the reference's default setting
+        (thb.SpecSetting(), 44100, PAIR, None),
+        (thb.SpecSetting(), 24000, WARP, None),
+        (thb.SpecSetting(), 22050, WARP, None),
+        (thb.SpecSetting(), 16000, WARP, None),
+        (thb.SpecSetting(), 8000, WARP, None),
+        (thb.SpecSetting(), 96000, BIG, None),
+        (thb.SpecSetting(16384 / 96.0, 16, 1, F.Linear), 96000, BIG, 0),         # C4
+        (thb.SpecSetting(16384 / 96.0, 16, 1, F.Mel, 0), 96000, BIG, 1),
+    ]
+    for s, sr, fam, sch in cases:
+        got = ctx.plan_kernel(s, sr)
+        assert got[0] == fam, (sr, s, got)
+        if sch is not None:
+            assert got[1] == sch, (sr, s, got)
+        elif s.freq_scale == F.Mel:
+            assert got[1] in (1, 2)

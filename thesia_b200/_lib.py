@@ -105,6 +105,7 @@ SIGNATURES = {
     "thb_release": (_i, [_vp, _u64, _u32]),
     "thb_release_all": (_i, [_vp]),
     "thb_plans_prepare": (_i, [_vp, _P(Setting), _P(_u32), C.c_size_t]),
+    "thb_plan_kernel": (_i, [_vp, _P(Setting), _u32, _P(_u32), _P(_u32)]),
     "thb_plans_retain": (_i, [_vp, _P(Setting), _P(_u32), C.c_size_t, _P(C.c_size_t)]),
     "thb_minmax_global": (_i, [_vp, _f32, _P(_f32), _P(_f32)]),
     "thb_spec_to_img": (_i, [_vp, _u64, _u32, _u64, _u64, _f32, _f32, _u32, _vp, _u64]),
@@ -159,7 +160,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.thb_abi_version() != 4:
+        if l.thb_abi_version() != 5:
             raise RuntimeError("libthesia_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -328,6 +328,12 @@ class Context:
         ids, n_ids = self._ids(only_ids)
         check(lib().thb_update_spec_imgs_range(self._h, dB_range[0], dB_range[1], colormap_length, max_sr, ids, n_ids), self._h)
 
+    def plan_kernel(self, setting: SpecSetting, sr: int) -> Tuple[int, int]:
+        """thb_plan_kernel: (kernel family, mel schedule) thb_spec_batch uses for (setting, sr)."""
+        fam, sch = C.c_uint32(), C.c_uint32()
+        check(lib().thb_plan_kernel(self._h, C.byref(setting._c()), sr, C.byref(fam), C.byref(sch)), self._h)
+        return fam.value, sch.value
+
     def range_get(self) -> Tuple[float, float]:
         a, b = C.c_float(), C.c_float()
         check(lib().thb_range_get(self._h, C.byref(a), C.byref(b)), self._h)

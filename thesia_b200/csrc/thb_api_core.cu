@@ -211,11 +211,13 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         }
     }
     if (!mi_blob.empty()) {
-        const thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
+        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
+        if (const char *e = getenv("THB_MEL_DIRECT")) mi.use_direct = mi.valid && d.n_fft <= 2048 && atoi(e) != 0;
         d.mi_words = static_cast<int>(mi_blob.size());
-        d.mi_groups = static_cast<int>(mi.n_groups);
-        d.mi_min_start = mi.min_start;
-        d.mi_max_reach = static_cast<int>(mi.max_reach);
+        // the band-major schedule keeps no partial sums (no groups) and starts at the bands' own first bins
+        d.mi_groups = mi.use_direct ? 0 : static_cast<int>(mi.n_groups);
+        d.mi_min_start = mi.use_direct ? 0 : mi.min_start;
+        d.mi_max_reach = static_cast<int>(mi.use_direct ? mi.direct_reach : mi.max_reach);
         if ((rc = upload(ctx, pl.get(), mi_blob, &d.mi_blob))) return rc;
     }
     d.big_wpad = nullptr;
@@ -666,6 +668,25 @@ int thb_plans_prepare(thb_ctx *ctx, const thb_setting *setting, const uint32_t *
         int rc = get_plan(ctx, *setting, srs[i], &pl);
         if (rc) return rc;
     }
+    return THB_OK;
+}
+
+int thb_plan_kernel(thb_ctx *ctx, const thb_setting *setting, uint32_t sr, uint32_t *family, uint32_t *mel_schedule) {
+    if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
+    if (!setting || !family) return fail(ctx, THB_ERR_INVALID, "bad argument");
+    WriteLock lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const Plan *pl = nullptr;
+    int rc = get_plan(ctx, *setting, sr, &pl);
+    if (rc) return rc;
+    const thb::PlanDev &pd = pl->dev;
+    // the order of thb_spec_batch (thb_api_spec.cu)
+    if (thb::stft_pair_supported(pd) && thb::stft_fast_supported(pd)) *family = THB_KERNEL_PAIR;
+    else if (thb::stft_warp_supported(pd)) *family = THB_KERNEL_WARP;
+    else if (thb::stft_big_supported(pd)) *family = THB_KERNEL_BIG;
+    else if (thb::stft_fast_supported(pd)) *family = THB_KERNEL_FAST;
+    else *family = THB_KERNEL_GENERIC;
+    if (mel_schedule) *mel_schedule = !pd.n_mel ? 0u : (pd.mi_blob && pd.mi_groups == 0 ? 2u : 1u);
     return THB_OK;
 }
 

@@ -399,7 +399,7 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
             it.direct_k0[m] = static_cast<int32_t>(b.k0[m]);
             for (uint32_t i = b.ptr[m]; i < b.ptr[m + 1]; i++)
                 it.direct_w[it.direct_woff[r] + static_cast<size_t>(i - b.ptr[m]) * 32 + (m - 32 * r)] = b.w[i];
-            it.max_reach = std::max<uint32_t>(it.max_reach, b.k0[m] + L - 1);
+            it.direct_reach = std::max<uint32_t>(it.direct_reach, b.k0[m] + L - 1);
         }
     }
     // instructions per frame (pair), from the kernels' SASS: bin-major = 36 per group + 4.75 per step + per round
@@ -415,64 +415,77 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
 }
 
 std::vector<uint32_t> MelItems::blob() const {
+    // header: {n_groups, n_mel, off_groups, off_start, off_rounds, off_goff, zero_slot, off_w,
+    //          off_rounds4, off_goff4, use_direct, off_drounds, off_dk0, off_dw, 0, 0}
+    // Only the arrays of the schedule in use are stored (the blob lives in shared memory next to the warps' tiles).
     std::vector<uint32_t> o(16, 0);
     auto align4 = [&]() {
         while (o.size() & 3) o.push_back(0);
     };
-    o[0] = n_groups;
+    const bool bin_major = !use_direct;
+    o[0] = bin_major ? n_groups : 0;
     o[1] = n_mel;
     o[6] = zero_slot;
+    o[10] = use_direct ? 1u : 0u;
     o[2] = static_cast<uint32_t>(o.size());  // {T, absolute word offset of the group's weights}
     const size_t grp_at = o.size();
-    for (uint32_t g = 0; g < n_groups; g++) {
-        o.push_back(T[g]);
-        o.push_back(woff[g]);
-    }
+    if (bin_major)
+        for (uint32_t g = 0; g < n_groups; g++) {
+            o.push_back(T[g]);
+            o.push_back(woff[g]);
+        }
     align4();
     o[3] = static_cast<uint32_t>(o.size());
-    for (int32_t v : start) o.push_back(static_cast<uint32_t>(v));
+    if (bin_major)
+        for (int32_t v : start) o.push_back(static_cast<uint32_t>(v));
     align4();
     o[4] = static_cast<uint32_t>(o.size());  // {K, first row} per round of 32 bands
-    for (size_t r = 0; r < gk.size(); r++) {
-        o.push_back(gk[r]);
-        o.push_back(gbase[r]);
-    }
+    if (bin_major)
+        for (size_t r = 0; r < gk.size(); r++) {
+            o.push_back(gk[r]);
+            o.push_back(gbase[r]);
+        }
     align4();
     o[5] = static_cast<uint32_t>(o.size());
-    for (size_t i = 0; i + 1 < goff.size() + 1; i += 2)
-        o.push_back(static_cast<uint32_t>(goff[i]) | (static_cast<uint32_t>(i + 1 < goff.size() ? goff[i + 1] : 0) << 16));
+    if (bin_major)
+        for (size_t i = 0; i + 1 < goff.size() + 1; i += 2)
+            o.push_back(static_cast<uint32_t>(goff[i]) | (static_cast<uint32_t>(i + 1 < goff.size() ? goff[i + 1] : 0) << 16));
     align4();
     o[8] = static_cast<uint32_t>(o.size());  // {rows of four, first row of four} per round
-    for (size_t r = 0; r < gk4.size(); r++) {
-        o.push_back(gk4[r]);
-        o.push_back(gbase4[r]);
-    }
+    if (bin_major)
+        for (size_t r = 0; r < gk4.size(); r++) {
+            o.push_back(gk4[r]);
+            o.push_back(gbase4[r]);
+        }
     align4();
     o[9] = static_cast<uint32_t>(o.size());
-    o.insert(o.end(), goff4.begin(), goff4.end());
+    if (bin_major) o.insert(o.end(), goff4.begin(), goff4.end());
     align4();
-    o[10] = use_direct ? 1u : 0u;
     o[11] = static_cast<uint32_t>(o.size());  // {steps, absolute word offset of the round's weights} per round
     const size_t dr_at = o.size();
-    for (size_t r = 0; r < direct_L.size(); r++) {
-        o.push_back(direct_L[r]);
-        o.push_back(direct_woff[r]);
-    }
+    if (use_direct)
+        for (size_t r = 0; r < direct_L.size(); r++) {
+            o.push_back(direct_L[r]);
+            o.push_back(direct_woff[r]);
+        }
     align4();
     o[12] = static_cast<uint32_t>(o.size());
-    for (int32_t v : direct_k0) o.push_back(static_cast<uint32_t>(v));
+    if (use_direct)
+        for (int32_t v : direct_k0) o.push_back(static_cast<uint32_t>(v));
     align4();
     o[13] = static_cast<uint32_t>(o.size());
-    {
+    if (use_direct) {
         const uint32_t *dp = reinterpret_cast<const uint32_t *>(direct_w.data());
         o.insert(o.end(), dp, dp + direct_w.size());
+        for (size_t r = 0; r < direct_L.size(); r++) o[dr_at + 2 * r + 1] += o[13];
     }
-    for (size_t r = 0; r < direct_L.size(); r++) o[dr_at + 2 * r + 1] += o[13];
     align4();
     o[7] = static_cast<uint32_t>(o.size());
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(w.data());
-    o.insert(o.end(), wp, wp + w.size());
-    for (uint32_t g = 0; g < n_groups; g++) o[grp_at + 2 * g + 1] += o[7];
+    if (bin_major) {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(w.data());
+        o.insert(o.end(), wp, wp + w.size());
+        for (uint32_t g = 0; g < n_groups; g++) o[grp_at + 2 * g + 1] += o[7];
+    }
     align4();
     return o;
 }

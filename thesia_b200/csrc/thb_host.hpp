@@ -75,6 +75,7 @@ struct MelItems {
     std::vector<int32_t> direct_k0;               // [rounds * 32] first bin of the lane's band
     std::vector<float> direct_w;
     bool use_direct = false;
+    uint32_t direct_reach = 0;                    // largest bin index the band-major walk reads
     uint32_t zero_slot = 0;
     size_t w_index(uint32_t g, uint32_t t, uint32_t lane) const {
         return woff[g] + static_cast<size_t>(t / 2) * 128 + 4 * static_cast<size_t>(lane) + 2 * (t & 1);
