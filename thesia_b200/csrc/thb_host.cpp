@@ -390,7 +390,7 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
     for (uint32_t r = 0; r < n_rounds; r++) {
         uint32_t L = 0;
         for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
-        L = (L + 1) & ~1u;  // two steps per trip
+        L = (L + 3) & ~3u;  // four steps per trip
         it.direct_L[r] = L;
         it.direct_woff[r] = static_cast<uint32_t>(it.direct_w.size());
         it.direct_w.resize(it.direct_w.size() + static_cast<size_t>(L) * 32, 0.0f);
@@ -402,14 +402,17 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
             it.direct_reach = std::max<uint32_t>(it.direct_reach, b.k0[m] + L - 1);
         }
     }
-    // instructions per frame (pair), from the kernels' SASS: bin-major = 36 per group + 4.75 per step + per round
-    // 12 + 13 per row of four; band-major = 10 per round + 3.5 per step
+    // Cost of a frame pair in issue slots.  bin-major, from the kernels' SASS: 36 per group + 4.75 per step + per round
+    // 12 + 13 per row of four gather entries.  band-major: 10 per round + 5 per step -- the walk is one short dependent
+    // chain per lane, so a step costs more than its 3.5 instructions (measured on B200, DESIGN.md section 4: 8.6 per step
+    // before the walk took four steps per trip).  The band-major schedule is chosen only when it is clearly cheaper: a
+    // bank of WIDE bands (mel 128 at 48 kHz: up to 64 bins per band, one lane each) is 13 % slower on it.
     uint32_t steps = 0, rows_of4 = 0;
     for (uint32_t g = 0; g < it.n_groups; g++) steps += it.T[g];
     for (uint32_t r = 0; r < n_rounds; r++) rows_of4 += it.gk4[r];
     const double cost_bin = 36.0 * it.n_groups + 4.75 * steps + 12.0 * n_rounds + 13.0 * rows_of4;
-    const double cost_band = 10.0 * n_rounds + 3.5 * direct_steps;
-    it.use_direct = cost_band < cost_bin;
+    const double cost_band = 10.0 * n_rounds + 5.0 * direct_steps;
+    it.use_direct = cost_band < 0.75 * cost_bin;
     it.valid = true;
     return it;
 }

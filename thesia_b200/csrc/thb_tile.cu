@@ -89,12 +89,12 @@ __global__ void __launch_bounds__(kTileThreads) tile_vert_kernel(const TileDesc 
 
 // Level 0 in x and y: both resize passes are copies (one tap of weight 2^precision per output pixel: the fixed-point
 // convolution returns the input value exactly), so the tile is colormap[index(img[y_first + y][x_first + x])] written
-// with its rows reversed -- one pass, 2 bytes read and 4 written per pixel, no intermediate.  A thread takes two
-// neighbouring pixels of kIdRows rows and strides over the tile's width (8-byte stores; 4-byte loads when the source
-// happens to be aligned); a CTA covers kIdRows whole rows of one tile.
-constexpr int kIdRows = 8;
-__global__ void __launch_bounds__(kTileThreads) tile_identity_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
-                                                                     unsigned colors) {
+// with its rows reversed -- one pass, 2 bytes read and 4 written per pixel, no intermediate.  A thread takes four
+// neighbouring pixels of kIdRows rows (8-byte loads and 16-byte stores when the addresses allow, which they do for
+// the 512-pixel tile grid with its 4-pixel gutter); a CTA covers kIdRows whole rows of one tile.
+constexpr int kIdRows = 8, kIdThreads = 160;   // 160 threads x 4 pixels cover a 520-pixel tile row in one pass
+__global__ void __launch_bounds__(kIdThreads) tile_identity_kernel(const TileDesc *__restrict__ descs, const uchar4 *__restrict__ colormap,
+                                                                   unsigned colors) {
     const TileDesc &d = descs[blockIdx.y];
     if (!d.identity) return;
     const unsigned width = d.width, height = d.height;
@@ -103,44 +103,33 @@ __global__ void __launch_bounds__(kTileThreads) tile_identity_kernel(const TileD
     const unsigned rows = min(static_cast<unsigned>(kIdRows), height - y0);
     const size_t pitch = d.pitch;
     const uint16_t *src0 = d.img + static_cast<size_t>(d.y_first + y0) * pitch + d.x_first;
-    uchar4 *out = reinterpret_cast<uchar4 *>(d.out);
+    unsigned *out = reinterpret_cast<unsigned *>(d.out);
+    const unsigned *cm = reinterpret_cast<const unsigned *>(colormap);   // about 1 KB, read through L1
     const unsigned scale = colors - 1;
-    // the colormap (about 1 KB) is read through L1: no per-block staging, no barrier
+    const bool small_map = colors <= 65536u;
     auto look = [&](unsigned v) -> unsigned {
-        // render_tiles.rs:339-346: (value * (color_count - 1) + u16::MAX / 2) / u16::MAX
-        const unsigned ci = colors <= 1 ? 0u : (v * scale + 32767u) / 65535u;   // < 2^32: v, scale < 2^16
-        return __ldg(reinterpret_cast<const unsigned *>(colormap) + ci);
+        // render_tiles.rs:339-346: (value * (color_count - 1) + u16::MAX / 2) / u16::MAX  (32 bits hold it when colors <= 2^16)
+        const unsigned ci = colors <= 1 ? 0u : (small_map ? (v * scale + 32767u) / 65535u
+                                                          : static_cast<unsigned>((static_cast<unsigned long long>(v) * scale + 32767ull) / 65535ull));
+        return __ldg(cm + ci);
     };
-    const bool big_map = colors > 65536u;  // (index arithmetic above needs colors - 1 < 2^16; larger maps take 64 bits)
-    for (unsigned x = 2 * threadIdx.x; x < width; x += 2 * kTileThreads) {
-        const bool two = x + 1 < width;
+    for (unsigned x = 4 * threadIdx.x; x < width; x += 4 * kIdThreads) {
+        const unsigned npx = min(4u, width - x);
 #pragma unroll
         for (int r = 0; r < kIdRows; r++) {
             if (static_cast<unsigned>(r) >= rows) break;
             const uint16_t *s = src0 + static_cast<size_t>(r) * pitch + x;
-            unsigned v0, v1 = 0;
-            if (two && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
-                const unsigned w = __ldg(reinterpret_cast<const unsigned *>(s));
-                v0 = w & 0xffffu;
-                v1 = w >> 16;
+            unsigned *o = out + static_cast<size_t>(height - 1 - (y0 + r)) * width + x;
+            if (npx == 4 && (reinterpret_cast<uintptr_t>(s) & 7) == 0) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2 *>(s));
+                const uint4 c = make_uint4(look(w.x & 0xffffu), look(w.x >> 16), look(w.y & 0xffffu), look(w.y >> 16));
+                if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    *reinterpret_cast<uint4 *>(o) = c;
+                } else {
+                    o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
+                }
             } else {
-                v0 = __ldg(s);
-                if (two) v1 = __ldg(s + 1);
-            }
-            unsigned c0, c1 = 0;
-            if (big_map) {
-                c0 = __ldg(reinterpret_cast<const unsigned *>(colormap) + static_cast<unsigned>((static_cast<unsigned long long>(v0) * scale + 32767ull) / 65535ull));
-                if (two) c1 = __ldg(reinterpret_cast<const unsigned *>(colormap) + static_cast<unsigned>((static_cast<unsigned long long>(v1) * scale + 32767ull) / 65535ull));
-            } else {
-                c0 = look(v0);
-                if (two) c1 = look(v1);
-            }
-            unsigned *o = reinterpret_cast<unsigned *>(out + static_cast<size_t>(height - 1 - (y0 + r)) * width + x);
-            if (two && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
-                *reinterpret_cast<uint2 *>(o) = make_uint2(c0, c1);
-            } else {
-                o[0] = c0;
-                if (two) o[1] = c1;
+                for (unsigned i = 0; i < npx; i++) o[i] = look(__ldg(s + i));
             }
         }
     }
@@ -155,7 +144,7 @@ cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned ma
     for (int c0 = 0; c0 < n; c0 += 65535) {
         const unsigned nc = static_cast<unsigned>(n - c0 < 65535 ? n - c0 : 65535);
         // (each kernel returns at once for the descriptors of the other kind)
-        tile_identity_kernel<<<dim3((max_h + kIdRows - 1) / kIdRows, nc), kTileThreads, 0, st>>>(d_descs + c0, d_colormap, colors);
+        tile_identity_kernel<<<dim3((max_h + kIdRows - 1) / kIdRows, nc), kIdThreads, 0, st>>>(d_descs + c0, d_colormap, colors);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         tile_horiz_kernel<<<dim3(gx, (max_tmp_h + kTileRows - 1) / kTileRows, nc), kTileThreads, 0, st>>>(d_descs + c0);
