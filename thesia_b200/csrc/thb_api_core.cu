@@ -195,7 +195,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
             d.max_band_len = std::max<int>(d.max_band_len, static_cast<int>(mb.ptr[m + 1] - mb.ptr[m]));
     }
     d.n_bins = d.n_mel ? d.n_mel : d.n_freq;
-    d.mi_words = d.mi_groups = d.mi_min_start = d.mi_max_reach = 0;
+    d.mi_words = d.mi_groups = d.mi_min_start = d.mi_max_reach = d.mi_direct = 0;
     d.mi_blob = nullptr;
     std::vector<uint32_t> mi_blob;
     if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
@@ -215,6 +215,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         if (const char *e = getenv("THB_MEL_DIRECT")) mi.use_direct = mi.valid && d.n_fft <= 2048 && atoi(e) != 0;
         d.mi_words = static_cast<int>(mi_blob.size());
         // the band-major schedule keeps no partial sums (no groups) and starts at the bands' own first bins
+        d.mi_direct = mi.use_direct ? 1 : 0;
         d.mi_groups = mi.use_direct ? 0 : static_cast<int>(mi.n_groups);
         d.mi_min_start = mi.use_direct ? 0 : mi.min_start;
         d.mi_max_reach = static_cast<int>(mi.use_direct ? mi.direct_reach : mi.max_reach);
@@ -686,7 +687,7 @@ int thb_plan_kernel(thb_ctx *ctx, const thb_setting *setting, uint32_t sr, uint3
     else if (thb::stft_big_supported(pd)) *family = THB_KERNEL_BIG;
     else if (thb::stft_fast_supported(pd)) *family = THB_KERNEL_FAST;
     else *family = THB_KERNEL_GENERIC;
-    if (mel_schedule) *mel_schedule = !pd.n_mel ? 0u : (pd.mi_blob && pd.mi_groups == 0 ? 2u : 1u);
+    if (mel_schedule) *mel_schedule = !pd.n_mel ? 0u : (pd.mi_blob && pd.mi_direct ? 2u : 1u);
     return THB_OK;
 }
 

@@ -41,6 +41,7 @@ struct PlanDev {
     // warp schedule of the sparse mel product (thb_host.hpp MelItems::blob); mel only, n_fft == 2048
     int mi_words;                     // size of mi_blob in 32-bit words
     int mi_groups, mi_min_start, mi_max_reach;
+    int mi_direct;                    // 1: the blob holds the band-major schedule (mel_direct), 0: the bin-major one
     const uint32_t *mi_blob;
     // n_fft == 16384 two-frame path (thb_stft_big.cu); null otherwise
     const float *big_wpad;            // [16384] 0.5 * window centred in the FFT buffer, zeros outside

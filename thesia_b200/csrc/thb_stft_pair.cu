@@ -64,7 +64,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *addr, unsigned byte
 // M4: the lean mel walk / gather (mel_walk4 / mel_band4; same results bit for bit)
 // PL (HS > 0): the PCM of the warp's NEXT frame pair is prefetched into L1 before the mel stage of the current one
 // (three instructions per pair), so that its 40 loads hit L1 instead of stalling the window multiply on L2 / HBM
-template <bool MEL, int NW, bool I16, int HS, bool M4, bool PL>
+// DIRECT: the plan carries the band-major mel schedule (compile-time: the kernel sits close to the instruction-cache
+// cliff noted in DESIGN.md, each variant holds only the mel code it runs)
+template <bool MEL, int NW, bool I16, int HS, bool M4, bool PL, bool DIRECT>
 __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev p,
                                                                         const TrackDesc *__restrict__ tracks,
                                                                         long long n_items, RescueList rescue, int flags) {
@@ -306,15 +308,16 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             if (MEL) {
                 __syncwarp();
                 const MelView mv(sm.ms);
-                if (!mv.direct) {
+                if constexpr (!DIRECT) {
                     if constexpr (M4) mel_walk4<float2>(mv, mag, part, lane);
                     else mel_walk<float2>(mv, mag, part, lane);
                     __syncwarp();
                 }
                 for (int r = 0; 32 * r < mv.n_mel; r++) {
                     const int m = 32 * r + lane;
-                    const f2 acc = mv.direct ? mel_direct<float2>(mv, mag, r, lane)
-                                             : (M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane));
+                    f2 acc;
+                    if constexpr (DIRECT) acc = mel_direct<float2>(mv, mag, r, lane);
+                    else acc = M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane);
                     if (m >= mv.n_mel) continue;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
@@ -355,20 +358,31 @@ int pair_warps() {
     return (w == 8 || w == 10 || w == 12 || w == 14 || w == 16) ? w : 12;
 }
 
-template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true, bool PL = false>
-cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
-                      cudaStream_t st) {
+template <bool MEL, int NW, bool I16, int HS, bool M4, bool PL, bool DIRECT>
+cudaError_t launch_nwd(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
+                       cudaStream_t st) {
     const size_t smem = pair_smem_bytes(plan, NW);
-    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS, M4, PL>;
+    auto kern = stft2048_pair_kernel<MEL, NW, I16, HS, M4, PL, DIRECT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long n_items = static_cast<long long>(n_tracks) * rescue.tiles_per_track;
     const int grid = static_cast<int>(n_items < sm_count ? n_items : sm_count);
-    // THB_PAIR_PREFETCH=0 turns the next-tile L2 prefetch off (A/B runs)
+    // THB_PAIR_PREFETCH=1 turns the next-tile L2 prefetch on (A/B runs).  Off by default: measured on B200 it buys
+    // nothing on the mel kernel (1.077 -> 1.074 ms at 450 k frames), 1.7 % on the linear one, and ncu shows 19 % more DRAM
+    // reads (lines prefetched 30 us ahead are partly evicted again before their tile starts).
     const char *pe = getenv("THB_PAIR_PREFETCH");
-    const int flags = (pe && atoi(pe) == 0) ? 0 : 1;
+    const int flags = (pe && atoi(pe) == 1) ? 1 : 0;
     kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks, n_items, rescue, flags);
     return cudaGetLastError();
+}
+
+template <bool MEL, int NW, bool I16, int HS = 0, bool M4 = true, bool PL = false>
+cudaError_t launch_nw(const PlanDev &plan, const TrackDesc *d_tracks, int n_tracks, RescueList rescue, int sm_count,
+                      cudaStream_t st) {
+    if constexpr (MEL && M4 && !PL) {
+        if (plan.mi_direct) return launch_nwd<MEL, NW, I16, HS, true, false, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+    }
+    return launch_nwd<MEL, NW, I16, HS, M4, PL, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
 }
 
 }  // namespace
@@ -401,16 +415,21 @@ cudaError_t launch_stft_pair(const PlanDev &plan, const TrackDesc *d_tracks, int
     // THB_PAIR_SHARE=0 turns the shared-load variants off (A/B runs)
     const char *se = getenv("THB_PAIR_SHARE");
     const bool share = !(se && atoi(se) == 0) && nw >= 12;
+#ifndef THB_PAIR_EXPERIMENTS
+    if (nw > 12) return cudaErrorInvalidValue;  // 14 / 16 warps are only built with -DTHB_PAIR_EXPERIMENTS
+#endif
     if (share && plan.hop == 512) {
         // THB_MEL4=0: the mel walk / gather with remainder code and 16-bit slot ids (A/B runs; same results)
         const char *m4 = getenv("THB_MEL4");
         if (plan.n_mel && m4 && atoi(m4) == 0) return launch_nw<true, 12, false, 8, false>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-        // THB_PAIR_PL=1: software-pipelined PCM loads (A/B runs)
+#ifdef THB_PAIR_EXPERIMENTS   // the round-2 A/B variants: make NVFLAGS+=-DTHB_PAIR_EXPERIMENTS
+        // THB_PAIR_PL=1: the PCM of the warp's next pair prefetched into L1 ahead of the mel stage (3 % slower)
         const char *pl = getenv("THB_PAIR_PL");
         if (plan.n_mel && pl && atoi(pl) == 1) return launch_nw<true, 12, false, 8, true, true>(plan, d_tracks, n_tracks, rescue, sm_count, st);
-        // THB_PAIR_WARPS=14 | 16: more warps on fewer registers (144 / 128: the DFT state spills) -- occupancy experiment
+        // THB_PAIR_WARPS=14 | 16: more warps on fewer registers (128: the DFT state spills; 32 % / 26 % slower)
         if (plan.n_mel && nw == 14) return launch_nw<true, 14, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         if (plan.n_mel && nw == 16) return launch_nw<true, 16, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
+#endif
         if (plan.n_mel) return launch_nw<true, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
         return launch_nw<false, 12, false, 8>(plan, d_tracks, n_tracks, rescue, sm_count, st);
     }
