@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
         const long long f_end = min(f_begin + kTile, d.n_frames);
         float lmax = -CUDART_INF_F, lnmin = -CUDART_INF_F;
         bool flagged = false;
+#ifdef THB_PAIR_EXPERIMENTS
         if ((flags & 1) && lane == 0) {
             const long long nxt = item + gridDim.x;
             if (nxt < n_items) {
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
             }
         }
 
+#endif
         for (long long fa = f_begin + 2 * warp; fa < f_end; fa += 2 * NW) {
             const long long fb = fa + 1;
             cx v[32];
