@@ -334,7 +334,9 @@ def strong_scaling(args, torch, dist, thb, ctx, pcm_weak, n, rank, world, local_
                           f"the rest launch gaps / tails of the smaller grids")
         return rec
 
-    out = {"note": "fixed total work split over the ranks; `scaling` of the headline stays weak (the driver computes its efficiency)"}
+    out = {"note": "fixed total work split over the ranks; `scaling` of the headline stays weak (the driver computes its efficiency)",
+           "global_range_exchange": ("one kernel over NVLink peer memory (CUDA IPC)" if ctx.comm_peer_exchange() else
+                                     ("ncclAllReduce(max) of 2 floats" if world > 1 else "single rank"))}
     # c3: 128 channels x 10 min (the weak batch of rank 0 IS this job: tracks 0..63)
     setting3 = thb.SpecSetting(WIN_MS, T_OVERLAP, 1, thb.FreqScale.Mel, N_MEL)
     n_ch = pcm_weak.shape[0]

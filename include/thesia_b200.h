@@ -333,6 +333,12 @@ int thb_apply_gain(thb_ctx *ctx, const thb_gain_channel *channels, size_t n, uin
 int thb_comm_unique_id(uint8_t id[128]);
 int thb_comm_init(thb_ctx *ctx, int n_ranks, int rank, const uint8_t id[128]);
 int thb_comm_destroy(thb_ctx *ctx);
+/* thb_comm_init also maps, through CUDA IPC, a 512-byte exchange buffer of every rank into every other rank (the handles
+ * travel over the new communicator): the global dB range then takes ONE kernel that stores {max, -min} into the peers'
+ * buffers over NVLink and polls its own, instead of reduce + ncclAllReduce + finalize.  If any mapping fails on any rank
+ * (no peer access, IPC not permitted, more than 16 ranks, or THB_PEER_EXCHANGE=0) every rank keeps the NCCL path.
+ * Returns 1 when the peer-memory exchange is in use. */
+int thb_comm_peer_exchange(const thb_ctx *ctx);
 
 /* ---- measurement support --------------------------------------------------------------------
  * Per-kernel CUDA-event timing on the ctx stream and a launch counter (bench.py's roofline /

@@ -130,6 +130,7 @@ SIGNATURES = {
     "thb_comm_unique_id": (_i, [_u8p]),
     "thb_comm_init": (_i, [_vp, _i, _i, _u8p]),
     "thb_comm_destroy": (_i, [_vp]),
+    "thb_comm_peer_exchange": (_i, [_vp]),
     "thb_profile_enable": (_i, [_vp, _i]),
     "thb_profile_reset": (_i, [_vp]),
     "thb_profile_get": (_i, [_vp, C.c_char_p, _P(C.c_double), _P(_u64)]),

@@ -334,6 +334,10 @@ class Context:
         check(lib().thb_plan_kernel(self._h, C.byref(setting._c()), sr, C.byref(fam), C.byref(sch)), self._h)
         return fam.value, sch.value
 
+    def comm_peer_exchange(self) -> bool:
+        """True when the global dB range is exchanged over the peers' NVLink-mapped memory (thb_comm_peer_exchange)."""
+        return bool(lib().thb_comm_peer_exchange(self._h))
+
     def range_get(self) -> Tuple[float, float]:
         a, b = C.c_float(), C.c_float()
         check(lib().thb_range_get(self._h, C.byref(a), C.byref(b)), self._h)

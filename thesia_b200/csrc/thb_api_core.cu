@@ -24,6 +24,7 @@ bool NcclApi::load(std::string *err) {
     GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
     CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(handle, "ncclAllGather"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
@@ -371,6 +372,14 @@ Spec *find_spec(thb_ctx *ctx, uint64_t id, uint32_t ch) {
 
 int global_minmax_on_stream(thb_ctx *ctx, float dB_range) {
     cudaError_t e;
+    if (ctx->nccl_comm && ctx->px.ok) {
+        // one launch: local reduce, exchange over the peers' NVLink-mapped slots, clamp rules (thb_image.cu)
+        ProfScope ps(ctx, "minmax_reduce", 1);
+        e = thb::launch_minmax_exchange(ctx->d_slots, ctx->slot_cap, ctx->px.d_peers, ctx->px.mine, ctx->n_ranks, ctx->rank, ++ctx->px.seq,
+                                        dB_range, ctx->d_range, ctx->d_send, ctx->px.d_fail, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax exchange: %s", cudaGetErrorString(e));
+        return THB_OK;
+    }
     {
         ProfScope ps(ctx, "minmax_reduce", 2);
         e = thb::launch_minmax_reduce(ctx->d_slots, ctx->slot_cap, ctx->d_send, ctx->stream);
@@ -384,6 +393,81 @@ int global_minmax_on_stream(thb_ctx *ctx, float dB_range) {
         e = thb::launch_minmax_finalize(ctx->d_send, dB_range, ctx->d_range, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "minmax finalize: %s", cudaGetErrorString(e));
     }
+    return THB_OK;
+}
+
+// Maps every rank's exchange slots into this process (CUDA IPC; the handles travel through one ncclAllGather) so that
+// the global dB range needs one kernel and an NVLink round trip instead of NCCL's launch + protocol for 8 bytes.
+// All ranks agree (ncclAllReduce(min) of a flag) on whether every mapping worked; if not, the NCCL path stays.
+void peer_exchange_close(thb_ctx *ctx) {
+    thb_ctx::PeerExchange &px = ctx->px;
+    for (void *p : px.opened) cudaIpcCloseMemHandle(p);
+    px.opened.clear();
+    if (px.mine) cudaFree(px.mine);
+    if (px.d_peers) cudaFree(px.d_peers);
+    if (px.d_fail) cudaFree(px.d_fail);
+    px = thb_ctx::PeerExchange{};
+}
+
+int peer_exchange_open(thb_ctx *ctx) {
+    thb_ctx::PeerExchange &px = ctx->px;
+    peer_exchange_close(ctx);
+    const char *env = getenv("THB_PEER_EXCHANGE");
+    const int n = ctx->n_ranks;
+    if ((env && atoi(env) == 0) || n < 2 || n > thb::kExchangeMaxRanks || !g_nccl.AllGather) return THB_OK;
+    int good = 1;
+    unsigned char *d_handles = nullptr;
+    int *d_flag = nullptr;
+    std::vector<unsigned char> h_handles(static_cast<size_t>(n) * sizeof(cudaIpcMemHandle_t));
+    std::vector<float4 *> peers(n, nullptr);
+    CK(cudaMalloc(reinterpret_cast<void **>(&px.mine), sizeof(float4) * 2 * thb::kExchangeMaxRanks));
+    CK(cudaMemset(px.mine, 0, sizeof(float4) * 2 * thb::kExchangeMaxRanks));   // sequence numbers start at 1
+    CK(cudaMalloc(reinterpret_cast<void **>(&px.d_peers), sizeof(float4 *) * thb::kExchangeMaxRanks));
+    CK(cudaMalloc(reinterpret_cast<void **>(&px.d_fail), sizeof(unsigned)));
+    CK(cudaMemset(px.d_fail, 0, sizeof(unsigned)));
+    CK(cudaMalloc(reinterpret_cast<void **>(&d_handles), h_handles.size()));
+    CK(cudaMalloc(reinterpret_cast<void **>(&d_flag), sizeof(int)));
+    cudaIpcMemHandle_t mine_h;
+    if (cudaIpcGetMemHandle(&mine_h, px.mine) != cudaSuccess) {
+        cudaGetLastError();
+        good = 0;
+        memset(&mine_h, 0, sizeof mine_h);
+    }
+    CK(cudaMemcpyAsync(d_handles + static_cast<size_t>(ctx->rank) * sizeof mine_h, &mine_h, sizeof mine_h, cudaMemcpyHostToDevice, ctx->stream));
+    int r = g_nccl.AllGather(d_handles + static_cast<size_t>(ctx->rank) * sizeof mine_h, d_handles, sizeof mine_h, kNcclUint8, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, THB_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    CK(cudaMemcpyAsync(h_handles.data(), d_handles, h_handles.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < n && good; q++) {
+        if (q == ctx->rank) {
+            peers[q] = px.mine;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_handles.data() + static_cast<size_t>(q) * sizeof h, sizeof h);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            good = 0;
+            break;
+        }
+        px.opened.push_back(p);
+        peers[q] = static_cast<float4 *>(p);
+    }
+    // every rank must take the same path: min over ranks of `good` (also the barrier after which every mapping exists)
+    CK(cudaMemcpyAsync(d_flag, &good, sizeof good, cudaMemcpyHostToDevice, ctx->stream));
+    r = g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclMin, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, THB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    CK(cudaMemcpyAsync(&good, d_flag, sizeof good, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_handles);
+    cudaFree(d_flag);
+    if (!good) {
+        peer_exchange_close(ctx);
+        return THB_OK;   // NCCL path
+    }
+    CK(cudaMemcpy(px.d_peers, peers.data(), sizeof(float4 *) * n, cudaMemcpyHostToDevice));
+    px.ok = true;
     return THB_OK;
 }
 
@@ -754,11 +838,14 @@ int thb_comm_init(thb_ctx *ctx, int n_ranks, int rank, const uint8_t id[128]) {
     }
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
-    return THB_OK;
+    return peer_exchange_open(ctx);
 }
+
+int thb_comm_peer_exchange(const thb_ctx *ctx) { return ctx && ctx->px.ok ? 1 : 0; }
 
 int thb_comm_destroy(thb_ctx *ctx) {
     if (!ctx) return THB_OK;
+    peer_exchange_close(ctx);
     if (ctx->nccl_comm && g_nccl.CommDestroy) {
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy(ctx->nccl_comm);

@@ -486,6 +486,17 @@ int thb_release_all(thb_ctx *ctx) {
 }
 
 // ---- update_spec_imgs -----------------------------------------------------------------------------
+
+// a peer that never showed up in the NVLink exchange leaves a NaN range and this flag (thb_image.cu): surface it at the
+// next point where the host waits anyway
+static int exchange_check(thb_ctx *ctx) {
+    if (!ctx->px.ok) return THB_OK;
+    unsigned f = 0;
+    CK(cudaMemcpy(&f, ctx->px.d_fail, sizeof f, cudaMemcpyDeviceToHost));
+    if (f) return fail(ctx, THB_ERR_NCCL, "a rank did not reach the global-range exchange within 5 s");
+    return THB_OK;
+}
+
 int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB) {
     if (!ctx) return fail(nullptr, THB_ERR_INVALID, "ctx is NULL");
     Nvtx nv("thb_minmax_global");
@@ -503,7 +514,7 @@ int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB
     CK(cudaStreamSynchronize(ctx->stream));
     if (min_dB) *min_dB = ctx->h_pinned[0];
     if (max_dB) *max_dB = ctx->h_pinned[1];
-    return THB_OK;
+    return exchange_check(ctx);
 }
 
 // which spec_to_img kernel a batch of descriptors may use (thb_kernels.cuh); THB_IMG_TILE=0|1|2|3 caps it (A/B runs)
@@ -630,7 +641,7 @@ int thb_update_spec_imgs(thb_ctx *ctx, float dB_range, uint32_t colormap_length,
     CK(cudaStreamSynchronize(ctx->stream));
     if (min_dB) *min_dB = ctx->h_pinned[0];
     if (max_dB) *max_dB = ctx->h_pinned[1];
-    return THB_OK;
+    return exchange_check(ctx);
 }
 
 int thb_update_spec_imgs_range(thb_ctx *ctx, float min_dB, float max_dB, uint32_t colormap_length, uint32_t max_sr,
@@ -659,7 +670,7 @@ int thb_range_get(thb_ctx *ctx, float *min_dB, float *max_dB) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (min_dB) *min_dB = ctx->h_pinned[0];
     if (max_dB) *max_dB = ctx->h_pinned[1];
-    return THB_OK;
+    return exchange_check(ctx);
 }
 
 int thb_img_read(thb_ctx *ctx, uint64_t id, uint32_t ch, uint16_t *out, uint64_t cap, uint64_t *height, uint64_t *width) {

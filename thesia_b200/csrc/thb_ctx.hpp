@@ -86,6 +86,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclId *) = nullptr;
     int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load(std::string *err);
@@ -93,6 +94,9 @@ struct NcclApi {
 extern NcclApi g_nccl;
 constexpr int kNcclFloat32 = 7;
 constexpr int kNcclMax = 2;
+constexpr int kNcclMin = 3;
+constexpr int kNcclUint8 = 1;
+constexpr int kNcclInt32 = 2;
 
 struct TileLane;
 struct PcmCache;
@@ -177,6 +181,15 @@ struct thb_ctx {
 
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // the global-range exchange over peer memory (thb_comm_init): every rank's slots mapped through CUDA IPC
+    struct PeerExchange {
+        bool ok = false;
+        float4 *mine = nullptr;                 // [2][kExchangeMaxRanks] {max, -min, seq, -}
+        float4 **d_peers = nullptr;             // device array of n_ranks pointers (peers[rank] == mine)
+        std::vector<void *> opened;             // IPC mappings to close
+        unsigned *d_fail = nullptr;
+        unsigned seq = 0;
+    } px;
 
     std::mutex prof_mu;
     bool profiling = false;

@@ -59,6 +59,65 @@ __global__ void minmax_reduce_kernel(const float *__restrict__ slots, int n_slot
     }
 }
 
+// The global dB range in ONE kernel when the ranks of a box can see each other's memory (thb_comm_init maps every
+// peer's exchange slots through CUDA IPC over NVLink): local max over the slots, each lane l < n_ranks stores
+// {max, -min} + the step's sequence number into ITS slot of peer l (remote store, payload before flag), polls peer l's
+// slot in the local buffer until the same sequence number arrives, max over ranks, clamp rules (mod.rs:179-180).
+// Replaces minmax_reduce + ncclAllReduce(max, 2 floats) + minmax_finalize: three launches and NCCL's ~40 us for 8 bytes
+// become one launch and an NVLink round trip.  Slots are double buffered by the parity of the sequence number: a rank
+// can start step s + 1 (other parity) while a slow rank still reads step s, and nobody can reach step s + 2 before
+// every rank has finished reading step s.  `fail` is set (and the range left NaN) if a peer does not show up in ~5 s.
+__global__ void minmax_exchange_kernel(const float *__restrict__ slots, int n_slots, float4 *const *peers, float4 *mine, int n_ranks,
+                                       int rank, unsigned seq, float dB_range, float *range, float *send, unsigned *fail) {
+    const int lane = threadIdx.x;
+    float a = -CUDART_INF_F, b = -CUDART_INF_F;
+    for (int i = lane; i < n_slots; i += 32) {
+        a = fmaxf(a, slots[2 * i]);
+        b = fmaxf(b, slots[2 * i + 1]);
+    }
+    a = warp_max(a);
+    b = warp_max(b);
+    const int base = (seq & 1u) * kExchangeMaxRanks;
+    if (lane < n_ranks) {
+        volatile float *dst = reinterpret_cast<volatile float *>(peers[lane] + base + rank);
+        dst[0] = a;
+        dst[1] = b;
+        __threadfence_system();
+        reinterpret_cast<volatile unsigned *>(dst)[2] = seq;
+    }
+    float ra = -CUDART_INF_F, rb = -CUDART_INF_F;
+    bool ok = true;
+    if (lane < n_ranks) {
+        volatile float *src = reinterpret_cast<volatile float *>(mine + base + lane);
+        unsigned spins = 0;
+        while (reinterpret_cast<volatile unsigned *>(src)[2] != seq) {
+            __nanosleep(100);
+            if (++spins > 50000000u) {
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        ra = src[0];
+        rb = src[1];
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    ra = warp_max(ra);
+    rb = warp_max(rb);
+    if (lane == 0) {
+        if (!ok) {
+            *fail = 1u;
+            range[0] = range[1] = CUDART_NAN_F;
+            return;
+        }
+        send[0] = ra;
+        send[1] = rb;
+        const float mx = fminf(ra, 0.0f);
+        range[0] = fmaxf(-rb, __fsub_rn(mx, dB_range));
+        range[1] = mx;
+    }
+}
+
 // max <- min(max, 0); min <- max(min, max - dB_range)   (mod.rs:179-180)
 __global__ void minmax_finalize_kernel(const float *__restrict__ send, float dB_range, float *range) {
     const float mx = fminf(send[0], 0.0f);
@@ -295,6 +354,12 @@ cudaError_t launch_minmax_array(const float *d_x, unsigned long long n, float *d
 
 cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_send, cudaStream_t st) {
     minmax_reduce_kernel<<<1, 32, 0, st>>>(d_slots, n_slots, d_send);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_exchange(const float *d_slots, int n_slots, float4 *const *d_peers, float4 *d_mine, int n_ranks, int rank,
+                                   unsigned seq, float dB_range, float *d_range, float *d_send, unsigned *d_fail, cudaStream_t st) {
+    minmax_exchange_kernel<<<1, 32, 0, st>>>(d_slots, n_slots, d_peers, d_mine, n_ranks, rank, seq, dB_range, d_range, d_send, d_fail);
     return cudaGetLastError();
 }
 

@@ -167,6 +167,11 @@ cudaError_t launch_minmax_init_tracks(const TrackDesc *d_tracks, int n, cudaStre
 cudaError_t launch_minmax_array(const float *d_x, unsigned long long n, float *d_slot, int sm_count, cudaStream_t st);
 // d_send[0..1] = max over live slots of {max, -min}
 cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_send, cudaStream_t st);
+// reduce + exchange over peer memory + finalize in one launch (thb_image.cu); d_peers[r] / d_mine: the exchange slots
+// of rank r / of this rank, 2 x kExchangeMaxRanks float4 each
+constexpr int kExchangeMaxRanks = 16;
+cudaError_t launch_minmax_exchange(const float *d_slots, int n_slots, float4 *const *d_peers, float4 *d_mine, int n_ranks, int rank,
+                                   unsigned seq, float dB_range, float *d_range, float *d_send, unsigned *d_fail, cudaStream_t st);
 // d_range = {min_dB, max_dB} after the clamp rules of mod.rs:179-180
 cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d_range, cudaStream_t st);
 

@@ -43,6 +43,7 @@ def main():
         uid = [thb.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
+        px = ctx.comm_peer_exchange()   # the global range over NVLink peer memory (or NCCL when IPC is not available)
         units = plan[rank]
         tracks = []
         for k, u in enumerate(units):
@@ -72,7 +73,7 @@ def main():
         dist.all_gather_object(gathered, rng)
         assert all(g == rng for g in gathered)
         if rank == 0:
-            print(f"setting win {win} hop {hop}: {world} ranks agree, dB range {rng}, "
+            print(f"setting win {win} hop {hop}: {world} ranks agree (range over {'peer memory' if px else 'NCCL'}), dB range {rng}, "
                   f"{sum(len(p) for p in plan)} units", flush=True)
     dist.barrier()
     if rank == 0:
