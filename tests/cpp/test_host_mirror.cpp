@@ -9,6 +9,7 @@
 //                            (drawing.rs:43-56) and the waveform tile KATs (render_tiles.rs:408-433)
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <string>
@@ -294,7 +295,9 @@ static void test_tile_readers_overlap() {
                 kThreads, kCalls, 1e3 * serial, 1e6 * serial / (kThreads * kCalls), kThreads, 1e3 * parallel,
                 1e6 * parallel / (kThreads * kCalls), serial / parallel);
     EXPECT(bad == 0);
-    EXPECT(parallel < 0.8 * serial);  // a context-wide lock would make the two equal (measured: 2.5x faster)
+    // a context-wide lock would make the two equal (measured: 2.5x faster); under compute-sanitizer the tool itself
+    // serialises the launches, so the wall-clock bar is skipped there (THB_NO_TIMING=1)
+    if (!std::getenv("THB_NO_TIMING")) EXPECT(parallel < 0.8 * serial);
 }
 
 int main(int argc, char **argv) {

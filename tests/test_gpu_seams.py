@@ -146,7 +146,9 @@ def test_tile_readers_run_concurrently(ctx, orc):
         th.join()
     t_eight = time.perf_counter() - t0
     assert not bad
-    assert t_eight < 12.0 * t_one, (t_one, t_eight)
+    import os
+    if not os.environ.get("THB_NO_TIMING"):
+        assert t_eight < 12.0 * t_one, (t_one, t_eight)
     print(f"one thread {1e6 * t_one / reps:.0f} us/tile; eight threads {1e6 * t_eight / (8 * reps):.0f} us/tile "
           f"({8 * t_one / t_eight:.1f}x overlap)")
 

@@ -522,6 +522,9 @@ int thb_ctx_create(int device, void *cuda_stream, thb_ctx **out) {
         ctx->own_stream = true;
     }
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->h2d_ev, cudaEventDisableTiming);
     cudaMalloc(&ctx->d_send, sizeof(float) * 2);
     cudaMalloc(&ctx->d_range, sizeof(float) * 2);
@@ -571,6 +574,9 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     if (ctx->h2d_ev) cudaEventDestroy(ctx->h2d_ev);
     for (cudaEvent_t ev : ctx->stage_ev) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

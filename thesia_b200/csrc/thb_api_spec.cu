@@ -306,7 +306,7 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         size_t cap = 4096;
         while (cap < max_pair_tiles) cap <<= 1;
         CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_items), sizeof(uint2) * cap));
-        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_count), sizeof(unsigned) * (cap + 1)));
+        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rescue_count), sizeof(unsigned) * (cap + 2)));
         ctx->rescue_cap = cap;
     }
     // reset the {max, -min} slots of the channels being recomputed
@@ -330,12 +330,30 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             const char *kname = pd.n_mel ? "stft_mel_db" : "stft_lin_db";
             const char *ename = pd.n_mel ? "stft_mel_db_edges" : "stft_lin_db_edges";
             const bool is2048 = pd.n_fft == 2048;  // else n_fft 1024 / 512: thb_stft_warp.cu, same division of labour
-            if (l.n_pair) {
+            // The scalar kernel over the file-edge frames goes FIRST, on a side stream: a handful of CTAs for ~20 us that
+            // the packed kernel (whose work items are handed out dynamically) runs around instead of behind.  At N = 8 the
+            // two end ranks of a frame-range split would otherwise finish 20 us after the others.
+            static const bool side_ok = !(getenv("THB_EDGE_SIDE") && atoi(getenv("THB_EDGE_SIDE")) == 0);
+            const bool side = side_ok && l.n_pair && l.n_edge && ctx->side_stream;
+            auto launch_edges = [&](cudaStream_t st) {
+                ProfScope ps(ctx, ename, (l.n_edge + 65534) / 65535, st);
+                return is2048 ? thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, st)
+                              : thb::launch_stft_warp_scalar(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, st);
+            };
+            if (side) {
+                CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->side_stream, ctx->fork_ev, 0));
+                e = launch_edges(ctx->side_stream);
+                CK(cudaEventRecord(ctx->join_ev, ctx->side_stream));
+            }
+            if (e == cudaSuccess && l.n_pair) {
                 const unsigned tf = static_cast<unsigned>(is2048 ? thb::stft_pair_tile_frames() : thb::stft_warp_tile_frames(pd));
-                const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
-                                         static_cast<unsigned>(ctx->rescue_cap), tf,
-                                         static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf)};
-                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
+                // [0] = rescue count, [1 .. pair_tiles] = one flag per tile, [pair_tiles + 1] = the work-item counter
+                thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
+                                   static_cast<unsigned>(ctx->rescue_cap), tf,
+                                   static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf), nullptr};
+                if (is2048) rl.next_item = ctx->d_rescue_count + 1 + l.pair_tiles;
+                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 2), ctx->stream));
                 {
                     ProfScope ps(ctx, kname, 1);  // the packed kernel alone: this is the roofline kernel
                     e = is2048 ? thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream)
@@ -347,10 +365,10 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                                : thb::launch_stft_warp_list(pd, l.d_pair, rl, ctx->sm_count, ctx->stream);
                 }
             }
-            if (e == cudaSuccess && l.n_edge) {
-                ProfScope ps(ctx, ename, (l.n_edge + 65534) / 65535);
-                e = is2048 ? thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream)
-                           : thb::launch_stft_warp_scalar(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, ctx->stream);
+            if (side) {
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+            } else if (e == cudaSuccess && l.n_edge) {
+                e = launch_edges(ctx->stream);
             }
         } else {
             ProfScope ps(ctx, pd.n_mel ? "stft_mel_db" : "stft_lin_db", chunks);

@@ -111,6 +111,8 @@ struct thb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // H2D staging, overlapped with compute
+    cudaStream_t side_stream = nullptr;  // the scalar kernel over file-edge frames, next to the packed kernel
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     // Writers (update_specs, update_spec_imgs, release, ...) take `mu` exclusively; the tile readers
     // (thb_waveform_tile, thb_spectrogram_tile[_batch]) take it shared and run concurrently on their own
     // streams -- the reference's write-lock worker / read-locked IPC threads (interface.rs:12-56, lib.rs:343-389).

@@ -3,11 +3,11 @@
 # tool: THB_TEST_SMALL=1), racecheck over the kernels with shared-memory choreography.  Log -> gpurun_out/sanitize_<tag>.log
 TAG=${1:-r02}
 mkdir -p gpurun_out
-export THB_TEST_SMALL=1
+export THB_TEST_SMALL=1 THB_NO_TIMING=1
 {
 echo "== memcheck: tests -m gpu"
 timeout 3000 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 9 --target-processes all \
-  python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | grep -v "^=========\s*$" | tail -40
+  python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -v "^=========\s*$" | tail -40
 echo "memcheck exit: ${PIPESTATUS[0]}"
 echo "== racecheck: frame-pair / warp / large-FFT kernels, tiles"
 timeout 2400 compute-sanitizer --tool racecheck --error-exitcode 9 \
