@@ -330,11 +330,16 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             const char *kname = pd.n_mel ? "stft_mel_db" : "stft_lin_db";
             const char *ename = pd.n_mel ? "stft_mel_db_edges" : "stft_lin_db_edges";
             const bool is2048 = pd.n_fft == 2048;  // else n_fft 1024 / 512: thb_stft_warp.cu, same division of labour
-            // The scalar kernel over the file-edge frames goes FIRST, on a side stream: a handful of CTAs for ~20 us that
-            // the packed kernel (whose work items are handed out dynamically) runs around instead of behind.  At N = 8 the
-            // two end ranks of a frame-range split would otherwise finish 20 us after the others.
+            // A frame-range shard of one long file has a handful of file-edge frames (reflect padding) that only the scalar
+            // kernel can do: one or two CTAs for ~100 us.  Behind the packed kernel that is pure latency -- at N = 8 the two
+            // end ranks of a split file finish that much after the others.  So when the edge work is
+            // that small it runs on a side stream next to the packed kernel, which leaves it one SM (grid - 1: 0.7 % of
+            // its throughput).  Batches of many channels (C3: 256 edge descriptors) keep the serial order: their edge
+            // kernel fills the machine on its own.
             static const bool side_ok = !(getenv("THB_EDGE_SIDE") && atoi(getenv("THB_EDGE_SIDE")) == 0);
-            const bool side = side_ok && l.n_pair && l.n_edge && ctx->side_stream;
+            const long long edge_ctas = static_cast<long long>(l.n_edge) * ((l.max_edge_frames + 63) / 64);
+            const bool side = side_ok && l.n_pair && l.n_edge && ctx->side_stream && edge_ctas <= 2 && ctx->sm_count > 8;
+            const int pair_sms = side ? ctx->sm_count - 1 : ctx->sm_count;
             auto launch_edges = [&](cudaStream_t st) {
                 ProfScope ps(ctx, ename, (l.n_edge + 65534) / 65535, st);
                 return is2048 ? thb::launch_stft_fast(pd, l.d_edge, l.n_edge, l.max_edge_frames, ctx->sm_count, st)
@@ -348,16 +353,15 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
             }
             if (e == cudaSuccess && l.n_pair) {
                 const unsigned tf = static_cast<unsigned>(is2048 ? thb::stft_pair_tile_frames() : thb::stft_warp_tile_frames(pd));
-                // [0] = rescue count, [1 .. pair_tiles] = one flag per tile, [pair_tiles + 1] = the work-item counter
-                thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
-                                   static_cast<unsigned>(ctx->rescue_cap), tf,
-                                   static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf), nullptr};
-                if (is2048) rl.next_item = ctx->d_rescue_count + 1 + l.pair_tiles;
-                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 2), ctx->stream));
+                // [0] = rescue count, [1 .. pair_tiles] = one flag per tile
+                const thb::RescueList rl{ctx->d_rescue_items, ctx->d_rescue_count, ctx->d_rescue_count + 1,
+                                         static_cast<unsigned>(ctx->rescue_cap), tf,
+                                         static_cast<unsigned>((l.max_pair_frames + tf - 1) / tf)};
+                CK(cudaMemsetAsync(ctx->d_rescue_count, 0, sizeof(unsigned) * (l.pair_tiles + 1), ctx->stream));
                 {
                     ProfScope ps(ctx, kname, 1);  // the packed kernel alone: this is the roofline kernel
-                    e = is2048 ? thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream)
-                               : thb::launch_stft_warp_packed(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, ctx->sm_count, ctx->stream);
+                    e = is2048 ? thb::launch_stft_pair(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, pair_sms, ctx->stream)
+                               : thb::launch_stft_warp_packed(pd, l.d_pair, l.n_pair, rl, l.i16, l.pair_unaligned, pair_sms, ctx->stream);
                 }
                 if (e == cudaSuccess) {
                     ProfScope ps(ctx, ename, 1);

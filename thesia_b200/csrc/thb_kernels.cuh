@@ -63,8 +63,6 @@ struct RescueList {
     unsigned capacity;
     unsigned tile_frames;
     unsigned tiles_per_track;
-    unsigned *next_item;   // frame-pair kernel: work items are handed out through this counter (zeroed with the flags);
-                           // null: item = blockIdx.x + k gridDim.x
 };
 
 struct ImgDesc {
