@@ -49,6 +49,9 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 // = Pad::pad(.., PadMode::Reflect) of utils.rs:111-137 including its multi-wrap cycle().
 __device__ __forceinline__ long long reflect_index(long long s, long long n) {
     if (s >= 0 && s < n) return s;
+    // one reflection (every frame of a file at least half a window long): no 64-bit division
+    if (s < 0 && -s < n) return -s;
+    if (s >= n && s <= 2 * (n - 1)) return 2 * (n - 1) - s;
     const long long period = 2 * (n - 1);
     long long m = s % period;
     if (m < 0) m += period;
