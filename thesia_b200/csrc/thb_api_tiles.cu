@@ -322,6 +322,7 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
     uint16_t *d_tmp = reinterpret_cast<uint16_t *>(lane.d_scratch);
     uint8_t *d_out = lane.d_scratch + tmp_bytes;
     size_t tmp_off = 0, out_off = 0;
+    int n_identity = 0;
     for (size_t k = 0; k < m; k++) {
         const Work &w = work[k];
         thb::TileDesc &t = h[k];
@@ -343,14 +344,15 @@ int thb_spectrogram_tile_batch(thb_ctx *ctx, const uint8_t *colormap_rgba, size_
         t.tmp = d_tmp + tmp_off;
         t.out = d_out + out_off;
         t.identity = axs[k]->identity && ays[k]->identity ? 1u : 0u;
+        n_identity += static_cast<int>(t.identity);
         t.x_first = axs[k]->first;
         tmp_off += (static_cast<size_t>(t.tmp_h) * t.width + 7) & ~size_t(7);
         out_off += static_cast<size_t>(t.width) * t.height * 4;
     }
     CK(cudaMemcpyAsync(lane.d_buf, lane.h_buf, desc_bytes + colormap_bytes, cudaMemcpyHostToDevice, lane.stream));
     {
-        ProfScope ps(ctx, "spectrogram_tile", 2 * static_cast<int>((m + 65534) / 65535), lane.stream);
-        cudaError_t e = thb::launch_spectrogram_tiles(d_desc, static_cast<int>(m), max_w, max_h, max_tmp_h, d_cm,
+        ProfScope ps(ctx, "spectrogram_tile", thb::spectrogram_tile_launches(static_cast<int>(m), n_identity), lane.stream);
+        cudaError_t e = thb::launch_spectrogram_tiles(d_desc, static_cast<int>(m), n_identity, max_w, max_h, max_tmp_h, d_cm,
                                                       static_cast<unsigned>(colormap_bytes / 4), lane.stream);
         if (e != cudaSuccess) return fail(ctx, THB_ERR_CUDA, "spectrogram_tile: %s", cudaGetErrorString(e));
     }

@@ -51,6 +51,7 @@ struct PlanDev {
     const float *big_w;               // per group [steps][32 lanes], zero padded
     const uint32_t *big_pptr;         // [n_mel + 1] pieces of band m: big_pptr[m] .. big_pptr[m + 1]
     int big_n_pieces;
+    int load_all_rows;                // thb_stft_warp.cu, A/B switch (THB_WARP_ALLROWS=1): also load the rows of the FFT buffer that hold no window tap
 };
 
 // Tiles (tile_frames consecutive frames of one descriptor) that the frame-pair kernel could not finish
@@ -197,8 +198,11 @@ cudaError_t launch_gain_peak(const GainDesc *d_descs, int n, long long max_len, 
 cudaError_t launch_gain_apply(const GainDesc *d_descs, int n, long long max_len, int mode, const unsigned *d_group_peak,
                               double *d_part_ss, GainOut *d_outs, cudaStream_t st);
 
-// spectrogram tiles (thb_tile.cu): grid y is sized for the largest tile of the batch, the others return early
-cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, unsigned max_w, unsigned max_h, unsigned max_tmp_h,
+// spectrogram tiles (thb_tile.cu): grid y is sized for the largest tile of the batch, the others return early;
+// n_identity = how many descriptors have `identity` set (the copy kernel / the two resample kernels are launched only
+// when the batch holds tiles of their kind); spectrogram_tile_launches = the number of launches that makes
+int spectrogram_tile_launches(int n, int n_identity);
+cudaError_t launch_spectrogram_tiles(const TileDesc *d_descs, int n, int n_identity, unsigned max_w, unsigned max_h, unsigned max_tmp_h,
                                      const uchar4 *d_colormap, unsigned colors, cudaStream_t st);
 
 cudaError_t launch_synth_pcm(float *d_out, unsigned long long len, uint32_t sr, uint32_t track,

@@ -273,6 +273,12 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
     const long long tiles_per_track = rescue.tiles_per_track;
     const int tile_frames = static_cast<int>(rescue.tile_frames);
     if (LIST) n_items = min(*rescue.count, rescue.capacity);
+    // rows of 64 FFT positions that hold a window tap: the reference zero-pads the windowed frame to n_fft (stft.rs:35-48),
+    // so at 40 ms / 16 kHz (win 640 in n_fft 1024) six of the sixteen rows are zeros and are not loaded at all
+    unsigned live_rows = 0;
+#pragma unroll
+    for (int n1 = 0; n1 < R1; n1++)
+        if (p.load_all_rows || (64 * n1 + 63 >= p.pad_left && 64 * n1 < p.pad_left + p.win)) live_rows |= 1u << n1;
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         long long track, tile_idx;
@@ -342,8 +348,10 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                         const float *src_b = d.pcm + (first_b - d.pcm_offset) + 2 * lane;
 #pragma unroll
                         for (int n1 = 0; n1 < R1; n1++) {
-                            const float2 xa = __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1));
-                            const float2 xb = __ldg(reinterpret_cast<const float2 *>(src_b + 64 * n1));
+                            const bool live = (live_rows >> n1) & 1u;
+                            const float2 zero2 = make_float2(0.0f, 0.0f);
+                            const float2 xa = live ? __ldg(reinterpret_cast<const float2 *>(src_a + 64 * n1)) : zero2;
+                            const float2 xb = live ? __ldg(reinterpret_cast<const float2 *>(src_b + 64 * n1)) : zero2;
                             const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
                             v[g * R1 + n1].re = make_float2(xa.x * w.x, xb.x * w.x);
                             v[g * R1 + n1].im = make_float2(xa.y * w.y, xb.y * w.y);
@@ -390,8 +398,9 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                             const float2 w = *reinterpret_cast<const float2 *>(sm.wpad + 64 * n1 + 2 * lane);
                             // the packed kernel's I16 path multiplies the INTEGER sample by (window * 2^-15); the exact
                             // power of two commutes with the rounding, so (s * 2^-15) * w is the same f32 value
-                            v[g * R1 + n1].re = pcm_sample(d, at + 64 * n1) * w.x;
-                            v[g * R1 + n1].im = pcm_sample(d, at + 64 * n1 + 1) * w.y;
+                            const bool live = (live_rows >> n1) & 1u;
+                            v[g * R1 + n1].re = (live ? pcm_sample(d, at + 64 * n1) : 0.0f) * w.x;
+                            v[g * R1 + n1].im = (live ? pcm_sample(d, at + 64 * n1 + 1) : 0.0f) * w.y;
                         }
                     } else {
 #pragma unroll
@@ -673,7 +682,10 @@ cudaError_t launch_one(const PlanDev &plan, const TrackDesc *d_tracks, long long
     auto kern = stft_warp_kernel<V, R1, MEL, I16, UNAL, LIST, NW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, st>>>(plan, d_tracks, n_items, rescue);
+    static const char *all_rows = getenv("THB_WARP_ALLROWS");
+    PlanDev pl = plan;
+    pl.load_all_rows = all_rows && atoi(all_rows) != 0;
+    kern<<<grid, NW * 32, smem, st>>>(pl, d_tracks, n_items, rescue);
     return cudaGetLastError();
 }
 
