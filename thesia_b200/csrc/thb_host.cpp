@@ -383,13 +383,17 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
         it.valid = true;
         return it;
     }
-    it.direct_L.assign(n_rounds, 0);
-    it.direct_woff.assign(n_rounds, 0);
-    it.direct_k0.assign(static_cast<size_t>(n_rounds) * 32, 0);
+    // Rounds come in PAIRS that the kernels walk together (two independent load -> FMA chains per lane: one chain alone
+    // is latency bound, mel_direct2 in thb_stft2048.cuh): both rounds of a pair get the pair's longest band as their
+    // step count, and an odd count of rounds is completed with a round of zero weights whose bands do not exist.
+    const uint32_t d_rounds = (n_rounds + 1) & ~1u;
+    it.direct_L.assign(d_rounds, 0);
+    it.direct_woff.assign(d_rounds, 0);
+    it.direct_k0.assign(static_cast<size_t>(d_rounds) * 32, 0);
     uint32_t direct_steps = 0;
-    for (uint32_t r = 0; r < n_rounds; r++) {
+    for (uint32_t r = 0; r < d_rounds; r++) {
         uint32_t L = 0;
-        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
+        for (uint32_t m = 32 * (r & ~1u); m < std::min(M, 32 * (r & ~1u) + 64); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
         L = (L + 3) & ~3u;  // four steps per trip
         it.direct_L[r] = L;
         it.direct_woff[r] = static_cast<uint32_t>(it.direct_w.size());
@@ -401,17 +405,19 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
                 it.direct_w[it.direct_woff[r] + static_cast<size_t>(i - b.ptr[m]) * 32 + (m - 32 * r)] = b.w[i];
             it.direct_reach = std::max<uint32_t>(it.direct_reach, b.k0[m] + L - 1);
         }
+        it.direct_reach = std::max<uint32_t>(it.direct_reach, L ? L - 1 : 0);   // lanes without a band read bins 0 .. L - 1
     }
     // Cost of a frame pair in issue slots.  bin-major, from the kernels' SASS: 36 per group + 4.75 per step + per round
-    // 12 + 13 per row of four gather entries.  band-major: 10 per round + 5 per step -- the walk is one short dependent
-    // chain per lane, so a step costs more than its 3.5 instructions (measured on B200, DESIGN.md section 4: 8.6 per step
-    // before the walk took four steps per trip).  The band-major schedule is chosen only when it is clearly cheaper: a
-    // bank of WIDE bands (mel 128 at 48 kHz: up to 64 bins per band, one lane each) is 13 % slower on it.
+    // 12 + 13 per row of four gather entries.  band-major: 10 per round + 4 per step (of the padded pairs) -- the walk is
+    // a short dependent chain per lane, so a step costs more than its 3.5 instructions (measured on B200, DESIGN.md
+    // section 4: 8.6 per step with one step per trip, ~5 with four, two rounds at a time since).  The band-major schedule
+    // is chosen only when it is clearly cheaper: a bank of WIDE bands (mel 128 at 48 kHz: up to 64 bins per band, one lane
+    // each) is 13 % slower on it.
     uint32_t steps = 0, rows_of4 = 0;
     for (uint32_t g = 0; g < it.n_groups; g++) steps += it.T[g];
     for (uint32_t r = 0; r < n_rounds; r++) rows_of4 += it.gk4[r];
     const double cost_bin = 36.0 * it.n_groups + 4.75 * steps + 12.0 * n_rounds + 13.0 * rows_of4;
-    const double cost_band = 10.0 * n_rounds + 5.0 * direct_steps;
+    const double cost_band = 10.0 * n_rounds + 4.0 * direct_steps;
     it.use_direct = cost_band < 0.75 * cost_bin;
     it.valid = true;
     return it;

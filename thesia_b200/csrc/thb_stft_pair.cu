@@ -317,12 +317,8 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                     else mel_walk<float2>(mv, mag, part, lane);
                     __syncwarp();
                 }
-                for (int r = 0; 32 * r < mv.n_mel; r++) {
-                    const int m = 32 * r + lane;
-                    f2 acc;
-                    if constexpr (DIRECT) acc = mel_direct<float2>(mv, mag, r, lane);
-                    else acc = M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane);
-                    if (m >= mv.n_mel) continue;
+                auto emit = [&](int m, f2 acc) {
+                    if (m >= mv.n_mel) return;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
                     orow_b[m] = db.y;
@@ -330,6 +326,17 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                         lmax = fmaxf(lmax, fmaxf(db.x, db.y));
                         lnmin = fmaxf(lnmin, fmaxf(-db.x, -db.y));
                     }
+                };
+                if constexpr (DIRECT) {
+                    for (int r = 0; 32 * r < mv.n_mel; r += 2) {   // two rounds per walk (the host pads them in pairs)
+                        f2 acc_a, acc_b;
+                        mel_direct2<float2>(mv, mag, r, lane, acc_a, acc_b);
+                        emit(32 * r + lane, acc_a);
+                        emit(32 * r + 32 + lane, acc_b);
+                    }
+                } else {
+                    for (int r = 0; 32 * r < mv.n_mel; r++)
+                        emit(32 * r + lane, M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane));
                 }
                 __syncwarp();
             }

@@ -225,7 +225,9 @@ __host__ __device__ inline int warp_tile_f2(const PlanDev &p) {
 
 // V = float2: NW warps, one persistent CTA per SM.  V = float: 8 warps, 2 CTAs per SM.
 // LIST (scalar only): walk the rescue list the packed kernel left behind instead of the (descriptor, tile) grid.
-template <typename V, int R1, bool MEL, bool I16, bool UNAL, bool LIST, int NW>
+// DIRECT (packed only): the plan's mel schedule is the band-major one -- a compile-time variant so that each packed kernel
+// carries one schedule's code (instruction-cache footprint: DESIGN.md section 4); the scalar twin decides at run time.
+template <typename V, int R1, bool MEL, bool I16, bool UNAL, bool LIST, int NW, bool DIRECT = false>
 __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
     stft_warp_kernel(const PlanDev p, const TrackDesc *__restrict__ tracks, long long n_items, RescueList rescue) {
     using O = Ops<V>;
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                 for (int g = 0; g < G; g++) {
                     const long long fg = f0 + static_cast<long long>(FPG) * g;
                     if (fg >= f_end) break;
-                    if (!mv.direct) {
+                    if (kPacked ? !DIRECT : !mv.direct) {
                         mel_walk4<V>(mv, mag0 + g * mag_stride, part, lane);
                         __syncwarp();
                     }
@@ -623,10 +625,8 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                     const bool has1 = kPacked && fg + 1 < f_end;
                     const bool g_ok = __shfl_sync(0xffffffffu, group_ok ? 1 : 0, g * R1) != 0;
                     const float g_off = __shfl_sync(0xffffffffu, db_off, g * R1);
-                    for (int r = 0; 32 * r < mv.n_mel; r++) {
-                        const int m = 32 * r + lane;
-                        const V acc = mv.direct ? mel_direct<V>(mv, mag0 + g * mag_stride, r, lane) : mel_band4<V>(mv, part, r, lane);
-                        if (m >= mv.n_mel) continue;
+                    auto emit = [&](int m, V acc) {
+                        if (m >= mv.n_mel) return;
                         if constexpr (kPacked) {
                             const float2 db = O::muls(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), kDbPerLog2Amp);
                             row0[m] = db.x;
@@ -642,6 +642,19 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                             lmax = fmaxf(lmax, db);
                             lnmin = fmaxf(lnmin, -db);
                         }
+                    };
+                    if constexpr (kPacked && DIRECT) {
+                        for (int r = 0; 32 * r < mv.n_mel; r += 2) {   // two rounds per walk (the host pads them in pairs)
+                            V acc_a, acc_b;
+                            mel_direct2<V>(mv, mag0 + g * mag_stride, r, lane, acc_a, acc_b);
+                            emit(32 * r + lane, acc_a);
+                            emit(32 * r + 32 + lane, acc_b);
+                        }
+                    } else if constexpr (kPacked) {
+                        for (int r = 0; 32 * r < mv.n_mel; r++) emit(32 * r + lane, mel_band4<V>(mv, part, r, lane));
+                    } else {
+                        for (int r = 0; 32 * r < mv.n_mel; r++)
+                            emit(32 * r + lane, mv.direct ? mel_direct<V>(mv, mag0 + g * mag_stride, r, lane) : mel_band4<V>(mv, part, r, lane));
                     }
                     __syncwarp();
                 }
@@ -676,10 +689,10 @@ size_t warp_smem_bytes(const PlanDev &p, int nw) {
            sizeof(uint32_t) * static_cast<size_t>(p.n_mel ? p.mi_words : 0);
 }
 
-template <typename V, int R1, bool MEL, bool I16, bool UNAL, bool LIST, int NW>
+template <typename V, int R1, bool MEL, bool I16, bool UNAL, bool LIST, int NW, bool DIRECT = false>
 cudaError_t launch_one(const PlanDev &plan, const TrackDesc *d_tracks, long long n_items, int grid, RescueList rescue, cudaStream_t st) {
     const size_t smem = warp_smem_bytes<V>(plan, NW);
-    auto kern = stft_warp_kernel<V, R1, MEL, I16, UNAL, LIST, NW>;
+    auto kern = stft_warp_kernel<V, R1, MEL, I16, UNAL, LIST, NW, DIRECT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     static const char *all_rows = getenv("THB_WARP_ALLROWS");
@@ -689,19 +702,18 @@ cudaError_t launch_one(const PlanDev &plan, const TrackDesc *d_tracks, long long
     return cudaGetLastError();
 }
 
+template <int R1, bool MEL, bool DIRECT>
+cudaError_t launch_packed_md(const PlanDev &plan, const TrackDesc *d, long long n_items, int grid, RescueList rl, bool i16, bool unal, cudaStream_t st) {
+    if (i16) return unal ? launch_one<float2, R1, MEL, true, true, false, kPackedWarps, DIRECT>(plan, d, n_items, grid, rl, st)
+                         : launch_one<float2, R1, MEL, true, false, false, kPackedWarps, DIRECT>(plan, d, n_items, grid, rl, st);
+    return unal ? launch_one<float2, R1, MEL, false, true, false, kPackedWarps, DIRECT>(plan, d, n_items, grid, rl, st)
+                : launch_one<float2, R1, MEL, false, false, false, kPackedWarps, DIRECT>(plan, d, n_items, grid, rl, st);
+}
 template <int R1>
 cudaError_t launch_packed_r1(const PlanDev &plan, const TrackDesc *d, long long n_items, int grid, RescueList rl, bool i16, bool unal, cudaStream_t st) {
-    const bool mel = plan.n_mel != 0;
-    if (mel) {
-        if (i16) return unal ? launch_one<float2, R1, true, true, true, false, kPackedWarps>(plan, d, n_items, grid, rl, st)
-                             : launch_one<float2, R1, true, true, false, false, kPackedWarps>(plan, d, n_items, grid, rl, st);
-        return unal ? launch_one<float2, R1, true, false, true, false, kPackedWarps>(plan, d, n_items, grid, rl, st)
-                    : launch_one<float2, R1, true, false, false, false, kPackedWarps>(plan, d, n_items, grid, rl, st);
-    }
-    if (i16) return unal ? launch_one<float2, R1, false, true, true, false, kPackedWarps>(plan, d, n_items, grid, rl, st)
-                         : launch_one<float2, R1, false, true, false, false, kPackedWarps>(plan, d, n_items, grid, rl, st);
-    return unal ? launch_one<float2, R1, false, false, true, false, kPackedWarps>(plan, d, n_items, grid, rl, st)
-                : launch_one<float2, R1, false, false, false, false, kPackedWarps>(plan, d, n_items, grid, rl, st);
+    if (!plan.n_mel) return launch_packed_md<R1, false, false>(plan, d, n_items, grid, rl, i16, unal, st);
+    return plan.mi_direct ? launch_packed_md<R1, true, true>(plan, d, n_items, grid, rl, i16, unal, st)
+                          : launch_packed_md<R1, true, false>(plan, d, n_items, grid, rl, i16, unal, st);
 }
 
 template <int R1, bool LIST>
