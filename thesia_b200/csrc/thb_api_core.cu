@@ -561,6 +561,7 @@ void thb_ctx_destroy(thb_ctx *ctx) {
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
     if (ctx->d_rescue_items) cudaFree(ctx->d_rescue_items);
+    if (ctx->d_img_desc) cudaFree(ctx->d_img_desc);
     if (ctx->d_rescue_count) cudaFree(ctx->d_rescue_count);
     if (ctx->d_send) cudaFree(ctx->d_send);
     if (ctx->d_range) cudaFree(ctx->d_range);

@@ -608,10 +608,9 @@ static int quantise_on_stream(thb_ctx *ctx, uint32_t colormap_length, uint32_t m
     if (max_sr == 0)
         for (auto &kv : ctx->specs) max_sr = std::max(max_sr, kv.second.sr);  // tracklist.max_sr() (track.rs:371-376)
     const size_t n = ctx->specs.size();
-    int rc = arena_begin(ctx, (sizeof(thb::ImgDesc) + 64) * n + 1024);
-    if (rc) return rc;
-    thb::ImgDesc *d_desc = nullptr;
-    thb::ImgDesc *h = n ? arena_push<thb::ImgDesc>(ctx, n, &d_desc) : nullptr;
+    int rc = THB_OK;
+    std::vector<unsigned char> raw(sizeof(thb::ImgDesc) * (n ? n : 1), 0);   // (zeroed: the padding takes part in the compare)
+    thb::ImgDesc *h = reinterpret_cast<thb::ImgDesc *>(raw.data());
     long long max_T = 0;
     int max_H = 0;
     size_t j = 0;
@@ -632,8 +631,37 @@ static int quantise_on_stream(thb_ctx *ctx, uint32_t colormap_length, uint32_t m
         max_H = std::max(max_H, h[j].H);
         j++;
     }
-    if ((rc = arena_commit(ctx))) return rc;
-    if (j) {
+    if (!j) return THB_OK;
+    raw.resize(sizeof(thb::ImgDesc) * j);
+    // The descriptors live in a device buffer of their own and are uploaded only when they differ from the last call's:
+    // in a loop over the same retained spectrograms the quantiser then follows the range exchange directly in the
+    // stream (no host-to-device copy between them: one DMA round trip less per step, and the quantiser can be launched
+    // under the exchange kernel, thb_kernels.cuh launch_pdl).
+    if (!ctx->d_img_desc || raw != ctx->img_desc_host) {
+        if (raw.size() > ctx->img_desc_cap) {
+            CK(cudaStreamSynchronize(ctx->stream));  // a queued quantiser may still read the old buffer
+            if (ctx->d_img_desc) cudaFree(ctx->d_img_desc);
+            ctx->d_img_desc = nullptr;
+            ctx->img_desc_cap = 0;
+            ctx->img_desc_host.clear();
+            size_t cap = 4096;
+            while (cap < raw.size()) cap <<= 1;
+            CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_img_desc), cap));
+            ctx->img_desc_cap = cap;
+        }
+        // through the pinned arena mirror (ring of four: rewritten only after this copy has been consumed)
+        if ((rc = arena_begin(ctx, raw.size() + 1024))) return rc;
+        unsigned char *d_unused = nullptr;
+        unsigned char *pin = arena_push<unsigned char>(ctx, raw.size(), &d_unused);
+        memcpy(pin, raw.data(), raw.size());
+        ctx->img_desc_host.clear();   // (stays empty if the copy cannot be queued)
+        CK(cudaMemcpyAsync(ctx->d_img_desc, pin, raw.size(), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->arena_used = 0;          // nothing for arena_commit to copy: it only marks the mirror as in flight
+        if ((rc = arena_commit(ctx))) return rc;
+        ctx->img_desc_host = raw;
+    }
+    const thb::ImgDesc *d_desc = reinterpret_cast<const thb::ImgDesc *>(ctx->d_img_desc);
+    {
         ProfScope ps(ctx, "spec_to_img", static_cast<int>((j + 65534) / 65535));
         cudaError_t e = thb::launch_spec_to_img(d_desc, static_cast<int>(j), max_T, max_H, ctx->d_range, colormap_length,
                                                 img_tile_mode(h, j), ctx->stream);

@@ -153,6 +153,13 @@ struct thb_ctx {
     unsigned *d_rescue_count = nullptr;  // [0] = count, [1 ..] = one flag per (descriptor, tile)
     size_t rescue_cap = 0;
 
+    // the quantiser's descriptors of the last thb_update_spec_imgs: re-quantising the same retained spectrograms (a new
+    // dB range, another colormap length, the next step of a batch loop) reuses the device copy instead of uploading it
+    // between the range exchange and the quantiser
+    std::vector<unsigned char> img_desc_host;
+    unsigned char *d_img_desc = nullptr;
+    size_t img_desc_cap = 0;
+
     std::vector<void *> env_outputs;  // device buffers of the last waveform level call
 
     // resize axes of the spectrogram tiles (thb_host.hpp ResizeAxis) on the device, keyed by

@@ -75,6 +75,13 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
+// Programmatic dependent launch (sm_90+).  A kernel launched through launch_pdl() (thb_kernels.cuh) may be scheduled while
+// the kernel before it in the stream is still draining; pdl_wait() returns once that kernel has completed and its writes
+// are visible -- it is the first statement of every kernel launched that way, and a no-op in a kernel launched the
+// ordinary way.  pdl_launch_dependents() lets the NEXT kernel's CTAs become resident (they then sit in their pdl_wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

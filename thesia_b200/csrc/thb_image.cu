@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) minmax_array_kernel(const float *__restri
 
 // one warp: max over all slots of {max, -min}  (the rayon reduce of mod.rs:169-178)
 __global__ void minmax_reduce_kernel(const float *__restrict__ slots, int n_slots, float *send) {
+    pdl_wait();
     float a = -CUDART_INF_F, b = -CUDART_INF_F;
     for (int i = threadIdx.x; i < n_slots; i += 32) {
         a = fmaxf(a, slots[2 * i]);
@@ -69,6 +70,8 @@ __global__ void minmax_reduce_kernel(const float *__restrict__ slots, int n_slot
 // every rank has finished reading step s.  `fail` is set (and the range left NaN) if a peer does not show up in ~5 s.
 __global__ void minmax_exchange_kernel(const float *__restrict__ slots, int n_slots, float4 *const *peers, float4 *mine, int n_ranks,
                                        int rank, unsigned seq, float dB_range, float *range, float *send, unsigned *fail) {
+    pdl_wait();
+    pdl_launch_dependents();   // the quantiser's CTAs may take their places while this warp waits for the peers
     const int lane = threadIdx.x;
     float a = -CUDART_INF_F, b = -CUDART_INF_F;
     for (int i = lane; i < n_slots; i += 32) {
@@ -120,6 +123,7 @@ __global__ void minmax_exchange_kernel(const float *__restrict__ slots, int n_sl
 
 // max <- min(max, 0); min <- max(min, max - dB_range)   (mod.rs:179-180)
 __global__ void minmax_finalize_kernel(const float *__restrict__ send, float dB_range, float *range) {
+    pdl_wait();
     const float mx = fminf(send[0], 0.0f);
     const float mn = fmaxf(-send[1], __fsub_rn(mx, dB_range));
     range[0] = mn;
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(256) spec_to_img_kernel(const ImgDesc *__restr
                                                           const float *__restrict__ range,
                                                           float min_value_f, float u16_span) {
     __shared__ uint16_t tile[kTileB][kTileT + 2];
+    pdl_wait();   // launched under the range kernel: d_range (and, in stream order, the spectrograms) are ready from here on
     const ImgDesc d = descs[blockIdx.z];
     const long long t0 = static_cast<long long>(blockIdx.x) * kTileT;
     const int r0 = blockIdx.y * kTileB;  // image row (relative to i0)
@@ -222,6 +227,7 @@ __global__ void __launch_bounds__(256) spec_to_img_tile_kernel(const ImgDesc *__
                                                                 const float *__restrict__ range, float min_value_f,
                                                                 float u16_span) {
     __shared__ uint32_t tile[kBigB][kBigT / 2];
+    pdl_wait();   // launched under the range kernel: d_range (and, in stream order, the spectrograms) are ready from here on
     const ImgDesc d = descs[blockIdx.z];
     const long long t0 = static_cast<long long>(blockIdx.x) * kBigT;
     const int r0 = blockIdx.y * kBigB;
@@ -353,19 +359,17 @@ cudaError_t launch_minmax_array(const float *d_x, unsigned long long n, float *d
 }
 
 cudaError_t launch_minmax_reduce(const float *d_slots, int n_slots, float *d_send, cudaStream_t st) {
-    minmax_reduce_kernel<<<1, 32, 0, st>>>(d_slots, n_slots, d_send);
-    return cudaGetLastError();
+    return launch_pdl(minmax_reduce_kernel, dim3(1), dim3(32), 0, st, d_slots, n_slots, d_send);
 }
 
 cudaError_t launch_minmax_exchange(const float *d_slots, int n_slots, float4 *const *d_peers, float4 *d_mine, int n_ranks, int rank,
                                    unsigned seq, float dB_range, float *d_range, float *d_send, unsigned *d_fail, cudaStream_t st) {
-    minmax_exchange_kernel<<<1, 32, 0, st>>>(d_slots, n_slots, d_peers, d_mine, n_ranks, rank, seq, dB_range, d_range, d_send, d_fail);
-    return cudaGetLastError();
+    return launch_pdl(minmax_exchange_kernel, dim3(1), dim3(32), 0, st, d_slots, n_slots, d_peers, d_mine, n_ranks, rank, seq, dB_range, d_range,
+                      d_send, d_fail);
 }
 
 cudaError_t launch_minmax_finalize(const float *d_send, float dB_range, float *d_range, cudaStream_t st) {
-    minmax_finalize_kernel<<<1, 1, 0, st>>>(d_send, dB_range, d_range);
-    return cudaGetLastError();
+    return launch_pdl(minmax_finalize_kernel, dim3(1), dim3(1), 0, st, d_send, dB_range, d_range);
 }
 
 cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, int max_H,
@@ -384,15 +388,12 @@ cudaError_t launch_spec_to_img(const ImgDesc *d_descs, int n, long long max_T, i
     for (int t0 = 0; t0 < n; t0 += 65535) {
         const int nt = n - t0 < 65535 ? n - t0 : 65535;
         dim3 grid(gx, gy, static_cast<unsigned>(nt));
-        if (tile_mode == 3)
-            spec_to_img_tile_kernel<true, true><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
-        else if (tile_mode == 2)
-            spec_to_img_tile_kernel<true, false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
-        else if (tile_mode == 1)
-            spec_to_img_tile_kernel<false, false><<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
-        else
-            spec_to_img_kernel<<<grid, 256, 0, st>>>(d_descs + t0, d_range, static_cast<float>(min_value), u16_span);
-        cudaError_t e = cudaGetLastError();
+        const float mv = static_cast<float>(min_value);
+        cudaError_t e;
+        if (tile_mode == 3) e = launch_pdl(spec_to_img_tile_kernel<true, true>, grid, dim3(256), 0, st, d_descs + t0, d_range, mv, u16_span);
+        else if (tile_mode == 2) e = launch_pdl(spec_to_img_tile_kernel<true, false>, grid, dim3(256), 0, st, d_descs + t0, d_range, mv, u16_span);
+        else if (tile_mode == 1) e = launch_pdl(spec_to_img_tile_kernel<false, false>, grid, dim3(256), 0, st, d_descs + t0, d_range, mv, u16_span);
+        else e = launch_pdl(spec_to_img_kernel, grid, dim3(256), 0, st, d_descs + t0, d_range, mv, u16_span);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

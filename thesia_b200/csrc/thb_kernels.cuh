@@ -1,6 +1,7 @@
 // thb_kernels.cuh -- launch interface between the C-ABI layer (thb_api.cu) and the sm_100a
 // kernels (thb_stft.cu, thb_image.cu, thb_envelope.cu).  Device pointers only.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -119,6 +120,26 @@ struct TileDesc {
 __device__ __forceinline__ float pcm_sample(const TrackDesc &d, long long idx) {
     if (d.pcm_i16) return static_cast<float>(__ldg(reinterpret_cast<const short *>(d.pcm) + idx)) * 3.0517578125e-05f;
     return __ldg(d.pcm + idx);
+}
+
+// Launch `kern` so that it may be scheduled under the tail of the kernel before it in the stream (programmatic stream
+// serialisation); the kernel's first statement is pdl_wait().  What it buys is the launch latency between the small
+// dependent kernels of a step (rescue list -> range exchange -> quantiser): a few microseconds each, which is what a
+// 250 us step of a frame-range shard at N = 8 is made of.  THB_PDL=0 launches the ordinary way.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool on = !(getenv("THB_PDL") && atoi(getenv("THB_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---- launchers (all asynchronous on `st`) ----

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
     const int tile_frames = LIST ? static_cast<int>(rescue.tile_frames) : kTileFrames;
     unsigned n_items = 1;
     if (LIST) {
+        pdl_wait();   // launched under the tail of the frame-pair kernel that fills the list
         n_items = min(*rescue.count, rescue.capacity);
         if (blockIdx.x >= n_items) return;
     } else if (static_cast<long long>(blockIdx.x) * kTileFrames >= tracks[blockIdx.y].n_frames) {
@@ -353,8 +354,7 @@ cudaError_t launch_stft_fast_list(const PlanDev &plan, const TrackDesc *d_tracks
     auto kern = plan.n_mel ? stft2048_kernel<true, true> : stft2048_kernel<false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<2 * sm_count, kWarps * 32, smem, st>>>(plan, d_tracks, rescue);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(2 * sm_count), dim3(kWarps * 32), smem, st, plan, d_tracks, rescue);
 }
 
 }  // namespace thb

@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
     constexpr int FI = G * FPG;             // frames per warp step
     constexpr int NFFT = 64 * R1, NC = 32 * R1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (LIST) pdl_wait();   // launched under the tail of the packed kernel that fills the list
 
     const int tile_f2 = warp_tile_f2<V>(p);
     WarpSmem sm;
@@ -698,6 +699,7 @@ cudaError_t launch_one(const PlanDev &plan, const TrackDesc *d_tracks, long long
     static const char *all_rows = getenv("THB_WARP_ALLROWS");
     PlanDev pl = plan;
     pl.load_all_rows = all_rows && atoi(all_rows) != 0;
+    if (LIST) return launch_pdl(kern, dim3(grid), dim3(NW * 32), smem, st, pl, d_tracks, n_items, rescue);
     kern<<<grid, NW * 32, smem, st>>>(pl, d_tracks, n_items, rescue);
     return cudaGetLastError();
 }

@@ -51,7 +51,10 @@ def main():
         # name[:warps][/ENV=VALUE...]   e.g.  pair/THB_PAIR_PREFETCH=0/THB_MEL4=0
         head, *envs = var.split("/")
         name, _, nw = head.partition(":")
-        os.environ["THB_STFT_KERNEL"] = name
+        if name == "auto":   # the library's own choice
+            os.environ.pop("THB_STFT_KERNEL", None)
+        else:
+            os.environ["THB_STFT_KERNEL"] = name
         os.environ.pop("THB_PAIR_WARPS", None)
         for k in ("THB_PAIR_PREFETCH", "THB_MEL4", "THB_PAIR_SHARE", "THB_PAIR_PL", "THB_MEL_DIRECT"):
             os.environ.pop(k, None)
