@@ -281,23 +281,28 @@ static void test_tile_readers_overlap() {
     };
     int bad = 0;
     work(0, &bad);  // warm-up
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int c = 0; c < kThreads; c++) work(c, &bad);
-    const auto t1 = std::chrono::steady_clock::now();
-    std::vector<std::thread> ths;
-    std::vector<int> bads(kThreads, 0);
-    for (int c = 0; c < kThreads; c++) ths.emplace_back(work, c, &bads[c]);
-    for (auto &t : ths) t.join();
-    const auto t2 = std::chrono::steady_clock::now();
-    for (int b : bads) bad += b;
-    const double serial = std::chrono::duration<double>(t1 - t0).count(), parallel = std::chrono::duration<double>(t2 - t1).count();
-    std::printf("tile readers: %d x %d calls one after the other %.1f ms (%.1f us / tile), from %d threads %.1f ms (%.1f us / tile): %.2fx\n",
-                kThreads, kCalls, 1e3 * serial, 1e6 * serial / (kThreads * kCalls), kThreads, 1e3 * parallel,
-                1e6 * parallel / (kThreads * kCalls), serial / parallel);
+    // Wall clock on a shared box: up to three attempts, the bar must be met once (a context-wide lock fails all three).
+    bool overlapped = false;
+    for (int attempt = 0; attempt < 3 && !overlapped; attempt++) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int c = 0; c < kThreads; c++) work(c, &bad);
+        const auto t1 = std::chrono::steady_clock::now();
+        std::vector<std::thread> ths;
+        std::vector<int> bads(kThreads, 0);
+        for (int c = 0; c < kThreads; c++) ths.emplace_back(work, c, &bads[c]);
+        for (auto &t : ths) t.join();
+        const auto t2 = std::chrono::steady_clock::now();
+        for (int b : bads) bad += b;
+        const double serial = std::chrono::duration<double>(t1 - t0).count(), parallel = std::chrono::duration<double>(t2 - t1).count();
+        std::printf("tile readers: %d x %d calls one after the other %.1f ms (%.1f us / tile), from %d threads %.1f ms (%.1f us / tile): %.2fx, %d wrong\n",
+                    kThreads, kCalls, 1e3 * serial, 1e6 * serial / (kThreads * kCalls), kThreads, 1e3 * parallel,
+                    1e6 * parallel / (kThreads * kCalls), serial / parallel, bad);
+        // a context-wide lock would make the two equal (measured: 2.5x faster); under compute-sanitizer the tool itself
+        // serialises the launches, so the wall-clock bar is skipped there (THB_NO_TIMING=1)
+        overlapped = std::getenv("THB_NO_TIMING") || parallel < 0.8 * serial;
+    }
     EXPECT(bad == 0);
-    // a context-wide lock would make the two equal (measured: 2.5x faster); under compute-sanitizer the tool itself
-    // serialises the launches, so the wall-clock bar is skipped there (THB_NO_TIMING=1)
-    if (!std::getenv("THB_NO_TIMING")) EXPECT(parallel < 0.8 * serial);
+    EXPECT(overlapped);
 }
 
 int main(int argc, char **argv) {

@@ -383,9 +383,9 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
         it.valid = true;
         return it;
     }
-    // Rounds come in PAIRS that the kernels walk together (two independent load -> FMA chains per lane: one chain alone
-    // is latency bound, mel_direct2 in thb_stft2048.cuh): both rounds of a pair get the pair's longest band as their
-    // step count, and an odd count of rounds is completed with a round of zero weights whose bands do not exist.
+    // The packed kernels walk the rounds in PAIRS (two independent load -> FMA chains per lane while both rounds have
+    // steps left, then the longer one alone: mel_direct2 in thb_stft2048.cuh), so an odd count of rounds is completed
+    // with a round of no steps whose bands do not exist.
     const uint32_t d_rounds = (n_rounds + 1) & ~1u;
     it.direct_L.assign(d_rounds, 0);
     it.direct_woff.assign(d_rounds, 0);
@@ -393,7 +393,7 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
     uint32_t direct_steps = 0;
     for (uint32_t r = 0; r < d_rounds; r++) {
         uint32_t L = 0;
-        for (uint32_t m = 32 * (r & ~1u); m < std::min(M, 32 * (r & ~1u) + 64); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
+        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
         L = (L + 3) & ~3u;  // four steps per trip
         it.direct_L[r] = L;
         it.direct_woff[r] = static_cast<uint32_t>(it.direct_w.size());
@@ -408,7 +408,7 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
         it.direct_reach = std::max<uint32_t>(it.direct_reach, L ? L - 1 : 0);   // lanes without a band read bins 0 .. L - 1
     }
     // Cost of a frame pair in issue slots.  bin-major, from the kernels' SASS: 36 per group + 4.75 per step + per round
-    // 12 + 13 per row of four gather entries.  band-major: 10 per round + 4 per step (of the padded pairs) -- the walk is
+    // 12 + 13 per row of four gather entries.  band-major: 10 per round + 4 per step -- the walk is
     // a short dependent chain per lane, so a step costs more than its 3.5 instructions (measured on B200, DESIGN.md
     // section 4: 8.6 per step with one step per trip, ~5 with four, two rounds at a time since).  The band-major schedule
     // is chosen only when it is clearly cheaper: a bank of WIDE bands (mel 128 at 48 kHz: up to 64 bins per band, one lane
