@@ -201,7 +201,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
     std::vector<uint32_t> mi_blob;
     if (d.n_mel && (d.n_fft == 2048 || d.n_fft == 1024 || d.n_fft == 512 || d.n_fft == 4096 || d.n_fft == 8192 || d.n_fft == 16384)) {
         // (the large-FFT kernel walks the same bin-major schedule out of global memory)
-        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
+        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048, d.n_fft <= 1024);
         // THB_MEL_DIRECT=0|1 pins the mel schedule of the n_fft <= 2048 kernels (A/B runs); default: the cheaper one
         if (const char *e = getenv("THB_MEL_DIRECT")) mi.use_direct = mi.valid && d.n_fft <= 2048 && atoi(e) != 0;
         if (mi.valid) mi_blob = mi.blob();
@@ -212,7 +212,7 @@ int get_plan(thb_ctx *ctx, const thb_setting &s, uint32_t sr, const Plan **out) 
         }
     }
     if (!mi_blob.empty()) {
-        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048);
+        thb::MelItems mi = thb::mel_items(thb::mel_bank(sr, f.n_fft, s.n_mel), 2, d.n_fft <= 2048, d.n_fft <= 1024);
         if (const char *e = getenv("THB_MEL_DIRECT")) mi.use_direct = mi.valid && d.n_fft <= 2048 && atoi(e) != 0;
         d.mi_words = static_cast<int>(mi_blob.size());
         // the band-major schedule keeps no partial sums (no groups) and starts at the bands' own first bins
@@ -665,7 +665,7 @@ int thb_mel_fb(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t
 int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *out, uint32_t stats[4]) {
     if (!out || !stats || n_fft < 4) return THB_ERR_INVALID;
     const thb::MelBank mb = thb::mel_bank(sr, n_fft, n_mel);
-    const thb::MelItems mi = thb::mel_items(mb, 2, n_fft <= 2048);
+    const thb::MelItems mi = thb::mel_items(mb, 2, n_fft <= 2048, n_fft <= 1024);
     stats[0] = mi.valid ? 1u : 0u;
     stats[1] = mi.n_groups;
     stats[2] = stats[3] = 0;

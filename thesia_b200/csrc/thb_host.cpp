@@ -166,7 +166,7 @@ MelBank mel_bank(uint32_t sr, uint64_t n_fft, uint32_t n_mel) {
     }
 }
 
-MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
+MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct, bool direct_pairs) {
     MelItems it;
     const uint32_t tm = t_multiple < 2 ? 2 : t_multiple;  // the walk takes two steps per float4 of weights
     it.n_mel = b.n_mel;
@@ -383,17 +383,20 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
         it.valid = true;
         return it;
     }
-    // The packed kernels walk the rounds in PAIRS (two independent load -> FMA chains per lane while both rounds have
-    // steps left, then the longer one alone: mel_direct2 in thb_stft2048.cuh), so an odd count of rounds is completed
-    // with a round of no steps whose bands do not exist.
-    const uint32_t d_rounds = (n_rounds + 1) & ~1u;
+    // direct_pairs (thb_stft_warp.cu walks two rounds at a time: two independent load -> FMA chains per lane, mel_direct2
+    // in thb_stft2048.cuh): both rounds of a pair get the pair's longest band as their step count, and an odd count of
+    // rounds is completed with a round of zero weights whose bands do not exist.  The zero steps are shared-memory
+    // loads like any other: worth it where the walk is latency bound (n_fft 1024 / 512: -10 %), not in the n_fft 2048
+    // frame-pair kernel, whose shared-memory pipe is its busiest unit (+14 % at the 48 kHz default bank).
+    const uint32_t d_rounds = direct_pairs ? (n_rounds + 1) & ~1u : n_rounds;
     it.direct_L.assign(d_rounds, 0);
     it.direct_woff.assign(d_rounds, 0);
     it.direct_k0.assign(static_cast<size_t>(d_rounds) * 32, 0);
     uint32_t direct_steps = 0;
     for (uint32_t r = 0; r < d_rounds; r++) {
+        const uint32_t m_lo = direct_pairs ? 32 * (r & ~1u) : 32 * r, m_hi = std::min(M, m_lo + (direct_pairs ? 64u : 32u));
         uint32_t L = 0;
-        for (uint32_t m = 32 * r; m < std::min(M, 32 * r + 32); m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
+        for (uint32_t m = m_lo; m < m_hi; m++) L = std::max(L, b.ptr[m + 1] - b.ptr[m]);
         L = (L + 3) & ~3u;  // four steps per trip
         it.direct_L[r] = L;
         it.direct_woff[r] = static_cast<uint32_t>(it.direct_w.size());
@@ -417,7 +420,7 @@ MelItems mel_items(const MelBank &b, uint32_t t_multiple, bool with_direct) {
     for (uint32_t g = 0; g < it.n_groups; g++) steps += it.T[g];
     for (uint32_t r = 0; r < n_rounds; r++) rows_of4 += it.gk4[r];
     const double cost_bin = 36.0 * it.n_groups + 4.75 * steps + 12.0 * n_rounds + 13.0 * rows_of4;
-    const double cost_band = 10.0 * n_rounds + 4.0 * direct_steps;
+    const double cost_band = 10.0 * n_rounds + (direct_pairs ? 4.0 : 5.0) * direct_steps;
     it.use_direct = cost_band < 0.75 * cost_bin;
     it.valid = true;
     return it;

@@ -90,7 +90,9 @@ struct MelItems {
 // steps carry zero weights and add +0).  4 would spare the n_fft == 2048 walk its two-step tail but costs the default
 // banks (10 - 11 groups of 2 - 12 steps) 12 - 14 extra steps per frame pair: measured on the host, not adopted.
 // with_direct: also build the band-major schedule (n_fft <= 2048 kernels) and choose between the two
-MelItems mel_items(const MelBank &b, uint32_t t_multiple = 2, bool with_direct = false);
+// direct_pairs: the band-major rounds come in pairs of equal step count (zero-weight padding; an odd count of rounds is
+// completed with an empty round) for kernels that walk two rounds at a time (thb_stft_warp.cu: n_fft 1024 / 512)
+MelItems mel_items(const MelBank &b, uint32_t t_multiple = 2, bool with_direct = false, bool direct_pairs = false);
 float mel_from_hz(float hz);
 float mel_to_hz(float mel);
 // n_mel == 0 -> calc_mel_fb_default's rule

@@ -234,13 +234,14 @@ __device__ __forceinline__ V mel_direct(const MelView &mv, const V *mag, int r, 
     return O::add(acc0, acc1);
 }
 
-// Two rounds (bands 32 r + l and 32 r + 32 + l, r even) in one walk: while both rounds have steps left one loop carries
-// two independent load -> FMA chains per lane (four accumulators), then the longer round finishes alone.  Each band's
-// sum is formed exactly as in mel_direct -- same steps, same order, same two accumulators -- so the scalar kernels, which
-// still go round by round, agree bit for bit.  One round at a time measured ~390 cycles per round and warp at 10 - 12
-// resident warps: the latency of table word -> addresses -> eight loads -> FMA chain -> MUFU -> store with nothing to
-// overlap it with.  (Padding both rounds of a pair to a common step count instead was tried first: the zero steps are
-// shared-memory loads all the same, +33 % of them at the 48 kHz default bank, and the pair kernel lost 14 % there.)
+// Two rounds (bands 32 r + l and 32 r + 32 + l, r even) in one walk, for schedules built with direct_pairs (both rounds
+// of a pair have the same step count): one loop carries two independent load -> FMA chains per lane (four
+// accumulators).  Each band's sum is formed exactly as in mel_direct -- same steps, same order, same two accumulators --
+// so the scalar kernel, which still goes round by round, agrees bit for bit.  One round at a time measured ~390 cycles
+// per round and warp at 10 resident warps: the latency of table word -> addresses -> eight loads -> FMA chain -> MUFU ->
+// store with nothing to overlap it with.  Measured (ms, 32 ch x 10 min, default bank): 16 kHz 3.99 -> 3.58, 8 kHz
+// 2.40 -> 2.19, 22.05 kHz 3.77 -> 3.41, 24 kHz 3.68 -> 3.32; without the padding (joint loop, then the longer round alone)
+// 3.78 / 2.32 / 3.61 / 3.50 -- the lone tail is the slow part.
 template <typename V>
 __device__ __forceinline__ void mel_direct2(const MelView &mv, const V *mag, int r, int lane, V &acc_a, V &acc_b) {
     using O = MelOps<V>;
@@ -250,9 +251,8 @@ __device__ __forceinline__ void mel_direct2(const MelView &mv, const V *mag, int
     const V *ma = mag + mv.dk0[32 * r + lane];
     const V *mb = mag + mv.dk0[32 * r + 32 + lane];
     V a0 = O::zero(), a1 = O::zero(), b0 = O::zero(), b1 = O::zero();
-    const uint32_t joint = min(rd.x, rd.z);
 #pragma unroll 1
-    for (uint32_t i = 0; i < joint; i += 4) {
+    for (uint32_t i = 0; i < rd.x; i += 4) {
         const float wa0 = wa[0], wa1 = wa[32], wa2 = wa[64], wa3 = wa[96];
         const float wb0 = wb[0], wb1 = wb[32], wb2 = wb[64], wb3 = wb[96];
         const V ma0 = ma[0], ma1 = ma[1], ma2 = ma[2], ma3 = ma[3];
@@ -269,31 +269,6 @@ __device__ __forceinline__ void mel_direct2(const MelView &mv, const V *mag, int
         b0 = O::fma(mb2, wb2, b0);
         a1 = O::fma(ma3, wa3, a1);
         b1 = O::fma(mb3, wb3, b1);
-    }
-    const uint32_t longest = max(rd.x, rd.z);
-    if (longest > joint) {   // (uniform over the warp)
-        const bool a_longer = rd.x > rd.z;
-        const float *w = a_longer ? wa : wb;
-        const V *mq = a_longer ? ma : mb;
-        V t0 = a_longer ? a0 : b0, t1 = a_longer ? a1 : b1;
-#pragma unroll 1
-        for (uint32_t i = joint; i < longest; i += 4) {
-            const float w0 = w[0], w1 = w[32], w2 = w[64], w3 = w[96];
-            const V m0 = mq[0], m1 = mq[1], m2 = mq[2], m3 = mq[3];
-            w += 128;
-            mq += 4;
-            t0 = O::fma(m0, w0, t0);
-            t1 = O::fma(m1, w1, t1);
-            t0 = O::fma(m2, w2, t0);
-            t1 = O::fma(m3, w3, t1);
-        }
-        if (a_longer) {
-            a0 = t0;
-            a1 = t1;
-        } else {
-            b0 = t0;
-            b1 = t1;
-        }
     }
     acc_a = O::add(a0, a1);
     acc_b = O::add(b0, b1);

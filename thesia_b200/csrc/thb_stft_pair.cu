@@ -317,8 +317,14 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                     else mel_walk<float2>(mv, mag, part, lane);
                     __syncwarp();
                 }
-                auto emit = [&](int m, f2 acc) {
-                    if (m >= mv.n_mel) return;
+                // (two rounds per walk -- mel_direct2, as in thb_stft_warp.cu -- were measured here too: 5.04 -> 5.26 ms at the
+                // 48 kHz default bank, 5.75 with its padding; this kernel's shared-memory pipe is its busiest unit)
+                for (int r = 0; 32 * r < mv.n_mel; r++) {
+                    const int m = 32 * r + lane;
+                    f2 acc;
+                    if constexpr (DIRECT) acc = mel_direct<float2>(mv, mag, r, lane);
+                    else acc = M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane);
+                    if (m >= mv.n_mel) continue;
                     const f2 db = pmul(make_float2(lg2_ftz(acc.x), lg2_ftz(acc.y)), bc(kDbPerLog2Amp));
                     orow_a[m] = db.x;
                     orow_b[m] = db.y;
@@ -326,17 +332,6 @@ __global__ void __launch_bounds__(NW * 32, 1) stft2048_pair_kernel(const PlanDev
                         lmax = fmaxf(lmax, fmaxf(db.x, db.y));
                         lnmin = fmaxf(lnmin, fmaxf(-db.x, -db.y));
                     }
-                };
-                if constexpr (DIRECT) {
-                    for (int r = 0; 32 * r < mv.n_mel; r += 2) {   // two rounds per walk (the host pads them in pairs)
-                        f2 acc_a, acc_b;
-                        mel_direct2<float2>(mv, mag, r, lane, acc_a, acc_b);
-                        emit(32 * r + lane, acc_a);
-                        emit(32 * r + 32 + lane, acc_b);
-                    }
-                } else {
-                    for (int r = 0; 32 * r < mv.n_mel; r++)
-                        emit(32 * r + lane, M4 ? mel_band4<float2>(mv, part, r, lane) : mel_band<float2>(mv, part, r, lane));
                 }
                 __syncwarp();
             }
