@@ -77,6 +77,47 @@ def test_queued_update_and_range_variant_equal_the_waiting_call(ctx):
     ctx.release_all()
 
 
+def test_quantiser_descriptors_follow_the_store(ctx):
+    """thb_update_spec_imgs keeps the quantiser's descriptors on the device between calls and uploads them only when
+    they changed.  Walk the store through every kind of change -- same set again, a track released, a track recomputed
+    with another length (new buffers), a track added, a subset, another max_sr (image height) -- and compare every image
+    with what a fresh context produces for the same set."""
+    s = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    wav = {t: synth_pcm(70000 + 4096 * t, 48000, t, 0, 0) for t in range(4)}
+
+    def fresh(ids, lens, max_sr=48000):
+        c = thb.Context(0)
+        c.spec_batch([dict(pcm=wav[t][:lens[t]], id=t, ch=0, sr=48000) for t in ids], s)
+        rng = c.update_spec_imgs(90.0, 258, max_sr)
+        out = {t: c.img_read(t, 0) for t in ids}
+        c.close()
+        return rng, out
+
+    def same(ids, lens, max_sr=48000):
+        rng = ctx.update_spec_imgs(90.0, 258, max_sr)
+        want_rng, want = fresh(ids, lens, max_sr)
+        assert rng == want_rng
+        for t in ids:
+            got = ctx.img_read(t, 0)
+            assert got.shape == want[t].shape and np.array_equal(got, want[t]), t
+
+    ctx.release_all()
+    lens = {t: len(wav[t]) for t in wav}
+    ctx.spec_batch([dict(pcm=wav[t], id=t, ch=0, sr=48000) for t in (0, 1, 2)], s)
+    same((0, 1, 2), lens)
+    same((0, 1, 2), lens)                       # unchanged: the cached descriptors
+    ctx.release(1, 0)
+    same((0, 2), lens)                          # one fewer
+    lens[2] = 50000
+    ctx.spec_batch([dict(pcm=wav[2][:50000], id=2, ch=0, sr=48000)], s)
+    same((0, 2), lens)                          # same keys, other buffers and sizes
+    ctx.spec_batch([dict(pcm=wav[3], id=3, ch=0, sr=48000)], s)
+    same((0, 2, 3), lens)                       # one more
+    same((0, 2, 3), lens, max_sr=24000)         # lower Nyquist limit: fewer image rows
+    same((0, 2, 3), lens)
+    ctx.release_all()
+
+
 def _tile_ok(got, want):
     a = np.frombuffer(got, np.float32, offset=24).reshape(-1, 3)
     b = np.frombuffer(want, np.float32, offset=24).reshape(-1, 3)
