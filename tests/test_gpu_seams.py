@@ -118,6 +118,30 @@ def test_quantiser_descriptors_follow_the_store(ctx):
     ctx.release_all()
 
 
+def test_many_queued_small_steps_equal_one_batch(ctx):
+    """Sixty small steps queued back to back without a host round trip -- thb_spec_batch of ONE new short track (file
+    edges: the scalar kernel on its side stream next to the packed one) + thb_update_spec_imgs (which re-quantises every
+    retained track with the range so far; its small kernels are launched programmatically under each other's tails, its
+    descriptors grow by one each step) -- must leave exactly the store that ONE batch of the sixty tracks + ONE update
+    leaves: any kernel that started before what it depends on had finished would show up as a differing row."""
+    ctx.release_all()
+    s = thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Mel, 128)
+    n = 60
+    wavs = [synth_pcm(30000 + 1024 * (t % 7), 48000, t % 5, t % 2, 0) * np.float32(1.0 / (1 + t % 3)) for t in range(n)]
+    for t in range(n):
+        ctx.spec_batch([dict(pcm=wavs[t], id=t, ch=0, sr=48000)], s)
+        assert ctx.update_spec_imgs(85.0, 258, 48000, wait=False) is None
+    rng = ctx.range_get()
+    got = [(ctx.spec_read(t, 0), ctx.img_read(t, 0)) for t in range(n)]
+    ctx.release_all()
+    ctx.spec_batch([dict(pcm=wavs[t], id=t, ch=0, sr=48000) for t in range(n)], s)
+    assert ctx.update_spec_imgs(85.0, 258, 48000) == rng
+    for t in range(n):
+        assert np.array_equal(ctx.spec_read(t, 0), got[t][0], equal_nan=True), t
+        assert np.array_equal(ctx.img_read(t, 0), got[t][1]), t
+    ctx.release_all()
+
+
 def _tile_ok(got, want):
     a = np.frombuffer(got, np.float32, offset=24).reshape(-1, 3)
     b = np.frombuffer(want, np.float32, offset=24).reshape(-1, 3)

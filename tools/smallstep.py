@@ -60,14 +60,15 @@ def run(ctx, stream, name, n, setting, sr, interior, steps=300):
 
 
 def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300   # (a handful under ncu)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = thb.Context(0, stream.cuda_stream)
     print("THB_PDL=%s THB_EDGE_SIDE=%s" % (os.environ.get("THB_PDL", "(default)"), os.environ.get("THB_EDGE_SIDE", "(default)")))
     c2 = thb.SpecSetting(2048 / 48.0, 8, 1, thb.FreqScale.Mel, 128)
-    run(ctx, stream, "C2 / 8, a middle rank's shard (no file edge)", 3600 * 48000 // 8, c2, 48000, True)
-    run(ctx, stream, "C2 / 8 as a whole file (both file edges)", 3600 * 48000 // 8, c2, 48000, False)
-    run(ctx, stream, "C1 (44 s mono, linear 2048/512)", 2113529, thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear), 48000, False)
+    run(ctx, stream, "C2 / 8, a middle rank's shard (no file edge)", 3600 * 48000 // 8, c2, 48000, True, steps)
+    run(ctx, stream, "C2 / 8 as a whole file (both file edges)", 3600 * 48000 // 8, c2, 48000, False, steps)
+    run(ctx, stream, "C1 (44 s mono, linear 2048/512)", 2113529, thb.SpecSetting(2048 / 48.0, 4, 1, thb.FreqScale.Linear), 48000, False, steps)
     ctx.close()
 
 
