@@ -128,6 +128,20 @@ def test_mel_warp_schedule_is_the_filterbank(sr, n_mel):
         assert stats[3] <= 8  # (almost) bank-conflict free for the headline configurations
 
 
+@pytest.mark.parametrize("sr,n_fft,n_mel", [(16000, 1024, 0), (22050, 1024, 0), (24000, 1024, 0), (8000, 512, 0), (16000, 1024, 64),
+                                            (8000, 512, 40), (16000, 512, 0), (11025, 512, 0)])
+def test_mel_schedules_of_the_warp_kernel_are_the_filterbank(sr, n_fft, n_mel):
+    """n_fft 1024 / 512 (thb_stft_warp.cu): the bin-major schedule and the band-major one with its rounds PADDED IN PAIRS
+    (the packed kernel walks two rounds at a time) both spell calc_mel_fb weight for weight -- the replay also checks
+    that padding only ever adds zero weights and that bands past the last one have none."""
+    fb = thb.calc_mel_fb(sr, n_fft, n_mel) if n_mel else thb.calc_mel_fb_default(sr, n_fft)
+    out = np.zeros_like(fb)
+    stats = (C.c_uint32 * 4)()
+    rc = _lib.lib().thb_mel_schedule_replay(sr, n_fft, n_mel, out.ctypes.data_as(C.POINTER(C.c_float)), stats)
+    assert rc == 0 and stats[0] == 1
+    assert np.array_equal(out, fb)
+
+
 # dynamics/normalize.rs:84-110 through the C ABI's host arithmetic (no device needed)
 def test_normalize_gain_matches_reference_tests(orc):
     from thesia_b200.analysis import normalize_gain

@@ -697,6 +697,12 @@ int thb_mel_schedule_replay(uint32_t sr, uint64_t n_fft, uint32_t n_mel, float *
             }
             if (a != b4) return THB_ERR_INTERNAL;
         }
+    // rounds padded in pairs (n_fft <= 1024, mel_direct2): an even count, both rounds of a pair with one step count
+    if (n_fft <= 1024) {
+        if (mi.direct_L.size() % 2) return THB_ERR_INTERNAL;
+        for (size_t r = 0; r + 1 < mi.direct_L.size(); r += 2)
+            if (mi.direct_L[r] != mi.direct_L[r + 1]) return THB_ERR_INTERNAL;
+    }
     // the band-major schedule (n_fft <= 2048) must spell the same matrix: lane l of round r walks bins k0 + i with weight w[i][l]
     for (size_t r = 0; r < mi.direct_L.size(); r++)
         for (uint32_t l = 0; l < 32; l++) {
