@@ -275,4 +275,39 @@ __device__ __forceinline__ void mel_direct2(const MelView &mv, const V *mag, int
 }
 
 }  // namespace k2048
+
+// A file-edge frame of the warp-register kernels: stage[pos] = sample(reflect(tap0 + pos - pad_left)) * wpad[pos] for the FFT
+// positions pos = lane, lane + 32, ... < NFFT that hold a window tap, 0 for the others (numpy-style reflect, utils.rs:111-137;
+// the reference zero-pads the windowed frame, stft.rs:35-48).  Sixteen positions per lane at a time -- indices, then
+// the loads, then the products -- so that sixteen loads are in flight: one position after the other is one DRAM round
+// trip each on samples no one has touched yet (64 x ~0.5 us = the 31 - 35 us an edge launch used to take).
+template <int NFFT>
+__device__ __forceinline__ void stage_edge_frame(const TrackDesc &d, int pad_left, int win, long long tap0, const float *wpad,
+                                                 float *stage, int lane) {
+    constexpr int kPerLane = NFFT / 32, kBatch = kPerLane < 16 ? kPerLane : 16;
+    for (int b0 = 0; b0 < kPerLane; b0 += kBatch) {
+        long long idx[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; j++) {
+            const int a = (b0 + j) * 32 + lane - pad_left;
+            const int ac = a < 0 ? 0 : (a >= win ? win - 1 : a);   // a tap of the window in every case: a valid address
+            idx[j] = reflect_index(tap0 + ac, d.full_len) - d.pcm_offset;
+        }
+        float x[kBatch];
+        if (d.pcm_i16) {
+#pragma unroll
+            for (int j = 0; j < kBatch; j++)
+                x[j] = static_cast<float>(__ldg(reinterpret_cast<const short *>(d.pcm) + idx[j])) * 3.0517578125e-05f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kBatch; j++) x[j] = __ldg(d.pcm + idx[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; j++) {
+            const int pos = (b0 + j) * 32 + lane, a = pos - pad_left;
+            stage[pos] = (a >= 0 && a < win) ? x[j] * wpad[pos] : 0.0f;
+        }
+    }
+}
+
 }  // namespace thb

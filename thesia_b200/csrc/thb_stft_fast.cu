@@ -185,15 +185,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) stft2048_kernel(const PlanDev 
                 // file edges: numpy-style reflect (utils.rs:111-137), taps outside the window are zero;
                 // staged through the warp's tile so that v[] keeps compile-time indices
                 float *stage = reinterpret_cast<float *>(tile);
-                for (int pos = lane; pos < 2048; pos += 32) {
-                    const int a = pos - p.pad_left;
-                    float x = 0.0f;
-                    if (a >= 0 && a < p.win) {
-                        const long long s = reflect_index(tap0 + a, d.full_len);
-                        x = pcm_sample(d, s - d.pcm_offset) * sm.wpad[pos];
-                    }
-                    stage[pos] = x;
-                }
+                stage_edge_frame<2048>(d, p.pad_left, p.win, tap0, sm.wpad, stage, lane);
                 __syncwarp();
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1++) v[n1] = *reinterpret_cast<const float2 *>(stage + 64 * n1 + 2 * lane);

@@ -375,15 +375,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(V) == 8 ? 1 : 2)
                                           first + NFFT <= d.pcm_offset + d.slice_len;
                     if (!interior) {
                         any_edge = true;
-                        for (int pos = lane; pos < NFFT; pos += 32) {
-                            const int a = pos - p.pad_left;
-                            float x = 0.0f;
-                            if (a >= 0 && a < p.win) {
-                                const long long s = reflect_index(tap0 + a, d.full_len);
-                                x = pcm_sample(d, s - d.pcm_offset) * sm.wpad[pos];
-                            }
-                            stage[g * NFFT + pos] = x;
-                        }
+                        stage_edge_frame<NFFT>(d, p.pad_left, p.win, tap0, sm.wpad, stage + g * NFFT, lane);
                     }
                 }
                 if (any_edge) __syncwarp();
