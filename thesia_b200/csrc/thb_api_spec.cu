@@ -100,7 +100,9 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->stage_ev.push_back(ev);
     }
-    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * 4 * n + 4096);
+    // (per group: a small job may be cut into up to 4 * sm_count extra frame-range descriptors, see below)
+    int rc = arena_begin(ctx, (sizeof(thb::TrackDesc) + 256) * 4 * n +
+                                  (sizeof(thb::TrackDesc) * 4 * static_cast<size_t>(ctx->sm_count) + 512) * groups.size() + 4096);
     if (rc) return rc;
 
     // ---- device buffers; host PCM goes through stream-ordered staging ----
@@ -262,6 +264,37 @@ int thb_spec_batch(thb_ctx *ctx, const thb_track *tracks, size_t n, const thb_se
                 }
             }
             for (const thb::TrackDesc &e : edges) L.max_edge_frames = std::max(L.max_edge_frames, e.n_frames);
+            // A small job has fewer tiles than the persistent grid has CTAs (C1, one 44 s file: 43 tiles of 96 frames for 148
+            // SMs, and each of them four steps deep).  Its descriptors are cut into frame ranges of a quarter tile (one step
+            // per warp) to three quarters, so that every SM gets a work item.  Host-side only: the kernels see more, shorter
+            // descriptors, and a frame's result does not depend on which descriptor carries it (the property frame-range
+            // sharding rests on).  THB_SPLIT_SMALL=0 keeps whole channels (A/B runs).
+            {
+                static const bool split_ok = !(getenv("THB_SPLIT_SMALL") && atoi(getenv("THB_SPLIT_SMALL")) == 0);
+                const long long tf = use_pair ? thb::stft_pair_tile_frames() : thb::stft_warp_tile_frames(pd), unit = tf / 4;
+                long long tiles = 0, frames = 0;
+                for (const thb::TrackDesc &pr : pairs) {
+                    tiles += (pr.n_frames + tf - 1) / tf;
+                    frames += pr.n_frames;
+                }
+                if (split_ok && !pairs.empty() && unit >= 2 && unit % 2 == 0 && tiles < 2ll * ctx->sm_count) {
+                    const long long chunk = std::min(3 * unit, std::max(unit, frames / ctx->sm_count / unit * unit));
+                    std::vector<thb::TrackDesc> cut;
+                    for (const thb::TrackDesc &pr : pairs)
+                        for (long long off = 0; off < pr.n_frames; off += chunk) {
+                            thb::TrackDesc q = pr;
+                            q.frame_begin = pr.frame_begin + off;
+                            q.n_frames = std::min(chunk, pr.n_frames - off);
+                            q.out = pr.out + off * pd.n_bins;
+                            cut.push_back(q);
+                        }
+                    if (cut.size() <= 4 * static_cast<size_t>(ctx->sm_count) + pairs.size()) {   // (what the arena was sized for)
+                        pairs.swap(cut);
+                        L.max_pair_frames = 0;
+                        for (const thb::TrackDesc &pr : pairs) L.max_pair_frames = std::max(L.max_pair_frames, pr.n_frames);
+                    }
+                }
+            }
             L.n_pair = static_cast<int>(pairs.size());
             L.n_edge = static_cast<int>(edges.size());
             if (L.n_pair) {
