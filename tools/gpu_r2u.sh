@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 {
 nvidia-smi -L | head -1
 echo "== pytest gpu (all)"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-for v in 0 1; do
+for v in 1; do
   echo "== THB_SPLIT_SMALL=$v"
   THB_SPLIT_SMALL=$v timeout 300 python tools/smallstep.py 2>&1 | tail -3
   THB_SPLIT_SMALL=$v timeout 300 python tools/configs_bench.py --only C1 --reps 20 2>&1 | grep -E '^\{' | python -c "
