@@ -598,7 +598,7 @@ def run_b200(args) -> None:
                           "profiles/roofline_traffic.json (captured under ncu in a separate run, not measured by this one)",
         # what ncu says binds the kernel (profiles/): FP32 pipe + issue slots + shared-memory wavefronts, not HBM --
         # `bound`/`frac` above keep the contract's HBM figure, these two give the roof that actually limits it
-        "limiter_per_ncu": "fp32 pipe / issue slots (HBM traffic is 1.006x algorithmic and far below the roof)",
+        "limiter_per_ncu": "fp32 pipe / issue slots (HBM traffic is 1.004 - 1.006x algorithmic and far below the roof)",
         "frac_fp32": fp32_tflops / peak_fp32, "peak_fp32_tflops": peak_fp32, "sm_mhz_for_fp32_peak": sm_mhz,
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
         "achieved_fp32_tflops": fp32_tflops,
