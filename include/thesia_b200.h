@@ -183,7 +183,8 @@ int thb_plans_retain(thb_ctx *ctx, const thb_setting *setting, const uint32_t *s
 
 /* ---- TrackManager::update_spec_imgs (mod.rs:168-230) ----------------------------------------
  * thb_minmax_global: global (min, max) over every retained spectrogram (mod.rs:169-178), reduced
- * across ranks with one ncclAllReduce(max) of {max, -min} when a communicator is attached, then
+ * across ranks with one exchange of {max, -min} when a communicator is attached (one kernel over the peers'
+ * NVLink-mapped memory on one box, see thb_comm_init; ncclAllReduce(max) otherwise), then
  * max <- min(max, 0); min <- max(min, max - dB_range) (mod.rs:179-180). */
 int thb_minmax_global(thb_ctx *ctx, float dB_range, float *min_dB, float *max_dB);
 /* convert_spectrogram_to_img (visualize/drawing.rs:4-33) for one retained spectrogram:
